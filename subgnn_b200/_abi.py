@@ -1,0 +1,87 @@
+"""ctypes binding of the C ABI declared in include/subgnn_b200.h.
+
+There is NO fallback: importing this module raises if libsubgnn_b200.so has not been built
+(``python -c 'import __graft_entry__ as g; g.build()'`` or ``./build.sh``), and every call
+raises ``SubgnnError`` on a non-zero status.
+"""
+import ctypes as C
+import os
+from pathlib import Path
+
+import torch
+
+_LIB_PATH = Path(__file__).resolve().parent / 'libsubgnn_b200.so'
+
+
+class SubgnnError(RuntimeError):
+    pass
+
+
+if not _LIB_PATH.exists():
+    raise ImportError('libsubgnn_b200.so is missing at %s — build it with ./build.sh (no CPU fallback exists)' % _LIB_PATH)
+
+lib = C.CDLL(str(_LIB_PATH))
+
+P, I, F, U64, U32, LL = C.c_void_p, C.c_int, C.c_float, C.c_ulonglong, C.c_uint, C.c_longlong
+
+# name -> argtypes (every function returns int status unless listed in _OTHER)
+SIGNATURES = {
+    'subgnn_walk_full': [P, P, I, I, I, F, U64, P, P],
+    'subgnn_walk_patch': [P, P, I, P, P, I, I, I, I, F, I, U64, P, P],
+    'subgnn_sample_rows': [P, P, I, I, I, I, U64, U32, I, P, P],
+    'subgnn_border_khop_bitmap': [P, P, I, P, P, I, I, P, P, P],
+    'subgnn_border_khop_expand': [P, I, I, P, P, P],
+    'subgnn_sp_min_dense': [P, I, LL, P, P, I, P, P],
+    'subgnn_sp_min_gather': [P, LL, P, P, I, P, P, I, P, P],
+    'subgnn_degree_seq': [P, P, P, I, I, I, P, P, P],
+    'subgnn_dtw_batch': [P, P, I, I, P, P, I, I, I, I, I, P, P],
+}
+_OTHER = {
+    'subgnn_last_error': ([], C.c_char_p),
+    'subgnn_abi_version': ([], I),
+    'subgnn_device_sm_count': ([], I),
+}
+
+
+def _bind():
+    for name, args in SIGNATURES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch: fail loudly
+        fn.argtypes = args
+        fn.restype = I
+    for name, (args, res) in _OTHER.items():
+        fn = getattr(lib, name)
+        fn.argtypes = args
+        fn.restype = res
+
+
+def register(name, args):
+    """Late registration used by modules that add entry points (keeps one table for the export test)."""
+    SIGNATURES[name] = args
+    fn = getattr(lib, name)
+    fn.argtypes = args
+    fn.restype = I
+
+
+_bind()
+
+
+def ptr(t):
+    """Device pointer of a CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    assert t.is_cuda and t.is_contiguous(), 'C ABI takes contiguous device tensors'
+    return t.data_ptr()
+
+
+def stream_ptr():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def call(name, *args):
+    rc = getattr(lib, name)(*args)
+    if rc != 0:
+        raise SubgnnError('%s failed (%d): %s' % (name, rc, lib.subgnn_last_error().decode()))
+
+
+def exported_symbols():
+    return list(SIGNATURES) + list(_OTHER)

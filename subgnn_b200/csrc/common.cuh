@@ -1,0 +1,108 @@
+// Common device helpers for libsubgnn_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#define SUBGNN_OK 0
+#define SUBGNN_ERR_ARG -1
+#define SUBGNN_ERR_CUDA -2
+
+void subgnn_set_error(const char* fmt, ...);
+int subgnn_check_launch(const char* what);
+
+#define SG_REQUIRE(cond, msg)                                  \
+  do {                                                         \
+    if (!(cond)) {                                             \
+      subgnn_set_error("%s: %s", __func__, msg);               \
+      return SUBGNN_ERR_ARG;                                   \
+    }                                                          \
+  } while (0)
+
+static inline int sg_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// grid sizing: persistent-style grid, a multiple of the SM count (148 on B200)
+int subgnn_sm_count();
+static inline int sg_grid_for(long long work_items, int per_block, int max_blocks_per_sm = 8) {
+  long long need = (work_items + per_block - 1) / per_block;
+  long long cap = (long long)subgnn_sm_count() * max_blocks_per_sm;
+  if (need < 1) need = 1;
+  return (int)(need < cap ? need : cap);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 (counter-based); identical construction in oracle/rng.py
+struct Philox4 { uint32_t x, y, z, w; };
+
+__host__ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                          uint32_t k0, uint32_t k1) {
+  const uint32_t M0 = 0xD2511F53u, M1 = 0xCD9E8D57u, W0 = 0x9E3779B9u, W1 = 0xBB67AE85u;
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    uint64_t p0 = (uint64_t)M0 * c0;
+    uint64_t p1 = (uint64_t)M1 * c2;
+    uint32_t hi0 = (uint32_t)(p0 >> 32), lo0 = (uint32_t)p0;
+    uint32_t hi1 = (uint32_t)(p1 >> 32), lo1 = (uint32_t)p1;
+    uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+    c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+    k0 += W0; k1 += W1;
+  }
+  return Philox4{c0, c1, c2, c3};
+}
+
+#define SG_TAG_WALK 0x57414C4Bu
+#define SG_TAG_NEIGH 0x4E454947u
+#define SG_TAG_POS 0x504F5331u
+#define SG_TAG_STRUC 0x53545231u
+#define SG_TAG_DROP 0x44524F50u
+
+__host__ __device__ __forceinline__ Philox4 sg_draw(uint64_t seed, uint64_t item, uint32_t step, uint32_t tag) {
+  return philox4x32_10((uint32_t)item, (uint32_t)(item >> 32), step, tag, (uint32_t)seed, (uint32_t)(seed >> 32));
+}
+__host__ __device__ __forceinline__ uint32_t sg_index(uint32_t r, uint32_t n) { return (uint32_t)(((uint64_t)r * n) >> 32); }
+__host__ __device__ __forceinline__ float sg_unit(uint32_t r) { return (float)(r >> 8) * (1.0f / 16777216.0f); }
+
+// keep-mask for dropout: element idx of stream (seed, salt); returns scale (0 or 1/(1-p))
+__device__ __forceinline__ float sg_dropout_scale(uint64_t seed, uint32_t salt, uint64_t idx, float p) {
+  if (p <= 0.f) return 1.f;
+  Philox4 r = sg_draw(seed, idx >> 2, salt, SG_TAG_DROP);
+  uint32_t w = (idx & 3) == 0 ? r.x : (idx & 3) == 1 ? r.y : (idx & 3) == 2 ? r.z : r.w;
+  return sg_unit(w) >= p ? 1.f / (1.f - p) : 0.f;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ int warp_sum_i(int v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// lower_bound membership test in a sorted int list
+__device__ __forceinline__ bool sorted_contains(const int* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int v = a[mid];
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  return lo < n && a[lo] == key;
+}
+__device__ __forceinline__ int sorted_find(const int* __restrict__ a, int n, int key) {
+  int lo = 0, hi = n;
+  while (lo < hi) {
+    int mid = (lo + hi) >> 1;
+    int v = a[mid];
+    if (v < key) lo = mid + 1; else hi = mid;
+  }
+  return (lo < n && a[lo] == key) ? lo : -1;
+}

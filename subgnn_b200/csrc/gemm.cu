@@ -1,0 +1,185 @@
+// fp32 tiled GEMMs for the dense parts of the path: MPN projection, readout MLP, LSTM input
+// projections / weight gradients, with the row gathers / scatters of the embedding table fused into the
+// operand loads and the epilogue.
+//
+// Replaces the cuBLAS/ATen calls behind (reference):
+//   subgraph_mpn.py:239        F.relu(self.linear(cat[x, aggr]))           -> subgnn_linear_fwd (+ bwd)
+//   SubGNN.py:306-310          lin / lin2 / lin3                            -> subgnn_linear_fwd (+ bwd)
+//   SubGNN.py:73-78 nn.LSTM    x_t W_ih^T (all t at once), dW_ih, dW_hh, dX -> subgnn_linear_fwd/bwd_input/bwd_weight
+//   anchor_patch_samplers.py:409 node_matrix(ids) feeding the LSTM          -> row gather fused into the A-operand load
+//   embedding_dense_backward                                                -> atomic row scatter fused into the epilogue
+//
+// fp32 FFMA on purpose (round 1): the stated parity tolerance for the deterministic stages is fp32
+// (rtol 1e-4); tf32/bf16 tcgen05 tiles would not hold it for the gradient GEMMs.
+#include "common.cuh"
+#include "../../include/subgnn_b200.h"
+
+#define BM 64
+#define BN 64
+#define BK 16
+#define TM 4
+#define TN 4
+
+// Generic tile engine.  a(m, k) / b(k, n) fetch operand elements (bounds already checked by the caller),
+// epi(m, n, acc) consumes one output element.  A_KC / B_KC: operand is contiguous along k (choose the
+// thread->element map so that global loads coalesce).
+template <bool A_KC, bool B_KC, class AF, class BF, class EF>
+__device__ __forceinline__ void gemm_tile(int M, int N, int k0, int k1, AF a, BF b, EF epi) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Bs[BK][BN + 4];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  float acc[TM][TN];
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
+  for (int kb = k0; kb < k1; kb += BK) {
+#pragma unroll
+    for (int p = 0; p < (BM * BK) / 256; ++p) {
+      const int e = p * 256 + tid;
+      int mm, kk;
+      if (A_KC) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
+      const int m = m0 + mm, k = kb + kk;
+      As[kk][mm] = (m < M && k < k1) ? a(m, k) : 0.f;
+    }
+#pragma unroll
+    for (int p = 0; p < (BN * BK) / 256; ++p) {
+      const int e = p * 256 + tid;
+      int nn, kk;
+      if (B_KC) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
+      const int n = n0 + nn, k = kb + kk;
+      Bs[kk][nn] = (n < N && k < k1) ? b(k, n) : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float av[TM], bv[TN];
+#pragma unroll
+      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
+#pragma unroll
+      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
+#pragma unroll
+      for (int i = 0; i < TM; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < TM; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) {
+      const int m = m0 + ty * TM + i, n = n0 + tx * TN + j;
+      if (m < M && n < N) epi(m, n, acc[i][j]);
+    }
+}
+
+// y[m][n] = act( sum_k X[row(m)][k] * W[n][k] + bias[n] )
+__global__ void __launch_bounds__(256)
+linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
+                  const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
+  gemm_tile<true, true>(
+      M, N, 0, K,
+      [&](int m, int k) { const long long r = ids ? (long long)ids[m] : m; return __ldg(x + r * ldx + k); },
+      [&](int k, int n) { return __ldg(w + (long long)n * ldw + k); },
+      [&](int m, int n, float v) {
+        if (bias) v += bias[n];
+        if (relu) v = fmaxf(v, 0.f);
+        y[(long long)m * ldy + n] = v;
+      });
+}
+
+// dx[row(m)][k] (+)= sum_n dy[m][n] * W[n][k]     (scatter_ids: atomic row scatter, PAD row 0 skipped)
+__global__ void __launch_bounds__(256)
+linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w, int ldw, float* __restrict__ dx, int lddx,
+                        const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate) {
+  // output tile is (M x K); reduction over N
+  gemm_tile<true, false>(
+      M, K, 0, N,
+      [&](int m, int n) { return __ldg(dy + (long long)m * ldy + n); },
+      [&](int n, int k) { return __ldg(w + (long long)n * ldw + k); },
+      [&](int m, int k, float v) {
+        if (scatter_ids) {
+          const int r = scatter_ids[m];
+          if (r != 0) atomicAdd(dx + (long long)r * lddx + k, v);
+        } else if (accumulate) {
+          dx[(long long)m * lddx + k] += v;
+        } else {
+          dx[(long long)m * lddx + k] = v;
+        }
+      });
+}
+
+// dW[n][k] += sum_m dy[m][n] * X[row(m)][k]   (split over m across blockIdx.z, atomic accumulate)
+__global__ void __launch_bounds__(256)
+linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
+                         float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk) {
+  const int m_beg = blockIdx.z * m_chunk;
+  const int m_end = min(M, m_beg + m_chunk);
+  if (m_beg >= m_end) return;
+  gemm_tile<false, false>(
+      N, K, m_beg, m_end,
+      [&](int n, int m) { return __ldg(dy + (long long)m * ldy + n); },
+      [&](int m, int k) { const long long r = ids ? (long long)ids[m] : m; return __ldg(x + r * ldx + k); },
+      [&](int n, int k, float v) { atomicAdd(dw + (long long)n * lddw + k, v); });
+}
+
+// db[n] += sum_m dy[m][n]
+__global__ void colsum_kernel(const float* __restrict__ dy, int ldy, float* __restrict__ db, int M, int N, int m_chunk) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= N) return;
+  const int m_beg = blockIdx.y * m_chunk, m_end = min(M, m_beg + m_chunk);
+  float s = 0.f;
+  for (int m = m_beg; m < m_end; ++m) s += dy[(long long)m * ldy + n];
+  if (m_beg < m_end) atomicAdd(db + n, s);
+}
+
+extern "C" {
+
+int subgnn_linear_fwd(const float* x, int ldx, const int* gather_ids, const float* w, int ldw, const float* bias, float* y, int ldy,
+                      int M, int N, int K, int relu, void* stream) {
+  SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
+  if (M == 0) return SUBGNN_OK;
+  dim3 grid(sg_div_up(N, BN), sg_div_up(M, BM));
+  linear_fwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+  return subgnn_check_launch("linear_fwd_kernel");
+}
+
+int subgnn_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx, const int* scatter_ids, int M, int N,
+                            int K, int accumulate, void* stream) {
+  SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
+  if (M == 0) return SUBGNN_OK;
+  dim3 grid(sg_div_up(K, BN), sg_div_up(M, BM));
+  linear_bwd_input_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate);
+  return subgnn_check_launch("linear_bwd_input_kernel");
+}
+
+int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
+                             int M, int N, int K, void* stream) {
+  SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
+  if (M == 0) return SUBGNN_OK;
+  // split the reduction so that the grid covers the machine: tiles * splits ~ 2 waves
+  const int tiles = sg_div_up(K, BN) * sg_div_up(N, BM);
+  int splits = (2 * subgnn_sm_count() + tiles - 1) / tiles;
+  const int max_splits = sg_div_up(M, 4 * BK);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int m_chunk = sg_div_up(sg_div_up(M, splits), BK) * BK;
+  splits = sg_div_up(M, m_chunk);
+  dim3 grid(sg_div_up(K, BN), sg_div_up(N, BM), splits);
+  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+  int rc = subgnn_check_launch("linear_bwd_weight_kernel");
+  if (rc) return rc;
+  if (db) {
+    const int cs = sg_div_up(M, 64) > 64 ? 64 : sg_div_up(M, 64);
+    const int chunk = sg_div_up(M, cs);
+    dim3 g2(sg_div_up(N, 128), sg_div_up(M, chunk));
+    colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, chunk);
+    rc = subgnn_check_launch("colsum_kernel");
+  }
+  return rc;
+}
+
+}  // extern "C"
