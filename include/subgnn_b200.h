@@ -88,6 +88,125 @@ int subgnn_degree_seq(const int* rowptr, const int* col, const int* rows, int n_
 int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
                      int max_len_a, int max_len_b, int mode, float* out, void* stream);
 
+
+/* ---- dense building blocks (gemm.cu) ------------------------------------------------------------- */
+
+/* y[m][n] = act(sum_k X[row(m)][k] W[n][k] + bias[n]); row(m) = gather_ids ? gather_ids[m] : m.
+ * Replaces nn.Linear forward at subgraph_mpn.py:239, SubGNN.py:74,306-310 and the LSTM input projections
+ * (SubGNN.py:73); with gather_ids it also replaces the embedding lookup anchor_patch_samplers.py:409. */
+int subgnn_linear_fwd(const float* x, int ldx, const int* gather_ids, const float* w, int ldw, const float* bias, float* y, int ldy,
+                      int M, int N, int K, int relu, void* stream);
+/* dx[row(m)][k] (+)= sum_n dy[m][n] W[n][k]; with scatter_ids the rows are atomically added into a table
+ * gradient (embedding_dense_backward), id 0 (PAD) skipped. */
+int subgnn_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx, const int* scatter_ids, int M, int N,
+                            int K, int accumulate, void* stream);
+/* dW[n][k] += sum_m dy[m][n] X[row(m)][k];  db[n] += sum_m dy[m][n] (db may be NULL).  m_dev (may be NULL): device
+ * int holding the number of valid rows (<= M) when it is only known on the device. */
+int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
+                             int M, int N, int K, const int* m_dev, void* stream);
+
+/* ---- walk-encoder LSTM (lstm.cu): SubGNN.py:60-88, anchor_patch_samplers.py:413-433 ------------------ */
+int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
+int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
+                          void* stream);
+int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
+                          int steps_fwd, int steps_rev, void* stream);
+int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
+int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);
+int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream);
+int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream);
+int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
+                   void* stream);
+int subgnn_colsum(const float* dy, int ldy, float* db, int M, int N, const int* m_dev, void* stream);
+int subgnn_model_desc_size(void);
+
+/* ---- fused per-step model path (model.cu) ------------------------------------------------------------
+ * One descriptor names every device buffer of a training / inference step.  Rows = the valid connected
+ * components of the batch's subgraphs (ragged; padded components never influence logits or gradients
+ * because SubGNN.py:303 masks them in the readout).  Z column layout == the reference's concat order
+ * (SubGNN.py:271-295): [init D | per layer: N_in D, N_out D | P_in A_pi, P_out A_pb | S_in A_s, S_out A_s].
+ * MPN parameter block of (channel, layer l, side s) at mpn_params[ch] + (2 l + s) * (2 D D + 2 D + 1) floats:
+ * linear.weight (D x 2D) | linear.bias (D) | linear_position.weight (D) | linear_position.bias (1). */
+typedef struct subgnn_model_desc {
+  /* split tables (built once) */
+  const int* sub_ccptr;      /* [n_sub+1] first component row of each subgraph */
+  const int* sub_maxlen;     /* [n_sub]   largest component of each subgraph */
+  const int* cc_nodeptr;     /* [n_cc+1] */
+  const int* cc_nodes;       /* ids of all components, concatenated */
+  const int* n_ids[2];       /* [L][n_cc][A_n*]  neighbourhood anchors (internal, border), 0 = PAD */
+  const float* n_sim[2];     /* [L][n_cc][A_n*]  resolved similarity of (component, anchor) */
+  const int* p_int_ids;      /* [L][n_sub][A_pi] */
+  const int* p_bor_ids;      /* [L][A_pb] */
+  const float* p_sim[2];     /* [L][n_cc][A_pi | A_pb] */
+  const float* s_sim[2];     /* [L][n_cc][A_s] */
+  const int* labels;         /* [n_sub] class id (multiclass) */
+  const float* labels_multi; /* [n_sub][n_classes] 0/1 (multilabel) */
+  /* parameters / gradients */
+  const float* E;            /* [(N+1)][D] node embeddings, row 0 = 0 */
+  float* dE;
+  const float* mpn_params[3];   /* N, P, S */
+  float* mpn_grads[3];
+  const float* cc_tab[2];    /* trainable_cc: N_I, N_B tables [n_sub][C_pad][D]; else NULL */
+  float* cc_tab_grad[2];
+  const float* lin_w[3];     /* lin (h1 x hid), lin2 (h2 x h1), lin3 (K x h2) */
+  const float* lin_b[3];
+  float* lin_gw[3];          /* gradients of lin / lin2 / lin3 (may be NULL for inference) */
+  float* lin_gb[3];
+  const float* emb_s;        /* [2][L][A_s][D] structure anchor embeddings (LSTM output) */
+  float* d_emb_s;
+  /* per-step scratch */
+  const int* batch_idx;      /* [B] subgraph indices of this step */
+  const int* step_dev;       /* [1] optimizer step counter on the device (dropout salt; graph-replay safe) */
+  int* b_rowptr;             /* [B+1] */
+  int* meta;                 /* [0] = R (rows in the batch), [1] = max component length in the batch */
+  float* n_wt;               /* [L][2][2D][D] transposed MPN weights (N channel) */
+  float* lin_wt[3];          /* transposed MLP weights */
+  float* q_pi; float* q_pb; float* q_s;          /* [L][B][A_pi], [L][A_pb], [L][2][A_s] */
+  float* dq_pi; float* dq_pb; float* dq_s;
+  float* X0;                 /* [R_cap][D] pooled component embeddings */
+  float* Nh;                 /* [L+1][2][R_cap][D] N-channel component embeddings per layer */
+  float* Nagg;               /* [L][2][R_cap][D] aggregated messages */
+  float* Ndpre;              /* [L][2][R_cap][D] d(pre-activation) */
+  float* Z;                  /* [B][hid] subgraph embeddings */
+  float* H1; float* H2;      /* [B][h1], [B][h2] post-relu post-dropout */
+  float* logits;             /* [B][K] */
+  float* loss_b;             /* [B] per-sample loss terms (already divided by B [and K]) */
+  float* dlogits; float* dH2; float* dH1; float* dZ;
+  unsigned long long seed;   /* dropout key */
+  int n_sub, n_cc, n_nodes;
+  int D, L, hid, h1, h2, n_classes;
+  int use_n, use_p, use_s;
+  int A_ni, A_nb, A_pi, A_pb, A_s;
+  int pool_max, trainable_cc, C_pad, multilabel, training, use_proj;
+  int B, R_cap;
+  unsigned step;             /* dropout salt (optimizer step counter) */
+  float lin_dropout;
+} subgnn_model_desc;
+
+/* batch bookkeeping + per-step weight transposes + q = w_p . x_anchor for every shared anchor list */
+int subgnn_model_prep(const subgnn_model_desc* d, void* stream);
+int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream);
+/* SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers subgraph_mpn.py:133-241,
+ * masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training also the
+ * per-sample MLP backward (dZ). */
+int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream);
+/* per-sample MLP backward from externally supplied dlogits (autograd entry) */
+int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream);
+/* backward of all rows: N-channel chains, property-aware outputs, pooling; scatters into dE / dq / Ndpre */
+int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream);
+int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);
+/* weight gradients of the N-channel MPN projections and the MLP */
+int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream);
+
+/* ---- optimizer (optim.cu): SubGNN.py:1156-1164 Adam + Lightning's clip_grad_norm_ ---------------------- */
+int subgnn_fill_zero(float* p, long long n, void* stream);
+int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq /* [1], accumulated */, void* stream);
+int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                     const int* step_dev /* [1] step count t >= 1 */, const float* sumsq_dev, float clip_norm, float grad_scale,
+                     void* stream);
+int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
+int subgnn_inc_step(int* step_dev, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -35,11 +35,36 @@ SIGNATURES = {
     'subgnn_sp_min_gather': [P, LL, P, P, I, P, P, I, P, P],
     'subgnn_degree_seq': [P, P, P, I, I, I, P, P, P],
     'subgnn_dtw_batch': [P, P, I, I, P, P, I, I, I, I, I, P, P],
+    'subgnn_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],
+    'subgnn_linear_bwd_input': [P, I, P, I, P, I, P, I, I, I, I, P],
+    'subgnn_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P, P],
+    'subgnn_colsum': [P, I, P, I, I, P, P],
+    'subgnn_lstm_prep': [P, P, P, P, P, I, P],
+    'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
+    'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, P],
+    'subgnn_lstm_agg_fwd': [P, P, I, I, I, I, P],
+    'subgnn_lstm_agg_bwd': [P, P, I, I, I, I, P],
+    'subgnn_group_sum': [P, P, I, I, I, P],
+    'subgnn_group_bcast': [P, P, I, I, I, P],
+    'subgnn_dropout': [P, P, LL, F, U64, U32, P, P],
+    'subgnn_model_prep': [P, P],
+    'subgnn_model_q_fwd': [P, P],
+    'subgnn_model_sub_fwd': [P, P],
+    'subgnn_model_mlp_bwd': [P, P],
+    'subgnn_model_sub_bwd': [P, P],
+    'subgnn_model_q_bwd': [P, P],
+    'subgnn_model_wgrad': [P, P],
+    'subgnn_fill_zero': [P, LL, P],
+    'subgnn_grad_sumsq': [P, LL, P, P],
+    'subgnn_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],
+    'subgnn_sum_to_scalar': [P, I, P, P],
+    'subgnn_inc_step': [P, P],
 }
 _OTHER = {
     'subgnn_last_error': ([], C.c_char_p),
     'subgnn_abi_version': ([], I),
     'subgnn_device_sm_count': ([], I),
+    'subgnn_model_desc_size': ([], I),
 }
 
 
@@ -81,6 +106,39 @@ def call(name, *args):
     rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SubgnnError('%s failed (%d): %s' % (name, rc, lib.subgnn_last_error().decode()))
+
+
+def _parse_desc_fields():
+    """Builds the ctypes mirror of ``subgnn_model_desc`` from include/subgnn_b200.h so the two cannot drift."""
+    import re
+    hdr = (Path(__file__).resolve().parent.parent / 'include' / 'subgnn_b200.h').read_text()
+    body = hdr.split('typedef struct subgnn_model_desc {')[1].split('} subgnn_model_desc;')[0]
+    body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
+    fields = []
+    for stmt in body.split(';'):
+        stmt = ' '.join(stmt.split())
+        if not stmt:
+            continue
+        m = re.match(r'^(const )?(unsigned long long|unsigned|int|float)( ?\*)? ?(.*)$', stmt)
+        assert m, stmt
+        base, is_ptr, names = m.group(2), bool(m.group(3)), m.group(4)
+        ctype = P if is_ptr else {'unsigned long long': U64, 'unsigned': U32, 'int': I, 'float': F}[base]
+        for name in names.split(','):
+            name = name.strip()
+            arr = re.match(r'^(\w+)\[(\d+)\]$', name)
+            if arr:
+                fields.append((arr.group(1), ctype * int(arr.group(2))))
+            else:
+                fields.append((name, ctype))
+    return fields
+
+
+class ModelDesc(C.Structure):
+    _fields_ = _parse_desc_fields()
+
+
+assert C.sizeof(ModelDesc) == lib.subgnn_model_desc_size(), \
+    'subgnn_model_desc layout mismatch: ctypes %d vs C %d' % (C.sizeof(ModelDesc), lib.subgnn_model_desc_size())
 
 
 def exported_symbols():

@@ -115,7 +115,8 @@ linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __re
 // dW[n][k] += sum_m dy[m][n] * X[row(m)][k]   (split over m across blockIdx.z, atomic accumulate)
 __global__ void __launch_bounds__(256)
 linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
-                         float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk) {
+                         float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk, const int* __restrict__ m_dev) {
+  if (m_dev) M = min(M, *m_dev);
   const int m_beg = blockIdx.z * m_chunk;
   const int m_end = min(M, m_beg + m_chunk);
   if (m_beg >= m_end) return;
@@ -127,7 +128,9 @@ linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __r
 }
 
 // db[n] += sum_m dy[m][n]
-__global__ void colsum_kernel(const float* __restrict__ dy, int ldy, float* __restrict__ db, int M, int N, int m_chunk) {
+__global__ void colsum_kernel(const float* __restrict__ dy, int ldy, float* __restrict__ db, int M, int N, int m_chunk,
+                              const int* __restrict__ m_dev) {
+  if (m_dev) M = min(M, *m_dev);
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= N) return;
   const int m_beg = blockIdx.y * m_chunk, m_end = min(M, m_beg + m_chunk);
@@ -157,7 +160,7 @@ int subgnn_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, f
 }
 
 int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
-                             int M, int N, int K, void* stream) {
+                             int M, int N, int K, const int* m_dev, void* stream) {
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   if (M == 0) return SUBGNN_OK;
   // split the reduction so that the grid covers the machine: tiles * splits ~ 2 waves
@@ -169,17 +172,26 @@ int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, 
   const int m_chunk = sg_div_up(sg_div_up(M, splits), BK) * BK;
   splits = sg_div_up(M, m_chunk);
   dim3 grid(sg_div_up(K, BN), sg_div_up(N, BM), splits);
-  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk, m_dev);
   int rc = subgnn_check_launch("linear_bwd_weight_kernel");
   if (rc) return rc;
   if (db) {
     const int cs = sg_div_up(M, 64) > 64 ? 64 : sg_div_up(M, 64);
     const int chunk = sg_div_up(M, cs);
     dim3 g2(sg_div_up(N, 128), sg_div_up(M, chunk));
-    colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, chunk);
+    colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, chunk, m_dev);
     rc = subgnn_check_launch("colsum_kernel");
   }
   return rc;
+}
+
+int subgnn_colsum(const float* dy, int ldy, float* db, int M, int N, const int* m_dev, void* stream) {
+  if (M == 0) return SUBGNN_OK;
+  const int cs = sg_div_up(M, 64) > 64 ? 64 : sg_div_up(M, 64);
+  const int chunk = sg_div_up(M, cs);
+  dim3 g2(sg_div_up(N, 128), sg_div_up(M, chunk));
+  colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, chunk, m_dev);
+  return subgnn_check_launch("colsum_kernel");
 }
 
 }  // extern "C"

@@ -1,0 +1,307 @@
+// Walk-encoder LSTM (bidirectional, 1-2 layers) — recurrent forward / BPTT kernels and the aggregation head.
+//
+// Replaces the cuDNN/ATen RNN behind (reference):
+//   SubGNN.py:60-88                     class LSTM (nn.LSTM bidirectional + 'last' | 'sum' aggregator + Linear(2h -> D))
+//   anchor_patch_samplers.py:413-433    aggregate_structure_anchor_patch (embed walks -> LSTM -> sum over the W walks)
+//
+// Data layout (all fp32, row-major):
+//   G   [n_seq][T][2][4H]   gate pre-activations x_t W_ih^T + b_ih + b_hh of both directions, written by the input
+//                           projection GEMM (gemm.cu), overwritten in place by the recurrent kernel with the gate
+//                           activations (i, f, g, o) and, in the backward pass, by d(pre-activation).
+//   OUT [n_seq*T + 1][2H]   h_t of both directions ([:, :H] forward, [:, H:] reverse) == the next layer's input
+//                           == nn.LSTM's output; the extra last row stays zero (h_{-1} for the dW_hh gather).
+//   CS  [n_seq][T][2][H]    cell states.
+// One CTA owns S_TILE sequences of one direction for the whole recurrence: h and c live in shared memory,
+// thread j owns gate column j (coalesced reads of the transposed W_hh, L1/L2 resident), the four gates of a
+// hidden unit are exchanged through shared memory.  PAD steps are fed as zero vectors (no packing), exactly like
+// the reference.
+#include "common.cuh"
+#include "../../include/subgnn_b200.h"
+
+#define S_TILE 8
+
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
+
+// grid (ceil(n_seq / S_TILE), 2 directions); block = 4H rounded up to 32
+__global__ void __launch_bounds__(1024)
+lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2][H][4H]*/, float* __restrict__ OUT,
+                      float* __restrict__ CS, int n_seq, int T, int H, int steps_fwd, int steps_rev) {
+  extern __shared__ float sm[];
+  float* hbuf = sm;                       // [S_TILE][H]
+  float* cbuf = hbuf + S_TILE * H;        // [S_TILE][H]
+  float* gates = cbuf + S_TILE * H;       // [S_TILE][4H]
+  const int dir = blockIdx.y;
+  const int seq0 = blockIdx.x * S_TILE;
+  const int ns = min(S_TILE, n_seq - seq0);
+  const int j = threadIdx.x;
+  const int H4 = 4 * H;
+  const float* wt = WhhT + (size_t)dir * H * H4;
+  const int n_steps = dir == 0 ? steps_fwd : steps_rev;
+  for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { hbuf[e] = 0.f; cbuf[e] = 0.f; }
+  __syncthreads();
+  for (int st = 0; st < n_steps; ++st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    if (j < H4) {
+      float acc[S_TILE];
+#pragma unroll
+      for (int s = 0; s < S_TILE; ++s)
+        acc[s] = s < ns ? G[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + j] : 0.f;
+      if ((H & 3) == 0) {
+        for (int k = 0; k < H; k += 4) {
+          const float w0 = __ldg(wt + (size_t)k * H4 + j), w1 = __ldg(wt + (size_t)(k + 1) * H4 + j);
+          const float w2 = __ldg(wt + (size_t)(k + 2) * H4 + j), w3 = __ldg(wt + (size_t)(k + 3) * H4 + j);
+#pragma unroll
+          for (int s = 0; s < S_TILE; ++s) {
+            const float4 h4 = *reinterpret_cast<const float4*>(hbuf + s * H + k);
+            acc[s] = fmaf(h4.x, w0, acc[s]); acc[s] = fmaf(h4.y, w1, acc[s]);
+            acc[s] = fmaf(h4.z, w2, acc[s]); acc[s] = fmaf(h4.w, w3, acc[s]);
+          }
+        }
+      } else {
+        for (int k = 0; k < H; ++k) {
+          const float w = __ldg(wt + (size_t)k * H4 + j);
+#pragma unroll
+          for (int s = 0; s < S_TILE; ++s) acc[s] = fmaf(hbuf[s * H + k], w, acc[s]);
+        }
+      }
+      const bool is_tanh = (j / H) == 2;
+#pragma unroll
+      for (int s = 0; s < S_TILE; ++s) {
+        const float a = is_tanh ? tanhf(acc[s]) : sigmoidf_(acc[s]);
+        gates[s * H4 + j] = a;
+        if (s < ns) G[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + j] = a;
+      }
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < ns * H; e += blockDim.x) {
+      const int s = e / H, u = e % H;
+      const float ig = gates[s * H4 + u], fg = gates[s * H4 + H + u], gg = gates[s * H4 + 2 * H + u], og = gates[s * H4 + 3 * H + u];
+      const float c = fmaf(fg, cbuf[e], ig * gg);
+      const float h = og * tanhf(c);
+      cbuf[e] = c;
+      hbuf[e] = h;
+      CS[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H + u] = c;
+      OUT[((size_t)(seq0 + s) * T + t) * 2 * H + dir * H + u] = h;
+    }
+    __syncthreads();
+  }
+  // steps not taken (top-layer reverse direction with the 'last' aggregator): outputs are never read
+}
+
+// BPTT.  dOUT [n_seq*T][2H] gradient w.r.t. this layer's outputs; G holds gate activations on entry and
+// d(pre-activation) on exit (zero for steps that were not taken).  Whh [2][4H][H] native layout.
+__global__ void __launch_bounds__(1024)
+lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT,
+                      const float* __restrict__ CS, const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd,
+                      int steps_rev) {
+  extern __shared__ float sm[];
+  const int H4 = 4 * H;
+  float* dgate = sm;                        // [S_TILE][4H]
+  float* dh_rec = dgate + S_TILE * H4;      // [S_TILE][H]
+  float* dc_rec = dh_rec + S_TILE * H;      // [S_TILE][H]
+  float* red = dc_rec + S_TILE * H;         // [4][S_TILE][H]
+  const int dir = blockIdx.y;
+  const int seq0 = blockIdx.x * S_TILE;
+  const int ns = min(S_TILE, n_seq - seq0);
+  const float* w = Whh + (size_t)dir * H4 * H;
+  const int n_steps = dir == 0 ? steps_fwd : steps_rev;
+  for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { dh_rec[e] = 0.f; dc_rec[e] = 0.f; }
+  for (int e = threadIdx.x; e < S_TILE * H4; e += blockDim.x) dgate[e] = 0.f;
+  __syncthreads();
+  for (int st = n_steps - 1; st >= 0; --st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    const int t_prev = dir == 0 ? t - 1 : t + 1;
+    for (int e = threadIdx.x; e < ns * H; e += blockDim.x) {
+      const int s = e / H, u = e % H;
+      const size_t gbase = (((size_t)(seq0 + s) * T + t) * 2 + dir) * H4;
+      const float ig = G[gbase + u], fg = G[gbase + H + u], gg = G[gbase + 2 * H + u], og = G[gbase + 3 * H + u];
+      const float c = CS[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H + u];
+      const float c_prev = st > 0 ? CS[(((size_t)(seq0 + s) * T + t_prev) * 2 + dir) * H + u] : 0.f;
+      const float tc = tanhf(c);
+      const float dh = dOUT[((size_t)(seq0 + s) * T + t) * 2 * H + dir * H + u] + dh_rec[e];
+      const float dc = dc_rec[e] + dh * og * (1.f - tc * tc);
+      const float dai = dc * gg * ig * (1.f - ig);
+      const float daf = dc * c_prev * fg * (1.f - fg);
+      const float dag = dc * ig * (1.f - gg * gg);
+      const float dao = dh * tc * og * (1.f - og);
+      dc_rec[e] = dc * fg;
+      dgate[s * H4 + u] = dai; dgate[s * H4 + H + u] = daf; dgate[s * H4 + 2 * H + u] = dag; dgate[s * H4 + 3 * H + u] = dao;
+      G[gbase + u] = dai; G[gbase + H + u] = daf; G[gbase + 2 * H + u] = dag; G[gbase + 3 * H + u] = dao;
+    }
+    __syncthreads();
+    // dh_rec[s][k] = sum_j dgate[s][j] * Whh[j][k]; thread -> (k, quarter of j)
+    if (threadIdx.x < H4) {
+      const int k = threadIdx.x % H, part = threadIdx.x / H;
+      float acc[S_TILE];
+#pragma unroll
+      for (int s = 0; s < S_TILE; ++s) acc[s] = 0.f;
+      if ((H & 3) == 0) {
+        for (int jj = part * H; jj < (part + 1) * H; jj += 4) {
+          const float w0 = __ldg(w + (size_t)jj * H + k), w1 = __ldg(w + (size_t)(jj + 1) * H + k);
+          const float w2 = __ldg(w + (size_t)(jj + 2) * H + k), w3 = __ldg(w + (size_t)(jj + 3) * H + k);
+#pragma unroll
+          for (int s = 0; s < S_TILE; ++s) {
+            const float4 g4 = *reinterpret_cast<const float4*>(dgate + s * H4 + jj);
+            acc[s] = fmaf(g4.x, w0, acc[s]); acc[s] = fmaf(g4.y, w1, acc[s]);
+            acc[s] = fmaf(g4.z, w2, acc[s]); acc[s] = fmaf(g4.w, w3, acc[s]);
+          }
+        }
+      } else {
+        for (int jj = part * H; jj < (part + 1) * H; ++jj) {
+          const float wv = __ldg(w + (size_t)jj * H + k);
+#pragma unroll
+          for (int s = 0; s < S_TILE; ++s) acc[s] = fmaf(dgate[s * H4 + jj], wv, acc[s]);
+        }
+      }
+#pragma unroll
+      for (int s = 0; s < S_TILE; ++s) red[(part * S_TILE + s) * H + k] = acc[s];
+    }
+    __syncthreads();
+    for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x)
+      dh_rec[e] = red[e] + red[S_TILE * H + e] + red[2 * S_TILE * H + e] + red[3 * S_TILE * H + e];
+    __syncthreads();
+  }
+  // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations)
+  for (int st = n_steps; st < T; ++st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    for (int e = threadIdx.x; e < ns * H4; e += blockDim.x) {
+      const int s = e / H4, jg = e % H4;
+      G[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + jg] = 0.f;
+    }
+  }
+}
+
+// AGG[seq][2H] = OUT[seq][T-1][:] ('last', SubGNN.py:83) or sum_t OUT[seq][t][:] ('sum', :85)
+__global__ void lstm_agg_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGG, int n_seq, int T, int H2, int sum_mode) {
+  const long long total = (long long)n_seq * H2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int seq = (int)(e / H2), c = (int)(e % H2);
+    float v;
+    if (sum_mode) {
+      v = 0.f;
+      for (int t = 0; t < T; ++t) v += OUT[((size_t)seq * T + t) * H2 + c];
+    } else {
+      v = OUT[((size_t)seq * T + T - 1) * H2 + c];
+    }
+    AGG[e] = v;
+  }
+}
+
+// dOUT[seq][t][:] = dAGG[seq][:] for every t ('sum') or only t = T-1 ('last', zero elsewhere)
+__global__ void lstm_agg_bwd_kernel(const float* __restrict__ dAGG, float* __restrict__ dOUT, int n_seq, int T, int H2, int sum_mode) {
+  const long long total = (long long)n_seq * T * H2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % H2);
+    const long long st = e / H2;
+    const int t = (int)(st % T), seq = (int)(st / T);
+    dOUT[e] = (sum_mode || t == T - 1) ? dAGG[(size_t)seq * H2 + c] : 0.f;
+  }
+}
+
+// EMB[g][d] = sum_{w<group} Y[g*group + w][d]       (anchor_patch_samplers.py:433)
+__global__ void group_sum_kernel(const float* __restrict__ Y, float* __restrict__ EMB, int n_groups, int group, int D) {
+  const long long total = (long long)n_groups * D;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e / D), d = (int)(e % D);
+    float v = 0.f;
+    for (int w = 0; w < group; ++w) v += Y[((size_t)g * group + w) * D + d];
+    EMB[e] = v;
+  }
+}
+__global__ void group_bcast_kernel(const float* __restrict__ dEMB, float* __restrict__ dY, int n_groups, int group, int D) {
+  const long long total = (long long)n_groups * group * D;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)(e % D);
+    const long long row = e / D;
+    dY[e] = dEMB[(row / group) * D + d];
+  }
+}
+
+// inter-layer dropout (nn.LSTM dropout=p, training only): y = x * keep/(1-p); the same kernel applies the mask
+// to gradients.  Counter-based mask: element index within the buffer, salt = layer / step counter.
+__global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
+                               unsigned salt, const int* __restrict__ step_dev) {
+  if (step_dev) salt += 64u * (unsigned)*step_dev + 0x80000000u;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+    y[e] = x[e] * sg_dropout_scale(seed, salt, (uint64_t)e, p);
+}
+
+// per-step weight staging: WhhT[dir][k][j] = Whh[dir][j][k]; bsum[dir][j] = b_ih[dir][j] + b_hh[dir][j]
+__global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                 float* __restrict__ WhhT, float* __restrict__ bsum, int H) {
+  const int H4 = 4 * H;
+  const long long total = (long long)2 * H4 * H;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int dir = (int)(e / ((long long)H4 * H));
+    const int r = (int)(e % ((long long)H4 * H));
+    const int k = r / H4, j = r % H4;
+    WhhT[e] = Whh[((size_t)dir * H4 + j) * H + k];
+    if (e < 2 * H4) bsum[e] = b_ih[e] + b_hh[e];
+  }
+}
+
+extern "C" {
+
+static int lstm_block(int H) { return ((4 * H + 31) / 32) * 32; }
+
+int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream) {
+  SG_REQUIRE(H >= 1 && H <= 256, "hidden size must be in [1, 256]");
+  lstm_prep_kernel<<<sg_grid_for((long long)8 * H * H, 256, 4), 256, 0, (cudaStream_t)stream>>>(whh, b_ih, b_hh, whh_t, bsum, H);
+  return subgnn_check_launch("lstm_prep_kernel");
+}
+
+int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
+                          void* stream) {
+  SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
+  SG_REQUIRE(steps_fwd >= 0 && steps_fwd <= T && steps_rev >= 0 && steps_rev <= T, "bad step counts");
+  if (n_seq == 0) return SUBGNN_OK;
+  const size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(sg_div_up(n_seq, S_TILE), 2);
+  lstm_recur_fwd_kernel<<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
+  return subgnn_check_launch("lstm_recur_fwd_kernel");
+}
+
+int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
+                          int steps_fwd, int steps_rev, void* stream) {
+  SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
+  if (n_seq == 0) return SUBGNN_OK;
+  const size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  dim3 grid(sg_div_up(n_seq, S_TILE), 2);
+  lstm_recur_bwd_kernel<<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev);
+  return subgnn_check_launch("lstm_recur_bwd_kernel");
+}
+
+int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream) {
+  if (n_seq == 0) return SUBGNN_OK;
+  lstm_agg_fwd_kernel<<<sg_grid_for((long long)n_seq * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(OUT, AGG, n_seq, T, H2, sum_mode);
+  return subgnn_check_launch("lstm_agg_fwd_kernel");
+}
+
+int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream) {
+  if (n_seq == 0) return SUBGNN_OK;
+  lstm_agg_bwd_kernel<<<sg_grid_for((long long)n_seq * T * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(dAGG, dOUT, n_seq, T, H2, sum_mode);
+  return subgnn_check_launch("lstm_agg_bwd_kernel");
+}
+
+int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream) {
+  if (n_groups == 0) return SUBGNN_OK;
+  group_sum_kernel<<<sg_grid_for((long long)n_groups * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(Y, EMB, n_groups, group, D);
+  return subgnn_check_launch("group_sum_kernel");
+}
+
+int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream) {
+  if (n_groups == 0) return SUBGNN_OK;
+  group_bcast_kernel<<<sg_grid_for((long long)n_groups * group * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(dEMB, dY, n_groups, group, D);
+  return subgnn_check_launch("group_bcast_kernel");
+}
+
+int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
+                   void* stream) {
+  if (n == 0) return SUBGNN_OK;
+  dropout_kernel<<<sg_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, salt, step_dev);
+  return subgnn_check_launch("dropout_kernel");
+}
+
+}  // extern "C"

@@ -1,0 +1,826 @@
+// Fused per-step SubGNN path: one CTA per subgraph of the batch, one warp per connected component.
+//
+// Replaces, per training / inference step (reference):
+//   SubGNN.py:609-622                   initialize_cc_embeddings (sum | max pooling of node embeddings)
+//   anchor_patch_samplers.py:333-411    get_anchor_patches / embed_anchor_patch (N, P channels: row gathers)
+//   subgraph_mpn.py:36-241              SG_MPN.forward: edge list, similarity lookup, msg = sim * x_anchor,
+//                                       scatter-add, relu(W [x ; agg] + b), relu(w_p . msg + b_p)
+//   SubGNN.py:225-312                   forward: layer / channel loops, concat, masked_sum readout, MLP
+//   SubGNN.py:338-342                   CrossEntropy | BCEWithLogits loss
+//   and the autograd backward of all of the above.
+//
+// Closed form used (verified against the reference): for a valid component row r with
+// anchors a, mask m = (anchor id != PAD), similarity s:
+//     agg[r]   = sum_a m s x_a            cc'[r] = relu(W [cc[r] ; agg[r]] + b)
+//     pos[r,a] = relu(m s (w_p . x_a) + b_p)
+// Only the outputs that reach the logits are computed: for the P and S channels the updated component
+// embeddings are carried by the reference but never concatenated (SubGNN.py:281,291), and for the N channel
+// the property-aware output is discarded (SubGNN.py:265-266); their parameters receive no gradient in the
+// reference either.  Padded components are skipped: SubGNN.py:303 masks them out of the readout.
+// q[a] = w_p . x_a is computed once per shared anchor list (model_q_fwd) instead of once per (component, anchor).
+#include "common.cuh"
+#include "../../include/subgnn_b200.h"
+
+#define SUB_WARPS 8
+#define SUB_THREADS (SUB_WARPS * 32)
+#define MAXDPL 8   // D <= 256
+
+typedef subgnn_model_desc Desc;
+
+__device__ __forceinline__ int mpn_blk(const Desc& d) { return 2 * d.D * d.D + 2 * d.D + 1; }
+__device__ __forceinline__ int layer_width(const Desc& d) {
+  return (d.use_n ? 2 * d.D : 0) + (d.use_p ? d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
+}
+__device__ __forceinline__ int col_n(const Desc& d, int l, int side) { return d.D + l * layer_width(d) + side * d.D; }
+__device__ __forceinline__ int col_p(const Desc& d, int l, int side) {
+  return d.D + l * layer_width(d) + (d.use_n ? 2 * d.D : 0) + (side ? d.A_pi : 0);
+}
+__device__ __forceinline__ int col_s(const Desc& d, int l, int side) {
+  return d.D + l * layer_width(d) + (d.use_n ? 2 * d.D : 0) + (d.use_p ? d.A_pi + d.A_pb : 0) + side * d.A_s;
+}
+
+// ------------------------------------------------------------------------------------------------
+// prep: batch row offsets, R, max component length; transposed weights
+__global__ void __launch_bounds__(256) prep_batch_kernel(Desc d) {
+  __shared__ int part[256];
+  __shared__ int pmax[256];
+  const int t = threadIdx.x;
+  const int chunk = (d.B + 255) / 256;
+  const int beg = min(d.B, t * chunk), end = min(d.B, beg + chunk);
+  int s = 0, mx = 0;
+  for (int b = beg; b < end; ++b) {
+    const int sub = d.batch_idx[b];
+    s += d.sub_ccptr[sub + 1] - d.sub_ccptr[sub];
+    mx = max(mx, d.sub_maxlen[sub]);
+  }
+  part[t] = s;
+  pmax[t] = mx;
+  __syncthreads();
+  if (t == 0) {
+    int run = 0, m = 0;
+    for (int i = 0; i < 256; ++i) { const int v = part[i]; part[i] = run; run += v; m = max(m, pmax[i]); }
+    d.meta[0] = run;
+    d.meta[1] = m;
+    d.b_rowptr[d.B] = run;
+  }
+  __syncthreads();
+  int run = part[t];
+  for (int b = beg; b < end; ++b) {
+    const int sub = d.batch_idx[b];
+    d.b_rowptr[b] = run;
+    run += d.sub_ccptr[sub + 1] - d.sub_ccptr[sub];
+  }
+}
+
+// out[c][r] = in[r][c] for a list of matrices: job j -> (src, dst, rows, cols)
+__global__ void transpose_weights_kernel(Desc d) {
+  // jobs: N-channel projections (L*2 of D x 2D), then lin (h1 x hid), lin2 (h2 x h1), lin3 (K x h2)
+  const int n_jobs_n = d.use_n ? d.L * 2 : 0;
+  for (int job = blockIdx.y; job < n_jobs_n + 3; job += gridDim.y) {
+    const float* src;
+    float* dst;
+    int rows, cols;
+    if (job < n_jobs_n) {
+      src = d.mpn_params[0] + (size_t)job * (2 * d.D * d.D + 2 * d.D + 1);
+      dst = d.n_wt + (size_t)job * 2 * d.D * d.D;
+      rows = d.D; cols = 2 * d.D;
+    } else {
+      const int k = job - n_jobs_n;
+      src = d.lin_w[k];
+      dst = d.lin_wt[k];
+      rows = k == 0 ? d.h1 : (k == 1 ? d.h2 : d.n_classes);
+      cols = k == 0 ? d.hid : (k == 1 ? d.h1 : d.h2);
+    }
+    const int total = rows * cols;
+    for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
+      const int c = e / rows, r = e % rows;     // consecutive threads -> consecutive dst addresses (dst[c][r])
+      dst[(size_t)c * rows + r] = src[(size_t)r * cols + c];
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// q = w_p . x for every shared anchor list.  Entry space per layer l:
+//   [0, B*A_pi)            P-internal anchors of the batch's subgraphs
+//   [.., + A_pb)           P-border anchors
+//   [.., + 2*A_s)          S anchors (internal side, border side): x = LSTM embedding
+__device__ __forceinline__ int q_entries_per_layer(const Desc& d) {
+  return (d.use_p ? d.B * d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
+}
+
+struct QEntry {
+  const float* x;      // anchor row (D floats) or nullptr (PAD)
+  const float* wp;     // linear_position.weight of the owning MPN
+  float* q;            // destination of q
+  float* dq;           // gradient source
+  float* dwp;          // gradient of w_p
+  float* dx;           // gradient row destination (atomic if !unique)
+  bool unique;
+};
+
+__device__ __forceinline__ QEntry q_entry(const Desc& d, int l, int e) {
+  QEntry r;
+  const int blk = 2 * d.D * d.D + 2 * d.D + 1;
+  const int wp_off = 2 * d.D * d.D + d.D;
+  int id = -1;
+  if (d.use_p) {
+    if (e < d.B * d.A_pi) {
+      const int b = e / d.A_pi, a = e % d.A_pi;
+      id = d.p_int_ids[((size_t)l * d.n_sub + d.batch_idx[b]) * d.A_pi + a];
+      r.wp = d.mpn_params[1] + (size_t)(2 * l + 0) * blk + wp_off;
+      r.dwp = d.mpn_grads[1] ? d.mpn_grads[1] + (size_t)(2 * l + 0) * blk + wp_off : nullptr;
+      r.q = d.q_pi + (size_t)l * d.B * d.A_pi + e;
+      r.dq = d.dq_pi + (size_t)l * d.B * d.A_pi + e;
+    } else if (e < d.B * d.A_pi + d.A_pb) {
+      const int a = e - d.B * d.A_pi;
+      id = d.p_bor_ids[(size_t)l * d.A_pb + a];
+      r.wp = d.mpn_params[1] + (size_t)(2 * l + 1) * blk + wp_off;
+      r.dwp = d.mpn_grads[1] ? d.mpn_grads[1] + (size_t)(2 * l + 1) * blk + wp_off : nullptr;
+      r.q = d.q_pb + (size_t)l * d.A_pb + a;
+      r.dq = d.dq_pb + (size_t)l * d.A_pb + a;
+    }
+    e -= d.B * d.A_pi + d.A_pb;
+  }
+  if (id >= 0) {
+    r.x = id != 0 ? d.E + (size_t)id * d.D : nullptr;
+    r.dx = (id != 0 && d.dE) ? d.dE + (size_t)id * d.D : nullptr;
+    r.unique = false;
+    return r;
+  }
+  // structure
+  const int side = e / d.A_s, a = e % d.A_s;
+  const size_t gi = ((size_t)side * d.L + l) * d.A_s + a;
+  r.x = d.emb_s + gi * d.D;
+  r.dx = d.d_emb_s ? d.d_emb_s + gi * d.D : nullptr;
+  r.unique = true;
+  r.wp = d.mpn_params[2] + (size_t)(2 * l + side) * blk + wp_off;
+  r.dwp = d.mpn_grads[2] ? d.mpn_grads[2] + (size_t)(2 * l + side) * blk + wp_off : nullptr;
+  r.q = d.q_s + ((size_t)l * 2 + side) * d.A_s + a;
+  r.dq = d.dq_s + ((size_t)l * 2 + side) * d.A_s + a;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) q_fwd_kernel(Desc d) {
+  const int lane = threadIdx.x & 31;
+  const int per_layer = q_entries_per_layer(d);
+  const int total = per_layer * d.L;
+  const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int warps_total = (gridDim.x * blockDim.x) >> 5;
+  for (int w = warp_global; w < total; w += warps_total) {
+    const QEntry en = q_entry(d, w / per_layer, w % per_layer);
+    float acc = 0.f;
+    if (en.x)
+      for (int k = lane; k < d.D; k += 32) acc = fmaf(en.wp[k], en.x[k], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) *en.q = acc;
+  }
+}
+
+// grid (blocks_per_group, L * groups); group = one (channel side) parameter block, so that d w_p is reduced
+// inside the CTA and added once per CTA.
+__global__ void __launch_bounds__(256) q_bwd_kernel(Desc d) {
+  __shared__ float s_dwp[8][256];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int groups = (d.use_p ? 2 : 0) + (d.use_s ? 2 : 0);
+  const int l = blockIdx.y / groups;
+  int grp = blockIdx.y % groups;
+  int e_beg, e_cnt;
+  const int pi = d.B * d.A_pi;
+  if (d.use_p && grp == 0) { e_beg = 0; e_cnt = pi; }
+  else if (d.use_p && grp == 1) { e_beg = pi; e_cnt = d.A_pb; }
+  else {
+    if (d.use_p) grp -= 2;
+    e_beg = (d.use_p ? pi + d.A_pb : 0) + grp * d.A_s;
+    e_cnt = d.A_s;
+  }
+  float dwp[MAXDPL];
+#pragma unroll
+  for (int q = 0; q < MAXDPL; ++q) dwp[q] = 0.f;
+  float* dwp_dst = nullptr;
+  for (int i = blockIdx.x * 8 + warp; i < e_cnt; i += gridDim.x * 8) {
+    const QEntry en = q_entry(d, l, e_beg + i);
+    dwp_dst = en.dwp;
+    const float g = *en.dq;
+    if (!en.x) continue;
+#pragma unroll
+    for (int q = 0; q < MAXDPL; ++q) {
+      const int k = lane + 32 * q;
+      if (k < d.D) {
+        dwp[q] = fmaf(g, en.x[k], dwp[q]);
+        if (en.dx) {
+          const float v = g * en.wp[k];
+          if (en.unique) en.dx[k] = v; else if (v != 0.f) atomicAdd(en.dx + k, v);
+        }
+      }
+    }
+  }
+  if (!dwp_dst) {   // this warp had no entry: still need the destination for the block reduction
+    if (e_cnt > 0) dwp_dst = q_entry(d, l, e_beg).dwp;
+  }
+#pragma unroll
+  for (int q = 0; q < MAXDPL; ++q) if (lane + 32 * q < 256) s_dwp[warp][lane + 32 * q] = dwp[q];
+  __syncthreads();
+  if (dwp_dst)
+    for (int k = threadIdx.x; k < d.D; k += blockDim.x) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < 8; ++w) s += s_dwp[w][k];
+      if (s != 0.f) atomicAdd(dwp_dst + k, s);
+    }
+}
+
+__device__ __forceinline__ unsigned mlp_salt(const Desc& d) { return (d.step_dev ? (unsigned)*d.step_dev : d.step) * 4u; }
+
+// ------------------------------------------------------------------------------------------------
+// per-sample MLP (forward + optional backward).  zs: subgraph embedding in shared memory (hid floats);
+// work: shared scratch of at least h1 + h2 + K + h1 + h2 floats.
+__device__ void mlp_forward(const Desc& d, int b, const float* zs, float* work) {
+  float* h1s = work;
+  float* h2s = h1s + d.h1;
+  float* lg = h2s + d.h2;
+  const int tid = threadIdx.x;
+  for (int j = tid; j < d.h1; j += blockDim.x) {
+    float acc = d.lin_b[0][j];
+    const float* wt = d.lin_wt[0] + j;
+    for (int i = 0; i < d.hid; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
+    acc = fmaxf(acc, 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
+    h1s[j] = acc;
+    d.H1[(size_t)b * d.h1 + j] = acc;
+  }
+  __syncthreads();
+  for (int j = tid; j < d.h2; j += blockDim.x) {
+    float acc = d.lin_b[1][j];
+    const float* wt = d.lin_wt[1] + j;
+    for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], wt[(size_t)i * d.h2], acc);
+    acc = fmaxf(acc, 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
+    h2s[j] = acc;
+    d.H2[(size_t)b * d.h2 + j] = acc;
+  }
+  __syncthreads();
+  for (int c = tid; c < d.n_classes; c += blockDim.x) {
+    float acc = d.lin_b[2][c];
+    const float* wt = d.lin_wt[2] + c;
+    for (int i = 0; i < d.h2; ++i) acc = fmaf(h2s[i], wt[(size_t)i * d.n_classes], acc);
+    lg[c] = acc;
+    d.logits[(size_t)b * d.n_classes + c] = acc;
+  }
+  __syncthreads();
+  // loss term and d logits (thread 0: K is tiny)
+  if (tid == 0) {
+    const int K = d.n_classes;
+    const int sub = d.batch_idx[b];
+    float loss = 0.f;
+    if (!d.multilabel) {
+      float mx = lg[0];
+      for (int c = 1; c < K; ++c) mx = fmaxf(mx, lg[c]);
+      float se = 0.f;
+      for (int c = 0; c < K; ++c) se += expf(lg[c] - mx);
+      const float lse = mx + logf(se);
+      const int y = d.labels ? d.labels[sub] : 0;
+      loss = (lse - lg[y]) / (float)d.B;
+      if (d.dlogits)
+        for (int c = 0; c < K; ++c) d.dlogits[(size_t)b * K + c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)d.B;
+    } else {
+      const float inv = 1.f / ((float)d.B * (float)K);
+      for (int c = 0; c < K; ++c) {
+        const float x = lg[c], y = d.labels_multi[(size_t)sub * K + c];
+        loss += (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)))) * inv;
+        if (d.dlogits) d.dlogits[(size_t)b * K + c] = (1.f / (1.f + expf(-x)) - y) * inv;
+      }
+    }
+    d.loss_b[b] = loss;
+  }
+  __syncthreads();
+}
+
+// d logits (global) -> dH2, dH1 (pre-activation grads), dZ; dzs (shared, hid floats) receives dZ[b]
+__device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
+  float* dl = work;                 // K
+  float* g2 = dl + d.n_classes;     // h2
+  float* g1 = g2 + d.h2;            // h1
+  const int tid = threadIdx.x;
+  const int K = d.n_classes;
+  for (int c = tid; c < K; c += blockDim.x) dl[c] = d.dlogits[(size_t)b * K + c];
+  __syncthreads();
+  for (int j = tid; j < d.h2; j += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < K; ++c) acc = fmaf(dl[c], d.lin_w[2][(size_t)c * d.h2 + j], acc);
+    const float hv = d.H2[(size_t)b * d.h2 + j];
+    float sc = d.training ? sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout) : 1.f;
+    acc = hv > 0.f ? acc * sc : 0.f;
+    g2[j] = acc;
+    d.dH2[(size_t)b * d.h2 + j] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < d.h1; i += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < d.h2; ++j) acc = fmaf(g2[j], d.lin_w[1][(size_t)j * d.h1 + i], acc);
+    const float hv = d.H1[(size_t)b * d.h1 + i];
+    float sc = d.training ? sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + i, d.lin_dropout) : 1.f;
+    acc = hv > 0.f ? acc * sc : 0.f;
+    g1[i] = acc;
+    d.dH1[(size_t)b * d.h1 + i] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < d.hid; i += blockDim.x) {
+    float acc = 0.f;
+    for (int j = 0; j < d.h1; ++j) acc = fmaf(g1[j], d.lin_w[0][(size_t)j * d.hid + i], acc);
+    dzs[i] = acc;
+    d.dZ[(size_t)b * d.hid + i] = acc;
+  }
+  __syncthreads();
+}
+
+// ------------------------------------------------------------------------------------------------
+// forward over the rows of one subgraph
+template <int DPL>
+__global__ void __launch_bounds__(SUB_THREADS) sub_fwd_kernel(Desc d) {
+  extern __shared__ float sm[];
+  float* zs = sm;                               // [hid]
+  float* in_all = zs + d.hid;                   // [SUB_WARPS][2D]
+  float* work = in_all + SUB_WARPS * 2 * d.D;   // MLP scratch
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int D = d.D;
+  const int sub = d.batch_idx[b];
+  const int g0 = d.sub_ccptr[sub], g1 = d.sub_ccptr[sub + 1];
+  const int r0 = d.b_rowptr[b];
+  const int maxlen = d.meta[1];
+  const int blk = 2 * D * D + 2 * D + 1;
+  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) zs[i] = 0.f;
+  __syncthreads();
+  float* in_s = in_all + warp * 2 * D;
+  for (int g = g0 + warp; g < g1; g += SUB_WARPS) {
+    const int r = r0 + (g - g0);
+    // ---- pooling (SubGNN.py:609-622) ----
+    const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
+    float x0[DPL];
+#pragma unroll
+    for (int q = 0; q < DPL; ++q) x0[q] = d.pool_max ? -INFINITY : 0.f;
+    for (int i = nb; i < ne; ++i) {
+      const float* row = d.E + (size_t)d.cc_nodes[i] * D;
+#pragma unroll
+      for (int q = 0; q < DPL; ++q) {
+        const int k = lane + 32 * q;
+        if (k < D) x0[q] = d.pool_max ? fmaxf(x0[q], row[k]) : x0[q] + row[k];
+      }
+    }
+    if (d.pool_max && (ne - nb) < maxlen) {       // PAD rows (zero vectors) take part in the max (F: SubGNN.py:622)
+#pragma unroll
+      for (int q = 0; q < DPL; ++q) x0[q] = fmaxf(x0[q], 0.f);
+    }
+#pragma unroll
+    for (int q = 0; q < DPL; ++q) {
+      const int k = lane + 32 * q;
+      if (k < D) {
+        d.X0[(size_t)r * D + k] = x0[q];
+        atomicAdd(&zs[k], x0[q]);
+      }
+    }
+    // ---- neighbourhood channel: L chained MPN layers per side ----
+    if (d.use_n) {
+      for (int side = 0; side < 2; ++side) {
+        const int A = side ? d.A_nb : d.A_ni;
+        float h[DPL];
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) {
+          const int k = lane + 32 * q;
+          if (k < D) {
+            h[q] = d.trainable_cc ? d.cc_tab[side][((size_t)sub * d.C_pad + (g - g0)) * D + k] : x0[q];
+            d.Nh[((size_t)(0 * 2 + side) * d.R_cap + r) * D + k] = h[q];
+          } else h[q] = 0.f;
+        }
+        for (int l = 0; l < d.L; ++l) {
+          const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          float agg[DPL];
+#pragma unroll
+          for (int q = 0; q < DPL; ++q) agg[q] = 0.f;
+          int a = 0;
+          for (; a + 4 <= A; a += 4) {               // 4 independent row gathers in flight
+            const int i0 = ids[a], i1 = ids[a + 1], i2 = ids[a + 2], i3 = ids[a + 3];
+            const float s0 = sims[a], s1 = sims[a + 1], s2 = sims[a + 2], s3 = sims[a + 3];
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) {
+              const int k = lane + 32 * q;
+              if (k < D) {
+                const float v0 = i0 ? d.E[(size_t)i0 * D + k] : 0.f, v1 = i1 ? d.E[(size_t)i1 * D + k] : 0.f;
+                const float v2 = i2 ? d.E[(size_t)i2 * D + k] : 0.f, v3 = i3 ? d.E[(size_t)i3 * D + k] : 0.f;
+                agg[q] = fmaf(s0, v0, agg[q]); agg[q] = fmaf(s1, v1, agg[q]);
+                agg[q] = fmaf(s2, v2, agg[q]); agg[q] = fmaf(s3, v3, agg[q]);
+              }
+            }
+          }
+          for (; a < A; ++a) {
+            const int i0 = ids[a];
+            const float s0 = sims[a];
+            if (i0)
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < D) agg[q] = fmaf(s0, d.E[(size_t)i0 * D + k], agg[q]);
+              }
+          }
+          float out[DPL];
+          if (d.use_proj) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) {
+              const int k = lane + 32 * q;
+              if (k < D) { in_s[k] = h[q]; in_s[D + k] = agg[q]; }
+            }
+            __syncwarp();
+            const float* wt = d.n_wt + (size_t)(2 * l + side) * 2 * D * D;       // [2D][D]
+            const float* bias = d.mpn_params[0] + (size_t)(2 * l + side) * blk + 2 * D * D;
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; out[q] = k < D ? bias[k] : 0.f; }
+            for (int kk = 0; kk < 2 * D; ++kk) {
+              const float xv = in_s[kk];
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < D) out[q] = fmaf(xv, __ldg(wt + (size_t)kk * D + k), out[q]);
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) out[q] = fmaxf(out[q], 0.f);
+          } else {
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) out[q] = agg[q];                       // subgraph_mpn.py:240-241
+          }
+          const int zc = col_n(d, l, side);
+#pragma unroll
+          for (int q = 0; q < DPL; ++q) {
+            const int k = lane + 32 * q;
+            if (k < D) {
+              d.Nagg[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = agg[q];
+              d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + k] = out[q];
+              atomicAdd(&zs[zc + k], out[q]);
+              h[q] = out[q];
+            }
+          }
+        }
+      }
+    }
+    // ---- position / structure channels: property-aware outputs ----
+    for (int l = 0; l < d.L; ++l) {
+      if (d.use_p) {
+        for (int side = 0; side < 2; ++side) {
+          const int A = side ? d.A_pb : d.A_pi;
+          const float* sims = d.p_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* q = side ? d.q_pb + (size_t)l * A : d.q_pi + ((size_t)l * d.B + b) * A;
+          const float bp = d.mpn_params[1][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
+          const int zc = col_p(d, l, side);
+          for (int a = lane; a < A; a += 32) atomicAdd(&zs[zc + a], fmaxf(fmaf(sims[a], q[a], bp), 0.f));
+        }
+      }
+      if (d.use_s) {
+        for (int side = 0; side < 2; ++side) {
+          const int A = d.A_s;
+          const float* sims = d.s_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* q = d.q_s + ((size_t)l * 2 + side) * A;
+          const float bp = d.mpn_params[2][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
+          const int zc = col_s(d, l, side);
+          for (int a = lane; a < A; a += 32) atomicAdd(&zs[zc + a], fmaxf(fmaf(sims[a], q[a], bp), 0.f));
+        }
+      }
+    }
+  }
+  __syncthreads();
+  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) d.Z[(size_t)b * d.hid + i] = zs[i];
+  mlp_forward(d, b, zs, work);
+  if (d.training && d.dZ) mlp_backward(d, b, zs, work);
+}
+
+__global__ void __launch_bounds__(SUB_THREADS) mlp_bwd_kernel(Desc d) {
+  extern __shared__ float sm[];
+  mlp_backward(d, blockIdx.x, sm, sm + d.hid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// backward over the rows of one subgraph
+template <int DPL>
+__global__ void __launch_bounds__(SUB_THREADS) sub_bwd_kernel(Desc d) {
+  extern __shared__ float sm[];
+  const int D = d.D;
+  float* dzs = sm;                                   // [hid]
+  float* dpre_all = dzs + d.hid;                     // [SUB_WARPS][D]
+  float* acc_q = dpre_all + SUB_WARPS * D;           // [L][A_pi + A_pb + 2 A_s] dq accumulators
+  const int qw = (d.use_p ? d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
+  float* acc_bp = acc_q + d.L * qw;                  // [L][4] d b_p (P int, P bor, S int, S bor)
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int b = blockIdx.x;
+  const int sub = d.batch_idx[b];
+  const int g0 = d.sub_ccptr[sub], g1 = d.sub_ccptr[sub + 1];
+  const int r0 = d.b_rowptr[b];
+  const int blk = 2 * D * D + 2 * D + 1;
+  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) dzs[i] = d.dZ[(size_t)b * d.hid + i];
+  for (int i = threadIdx.x; i < d.L * qw + d.L * 4; i += blockDim.x) acc_q[i] = 0.f;
+  __syncthreads();
+  float* dpre_s = dpre_all + warp * D;
+  for (int g = g0 + warp; g < g1; g += SUB_WARPS) {
+    const int r = r0 + (g - g0);
+    float dx0[DPL];                                  // gradient w.r.t. the pooled embedding
+#pragma unroll
+    for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; dx0[q] = k < D ? dzs[k] : 0.f; }
+    if (d.use_n) {
+      for (int side = 0; side < 2; ++side) {
+        const int A = side ? d.A_nb : d.A_ni;
+        float dh[DPL];
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) dh[q] = 0.f;
+        for (int l = d.L - 1; l >= 0; --l) {
+          const int zc = col_n(d, l, side);
+          float dagg[DPL];
+          if (d.use_proj) {
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) {
+              const int k = lane + 32 * q;
+              if (k < D) {
+                const float outv = d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + k];
+                const float g_ = outv > 0.f ? dzs[zc + k] + dh[q] : 0.f;
+                dpre_s[k] = g_;
+                d.Ndpre[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = g_;
+              }
+            }
+            __syncwarp();
+            const float* w = d.mpn_params[0] + (size_t)(2 * l + side) * blk;      // [D][2D]
+            float dlo[DPL], dhi[DPL];
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) { dlo[q] = 0.f; dhi[q] = 0.f; }
+            for (int j = 0; j < D; ++j) {
+              const float gj = dpre_s[j];
+              const float* wr = w + (size_t)j * 2 * D;
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) {
+                const int k = lane + 32 * q;
+                if (k < D) { dlo[q] = fmaf(gj, __ldg(wr + k), dlo[q]); dhi[q] = fmaf(gj, __ldg(wr + D + k), dhi[q]); }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) { dh[q] = dlo[q]; dagg[q] = dhi[q]; }
+          } else {
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) {
+              const int k = lane + 32 * q;
+              dagg[q] = k < D ? dzs[zc + k] + dh[q] : 0.f;
+              dh[q] = 0.f;                                                        // update() ignores x without projection
+            }
+          }
+          // scatter d agg into the embedding gradient of every valid anchor
+          if (d.dE) {
+            const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
+            const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
+            for (int a = 0; a < A; ++a) {
+              const int id = ids[a];
+              const float s = sims[a];
+              if (id != 0 && s != 0.f)
+#pragma unroll
+                for (int q = 0; q < DPL; ++q) {
+                  const int k = lane + 32 * q;
+                  if (k < D) atomicAdd(d.dE + (size_t)id * D + k, s * dagg[q]);
+                }
+            }
+          }
+        }
+        // gradient of the layer-0 input
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) {
+          const int k = lane + 32 * q;
+          if (k < D) {
+            if (d.trainable_cc) {
+              if (d.cc_tab_grad[side]) atomicAdd(d.cc_tab_grad[side] + ((size_t)sub * d.C_pad + (g - g0)) * D + k, dh[q]);
+            } else {
+              dx0[q] += dh[q];
+            }
+          }
+        }
+      }
+    }
+    // ---- pooling backward ----
+    if (d.dE) {
+      const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
+      if (!d.pool_max) {
+        for (int i = nb; i < ne; ++i) {
+          float* row = d.dE + (size_t)d.cc_nodes[i] * D;
+#pragma unroll
+          for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; if (k < D) atomicAdd(row + k, dx0[q]); }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) {
+          const int k = lane + 32 * q;
+          if (k < D) {
+            const float mx = d.X0[(size_t)r * D + k];
+            for (int i = nb; i < ne; ++i) {
+              const int id = d.cc_nodes[i];
+              if (d.E[(size_t)id * D + k] == mx) { atomicAdd(d.dE + (size_t)id * D + k, dx0[q]); break; }
+            }
+          }
+        }
+      }
+    }
+    // ---- property-aware outputs backward: d q and d b_p ----
+    for (int l = 0; l < d.L; ++l) {
+      float* aq = acc_q + l * qw;
+      if (d.use_p) {
+        for (int side = 0; side < 2; ++side) {
+          const int A = side ? d.A_pb : d.A_pi;
+          const float* sims = d.p_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* q = side ? d.q_pb + (size_t)l * A : d.q_pi + ((size_t)l * d.B + b) * A;
+          const float bp = d.mpn_params[1][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
+          const int zc = col_p(d, l, side);
+          float* dst = aq + (side ? d.A_pi : 0);
+          float dbp = 0.f;
+          for (int a = lane; a < A; a += 32) {
+            const float s = sims[a];
+            if (fmaf(s, q[a], bp) > 0.f) {
+              const float g_ = dzs[zc + a];
+              dbp += g_;
+              atomicAdd(dst + a, s * g_);
+            }
+          }
+          dbp = warp_sum(dbp);
+          if (lane == 0) atomicAdd(acc_bp + l * 4 + side, dbp);
+        }
+      }
+      if (d.use_s) {
+        for (int side = 0; side < 2; ++side) {
+          const int A = d.A_s;
+          const float* sims = d.s_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* q = d.q_s + ((size_t)l * 2 + side) * A;
+          const float bp = d.mpn_params[2][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
+          const int zc = col_s(d, l, side);
+          float* dst = aq + (d.use_p ? d.A_pi + d.A_pb : 0) + side * A;
+          float dbp = 0.f;
+          for (int a = lane; a < A; a += 32) {
+            const float s = sims[a];
+            if (fmaf(s, q[a], bp) > 0.f) {
+              const float g_ = dzs[zc + a];
+              dbp += g_;
+              atomicAdd(dst + a, s * g_);
+            }
+          }
+          dbp = warp_sum(dbp);
+          if (lane == 0) atomicAdd(acc_bp + l * 4 + 2 + side, dbp);
+        }
+      }
+    }
+  }
+  __syncthreads();
+  // flush the CTA-level accumulators
+  for (int l = 0; l < d.L; ++l) {
+    const float* aq = acc_q + l * qw;
+    if (d.use_p) {
+      for (int a = threadIdx.x; a < d.A_pi; a += blockDim.x) d.dq_pi[((size_t)l * d.B + b) * d.A_pi + a] = aq[a];   // unique owner
+      for (int a = threadIdx.x; a < d.A_pb; a += blockDim.x) {
+        const float v = aq[d.A_pi + a];
+        if (v != 0.f) atomicAdd(d.dq_pb + (size_t)l * d.A_pb + a, v);
+      }
+    }
+    if (d.use_s) {
+      const float* as = aq + (d.use_p ? d.A_pi + d.A_pb : 0);
+      for (int a = threadIdx.x; a < 2 * d.A_s; a += blockDim.x) {
+        const float v = as[a];
+        if (v != 0.f) atomicAdd(d.dq_s + (size_t)l * 2 * d.A_s + a, v);
+      }
+    }
+    if (threadIdx.x < 4) {
+      const int ch = threadIdx.x < 2 ? 1 : 2, side = threadIdx.x & 1;
+      const bool on = ch == 1 ? d.use_p : d.use_s;
+      const float v = acc_bp[l * 4 + threadIdx.x];
+      if (on && d.mpn_grads[ch] && v != 0.f) atomicAdd(d.mpn_grads[ch] + (size_t)(2 * l + side) * blk + 2 * D * D + 2 * D, v);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+static size_t fwd_smem(const Desc& d) {
+  return (size_t)(d.hid + SUB_WARPS * 2 * d.D + 2 * (d.h1 + d.h2) + d.n_classes + 8) * sizeof(float);
+}
+static size_t bwd_smem(const Desc& d) {
+  const int qw = (d.use_p ? d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
+  return (size_t)(d.hid + SUB_WARPS * d.D + d.L * qw + d.L * 4 + 8) * sizeof(float);
+}
+static int check_desc(const Desc* d) {
+  if (!d) { subgnn_set_error("null descriptor"); return SUBGNN_ERR_ARG; }
+  if (d->D < 1 || d->D > 32 * MAXDPL) { subgnn_set_error("node_embed_size must be in [1, %d]", 32 * MAXDPL); return SUBGNN_ERR_ARG; }
+  if (d->B < 1 || d->L < 1) { subgnn_set_error("bad batch / layer count"); return SUBGNN_ERR_ARG; }
+  if (fwd_smem(*d) > 200 * 1024 || bwd_smem(*d) > 200 * 1024) { subgnn_set_error("hidden dimension too large for shared memory"); return SUBGNN_ERR_ARG; }
+  return SUBGNN_OK;
+}
+
+#define DISPATCH_DPL(D, KERNEL, ...)                                   \
+  do {                                                                 \
+    const int dpl_ = ((D) + 31) / 32;                                  \
+    if (dpl_ <= 1) { KERNEL<1> __VA_ARGS__; }                          \
+    else if (dpl_ <= 2) { KERNEL<2> __VA_ARGS__; }                     \
+    else if (dpl_ <= 4) { KERNEL<4> __VA_ARGS__; }                     \
+    else { KERNEL<8> __VA_ARGS__; }                                    \
+  } while (0)
+
+template <int DPL> static void set_smem_attr(size_t f, size_t b) {
+  cudaFuncSetAttribute(sub_fwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f);
+  cudaFuncSetAttribute(sub_bwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+}
+
+extern "C" {
+
+int subgnn_model_desc_size(void) { return (int)sizeof(subgnn_model_desc); }
+
+int subgnn_model_prep(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  prep_batch_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*d);
+  rc = subgnn_check_launch("prep_batch_kernel");
+  if (rc) return rc;
+  dim3 grid(8, (d->use_n ? 2 * d->L : 0) + 3);
+  transpose_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  return subgnn_check_launch("transpose_weights_kernel");
+}
+
+int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const long long total = (long long)d->L * ((d->use_p ? d->B * d->A_pi + d->A_pb : 0) + (d->use_s ? 2 * d->A_s : 0));
+  if (total == 0) return SUBGNN_OK;
+  q_fwd_kernel<<<sg_grid_for(total, 8, 8), 256, 0, (cudaStream_t)stream>>>(*d);
+  return subgnn_check_launch("q_fwd_kernel");
+}
+
+int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const size_t smem = fwd_smem(*d);
+  const int dpl = (d->D + 31) / 32;
+  if (dpl <= 1) set_smem_attr<1>(smem, bwd_smem(*d)); else if (dpl <= 2) set_smem_attr<2>(smem, bwd_smem(*d));
+  else if (dpl <= 4) set_smem_attr<4>(smem, bwd_smem(*d)); else set_smem_attr<8>(smem, bwd_smem(*d));
+  DISPATCH_DPL(d->D, sub_fwd_kernel, <<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d));
+  return subgnn_check_launch("sub_fwd_kernel");
+}
+
+int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const size_t smem = (size_t)(d->hid + d->h1 + d->h2 + d->n_classes + 8) * sizeof(float);
+  cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mlp_bwd_kernel<<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d);
+  return subgnn_check_launch("mlp_bwd_kernel");
+}
+
+int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const size_t smem = bwd_smem(*d);
+  const int dpl = (d->D + 31) / 32;
+  if (dpl <= 1) set_smem_attr<1>(fwd_smem(*d), smem); else if (dpl <= 2) set_smem_attr<2>(fwd_smem(*d), smem);
+  else if (dpl <= 4) set_smem_attr<4>(fwd_smem(*d), smem); else set_smem_attr<8>(fwd_smem(*d), smem);
+  DISPATCH_DPL(d->D, sub_bwd_kernel, <<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d));
+  return subgnn_check_launch("sub_bwd_kernel");
+}
+
+int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const int groups = (d->use_p ? 2 : 0) + (d->use_s ? 2 : 0);
+  if (groups == 0) return SUBGNN_OK;
+  dim3 grid(8, d->L * groups);
+  q_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  return subgnn_check_launch("q_bwd_kernel");
+}
+
+int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  const int D = d->D;
+  const int blk = 2 * D * D + 2 * D + 1;
+  if (d->use_n && d->use_proj && d->mpn_grads[0]) {
+    for (int l = 0; l < d->L; ++l)
+      for (int side = 0; side < 2; ++side) {
+        const float* dpre = d->Ndpre + (size_t)(l * 2 + side) * d->R_cap * D;
+        const float* hin = d->Nh + (size_t)(l * 2 + side) * d->R_cap * D;
+        const float* agg = d->Nagg + (size_t)(l * 2 + side) * d->R_cap * D;
+        float* gw = d->mpn_grads[0] + (size_t)(2 * l + side) * blk;
+        rc = subgnn_linear_bwd_weight(dpre, D, hin, D, nullptr, gw, 2 * D, gw + 2 * D * D, d->R_cap, D, D, d->meta, stream);
+        if (rc) return rc;
+        rc = subgnn_linear_bwd_weight(dpre, D, agg, D, nullptr, gw + D, 2 * D, nullptr, d->R_cap, D, D, d->meta, stream);
+        if (rc) return rc;
+      }
+  }
+  if (d->lin_gw[0]) {
+    // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)
+    rc = subgnn_linear_bwd_weight(d->dH1, d->h1, d->Z, d->hid, nullptr, d->lin_gw[0], d->hid, d->lin_gb[0], d->B, d->h1, d->hid, nullptr, stream);
+    if (rc) return rc;
+    rc = subgnn_linear_bwd_weight(d->dH2, d->h2, d->H1, d->h1, nullptr, d->lin_gw[1], d->h1, d->lin_gb[1], d->B, d->h2, d->h1, nullptr, stream);
+    if (rc) return rc;
+    rc = subgnn_linear_bwd_weight(d->dlogits, d->n_classes, d->H2, d->h2, nullptr, d->lin_gw[2], d->h2, d->lin_gb[2], d->B, d->n_classes, d->h2,
+                                  nullptr, stream);
+    if (rc) return rc;
+  }
+  return SUBGNN_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,553 @@
+"""Step engine: device-resident tables + one flat parameter arena + the fused CUDA step.
+
+Host-side orchestration of the kernels behind include/subgnn_b200.h for the per-step path
+(SubGNN.py:225-348 forward / training_step, :1156-1164 Adam + backward, Lightning's gradient clipping).
+torch provides device memory, streams, CUDA-graph capture and (for data parallel) the NCCL allreduce;
+all arithmetic happens in libsubgnn_b200.so.
+
+Data layout in HBM:
+  * parameters / gradients / Adam m, v: four flat fp32 arenas with identical offsets; nn.Parameters of the
+    SubGNN module are views into the parameter arena (reference state_dict names and shapes);
+  * per split: ragged component table (valid components only) + per-layer anchor ids and RESOLVED
+    similarities (component x sampled anchor) instead of the reference's dense (n_sub, C, N) slab;
+  * per step: only the batch's subgraph indices travel host -> device.
+"""
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+
+from . import _abi
+from ._abi import ModelDesc, call, ptr
+
+CHANNELS = ('neighborhood', 'position', 'structure')
+SIDES = ('internal', 'border')
+
+
+def _align(n, a=4):
+    return (n + a - 1) // a * a
+
+
+# ------------------------------------------------------------------------------------------------------
+class ParamArena:
+    """Flat fp32 storage for every trainable tensor, laid out for the kernels (see header comment of
+    subgnn_model_desc) and exposed under the reference's state_dict names."""
+
+    def __init__(self, hp, n_nodes, num_classes, hid_dim, n_train=0, C_pad=0, device='cuda'):
+        D, L = hp['node_embed_size'], hp['n_layers']
+        self.D, self.L = D, L
+        self.device = torch.device(device)
+        self.entries = {}      # name -> (offset, shape)
+        off = 0
+
+        def add(name, shape):
+            nonlocal off
+            n = int(np.prod(shape))
+            self.entries[name] = (off, tuple(shape))
+            off += n
+
+        def pad():
+            nonlocal off
+            off = _align(off)
+
+        self.embed_trainable = not hp['freeze_node_embeds']
+        if self.embed_trainable:
+            add('node_embeddings.weight', (n_nodes + 1, D)); pad()
+        self.mpn_base = {}
+        blk = 2 * D * D + 2 * D + 1
+        self.mpn_blk = blk
+        for ch, key in zip(CHANNELS, ('use_neighborhood', 'use_position', 'use_structure')):
+            if not hp[key]:
+                continue
+            pad()
+            self.mpn_base[ch] = off
+            for l in range(L):
+                for side in SIDES:
+                    pre = '%s_mpns.%d.%s.' % (ch, l, side)
+                    add(pre + 'linear.weight', (D, 2 * D))
+                    add(pre + 'linear.bias', (D,))
+                    add(pre + 'linear_position.weight', (1, D))
+                    add(pre + 'linear_position.bias', (1,))
+            pad()
+        H = D
+        self.lstm_layers = hp['lstm_n_layers']
+        self.lstm_off = {}
+        for k in range(self.lstm_layers):
+            din = D if k == 0 else 2 * H
+            pad()
+            self.lstm_off[k] = {}
+            for nm, shape in (('weight_ih', (4 * H, din)), ('weight_hh', (4 * H, H)), ('bias_ih', (4 * H,)), ('bias_hh', (4 * H,))):
+                pad()
+                self.lstm_off[k][nm] = off
+                add('lstm.lstm.%s_l%d' % (nm, k), shape)
+                add('lstm.lstm.%s_l%d_reverse' % (nm, k), shape)      # both directions contiguous
+        pad()
+        add('lstm.linear.weight', (D, 2 * H)); pad()
+        add('lstm.linear.bias', (D,)); pad()
+        for nm, shape in (('lin', (hp['linear_hidden_dim_1'], hid_dim)), ('lin2', (hp['linear_hidden_dim_2'], hp['linear_hidden_dim_1'])),
+                          ('lin3', (num_classes, hp['linear_hidden_dim_2']))):
+            add(nm + '.weight', shape); pad()
+            add(nm + '.bias', (shape[0],)); pad()
+        self.cc_tables = bool(hp['trainable_cc'])
+        if self.cc_tables:
+            for nm in ('N_I', 'N_B', 'S_I', 'S_B', 'P_I', 'P_B'):
+                add('train_%s_cc_embed' % nm, (n_train, C_pad, D)); pad()
+        self.size = _align(off)
+        z = lambda: torch.zeros(self.size, dtype=torch.float32, device=self.device)
+        self.params, self.grads, self.m, self.v = z(), z(), z(), z()
+
+    def view(self, name, which='params'):
+        off, shape = self.entries[name]
+        return getattr(self, which)[off:off + int(np.prod(shape))].view(shape)
+
+    def addr(self, name, which='params'):
+        off, _ = self.entries[name]
+        return getattr(self, which).data_ptr() + 4 * off
+
+    def base_addr(self, off, which='params'):
+        return getattr(self, which).data_ptr() + 4 * off
+
+    def load_state_dict(self, sd):
+        for name in self.entries:
+            if name in sd:
+                self.view(name).copy_(torch.as_tensor(sd[name]).to(self.device, torch.float32).reshape(self.entries[name][1]))
+
+    def state_dict(self):
+        return {k: self.view(k).detach().clone() for k in self.entries}
+
+
+# ------------------------------------------------------------------------------------------------------
+class SplitTables:
+    """Ragged, device-resident form of one split (train / val / test) of the prepared data."""
+
+    def __init__(self, prepared, split, hp, device, graph=None):
+        dev = torch.device(device)
+        L = hp['n_layers']
+        cc = np.asarray(prepared['cc_ids'][split])
+        n_sub, C_pad, Lcc = cc.shape
+        valid = cc[:, :, 0] != 0
+        counts = valid.sum(axis=1)
+        assert (valid[:, :1].all() or n_sub == 0), 'every subgraph needs at least one component'
+        # valid components come first along C (SubGNN.py:596-599 appends the padding)
+        assert all(valid[s, :counts[s]].all() for s in range(n_sub))
+        self.n_sub, self.C_pad = n_sub, C_pad
+        self.n_cc = int(counts.sum())
+        sub_ccptr = np.zeros(n_sub + 1, dtype=np.int64)
+        np.cumsum(counts, out=sub_ccptr[1:])
+        rows = cc[valid]                                   # (n_cc, Lcc) in (sub, c) order
+        lens = (rows != 0).sum(axis=1)
+        nodeptr = np.zeros(self.n_cc + 1, dtype=np.int64)
+        np.cumsum(lens, out=nodeptr[1:])
+        nodes = rows[rows != 0]
+        row_sub = np.repeat(np.arange(n_sub), counts)
+        sub_maxlen = np.zeros(n_sub, dtype=np.int64)
+        np.maximum.at(sub_maxlen, row_sub, lens)
+        self.max_cc_per_sub = int(counts.max()) if n_sub else 1
+        t32 = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+        tf = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float32)).to(dev)
+        self.sub_ccptr, self.sub_maxlen = t32(sub_ccptr), t32(sub_maxlen)
+        self.cc_nodeptr, self.cc_nodes = t32(nodeptr), t32(nodes)
+        self.row_sub = t32(row_sub)
+        self.counts_host = counts
+        lab = np.asarray(prepared['labels'][split])
+        self.multilabel = bool(prepared.get('multilabel', False))
+        self.labels = tf(lab) if self.multilabel else t32(lab.reshape(-1))
+        dense = prepared.get('NP_sim')
+        dense_rows = np.asarray(dense[split])[valid] if dense is not None else None     # (n_cc, N)
+        hop = graph.hop if (graph is not None and dense_rows is None) else None
+
+        def resolve(ids_rows, anchor_row=None):
+            """similarity of every (component row, anchor) pair; ids_rows: (n_lists, A) int ids."""
+            if dense_rows is not None:
+                lists = ids_rows if anchor_row is None else ids_rows[anchor_row]
+                g = np.take_along_axis(dense_rows, np.maximum(lists - 1, 0).astype(np.int64), axis=1)
+                return np.where(lists > 0, g, 0).astype(np.float32)
+            from . import ops
+            assert hop is not None, 'need either prepared["NP_sim"] or a hop table on the graph'
+            ar = None if anchor_row is None else t32(anchor_row)
+            return ops.sp_min_gather(hop, self.cc_nodeptr, self.cc_nodes, t32(ids_rows), ar)
+
+        as_dev = lambda x: x if isinstance(x, torch.Tensor) else tf(x)
+        self.n_ids, self.n_sim = [None, None], [None, None]
+        if hp['use_neighborhood']:
+            for si, key in enumerate(('anchors_neigh_int', 'anchors_neigh_border')):
+                ids = [np.asarray(prepared[key][split][l])[valid] for l in range(L)]
+                self.n_ids[si] = t32(np.stack(ids))
+                self.n_sim[si] = torch.stack([as_dev(resolve(i)) for i in ids]).contiguous()
+        self.p_int_ids = self.p_bor_ids = None
+        self.p_sim = [None, None]
+        if hp['use_position']:
+            pi = [np.asarray(prepared['anchors_pos_int'][split][l]) for l in range(L)]
+            pb = [np.asarray(prepared['anchors_pos_ext'][l]).reshape(1, -1) for l in range(L)]
+            self.p_int_ids, self.p_bor_ids = t32(np.stack(pi)), t32(np.concatenate(pb))
+            self.p_sim[0] = torch.stack([as_dev(resolve(i, row_sub)) for i in pi]).contiguous()
+            self.p_sim[1] = torch.stack([as_dev(resolve(i, np.zeros(self.n_cc, dtype=np.int64))) for i in pb]).contiguous()
+        self.s_sim = [None, None]
+        if hp['use_structure']:
+            for si, key in enumerate(('I_S_sim', 'B_S_sim')):
+                tab = np.asarray(prepared[key][split])[valid]                      # (n_cc, P_tot)
+                self.s_sim[si] = tf(np.stack([tab[:, np.asarray(prepared['anchors_structure'][l][1], dtype=np.int64)] for l in range(L)]))
+
+
+# ------------------------------------------------------------------------------------------------------
+class LstmRunner:
+    """Sequences the LSTM kernels for the structure anchor patches (all layers / sides in one batch:
+    the reference shares one LSTM across them, SubGNN.py:175)."""
+
+    def __init__(self, arena, hp, walks, n_groups, device):
+        """walks: int32 device tensor (n_groups * W, T)."""
+        self.arena, self.hp = arena, hp
+        self.dev = torch.device(device)
+        self.D = self.H = hp['node_embed_size']
+        self.nl = hp['lstm_n_layers']
+        self.W = hp['n_triangular_walks']
+        self.n_groups = n_groups
+        self.walks = walks.contiguous()
+        self.n_seq, self.T = walks.shape
+        self.sum_mode = 1 if hp['lstm_aggregator'] == 'sum' else 0
+        if hp['lstm_aggregator'] not in ('sum', 'last'):
+            raise NotImplementedError(hp['lstm_aggregator'])                       # SubGNN.py:86-87
+        self.p_drop = float(hp['lstm_dropout']) if self.nl > 1 else 0.0
+        H, M = self.H, self.n_seq * self.T
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=self.dev)
+        self.G = [z(M, 8 * H) for _ in range(self.nl)]
+        self.OUT = [z(M + 1, 2 * H) for _ in range(self.nl)]
+        self.CS = [z(M, 2 * H) for _ in range(self.nl)]
+        self.dOUT = [z(M, 2 * H) for _ in range(self.nl)]
+        self.X = [None] + [z(M + 1, 2 * H) for _ in range(1, self.nl)] if self.p_drop > 0 else [None] * self.nl
+        self.whh_t = [z(2 * H * 4 * H) for _ in range(self.nl)]
+        self.bsum = [z(8 * H) for _ in range(self.nl)]
+        self.AGG, self.dAGG = z(self.n_seq, 2 * H), z(self.n_seq, 2 * H)
+        self.Y, self.dY = z(self.n_seq, self.D), z(self.n_seq, self.D)
+        self.EMB, self.dEMB = z(n_groups, self.D), z(n_groups, self.D)
+        t = torch.arange(M, device=self.dev, dtype=torch.int64)
+        tt = t % self.T
+        zero_row = torch.full_like(t, M)
+        self.hprev = [torch.where(tt > 0, t - 1, zero_row).to(torch.int32).contiguous(),
+                      torch.where(tt < self.T - 1, t + 1, zero_row).to(torch.int32).contiguous()]
+        self.ids_flat = self.walks.reshape(-1).contiguous()
+
+    def steps(self, k):
+        top = k == self.nl - 1
+        return (self.T, 1) if (top and not self.sum_mode) else (self.T, self.T)
+
+    def forward(self, E_ptr, training, seed, step_dev, st):
+        a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        for k in range(self.nl):
+            o = a.lstm_off[k]
+            call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
+                 ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
+            if k == 0:
+                call('subgnn_linear_fwd', E_ptr, D, ptr(self.ids_flat), a.base_addr(o['weight_ih']), D, ptr(self.bsum[k]),
+                     ptr(self.G[k]), 8 * H, M, 8 * H, D, 0, st)
+            else:
+                x = self.OUT[k - 1]
+                if self.p_drop > 0 and training:
+                    call('subgnn_dropout', ptr(x), ptr(self.X[k]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+                    x = self.X[k]
+                call('subgnn_linear_fwd', ptr(x), 2 * H, None, a.base_addr(o['weight_ih']), 2 * H, ptr(self.bsum[k]),
+                     ptr(self.G[k]), 8 * H, M, 8 * H, 2 * H, 0, st)
+            sf, sr = self.steps(k)
+            call('subgnn_lstm_recur_fwd', ptr(self.G[k]), ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, self.T, H,
+                 sf, sr, st)
+        call('subgnn_lstm_agg_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_seq, self.T, 2 * H, self.sum_mode, st)
+        call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, a.addr('lstm.linear.bias'),
+             ptr(self.Y), D, self.n_seq, D, 2 * H, 0, st)
+        call('subgnn_group_sum', ptr(self.Y), ptr(self.EMB), self.n_groups, self.W, D, st)
+
+    def backward(self, E_ptr, dE_ptr, training, seed, step_dev, st):
+        """consumes self.dEMB; accumulates into the gradient arena (and dE)."""
+        a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        g = 'grads'
+        call('subgnn_group_bcast', ptr(self.dEMB), ptr(self.dY), self.n_groups, self.W, D, st)
+        call('subgnn_linear_bwd_weight', ptr(self.dY), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
+             a.addr('lstm.linear.bias', g), self.n_seq, D, 2 * H, None, st)
+        call('subgnn_linear_bwd_input', ptr(self.dY), D, a.addr('lstm.linear.weight'), 2 * H, ptr(self.dAGG), 2 * H, None, self.n_seq, D,
+             2 * H, 0, st)
+        call('subgnn_lstm_agg_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_seq, self.T, 2 * H, self.sum_mode, st)
+        for k in range(self.nl - 1, -1, -1):
+            o = a.lstm_off[k]
+            sf, sr = self.steps(k)
+            call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
+                 self.n_seq, self.T, H, sf, sr, st)
+            dG = ptr(self.G[k])
+            din = D if k == 0 else 2 * H
+            if k == 0:
+                x_ptr, ldx, ids = E_ptr, D, ptr(self.ids_flat)
+            else:
+                xin = self.X[k] if (self.p_drop > 0 and training) else self.OUT[k - 1]
+                x_ptr, ldx, ids = ptr(xin), 2 * H, None
+            call('subgnn_linear_bwd_weight', dG, 8 * H, x_ptr, ldx, ids, a.base_addr(o['weight_ih'], g), din, a.base_addr(o['bias_ih'], g),
+                 M, 8 * H, din, None, st)
+            call('subgnn_colsum', dG, 8 * H, a.base_addr(o['bias_hh'], g), M, 8 * H, None, st)
+            for d_ in range(2):
+                call('subgnn_linear_bwd_weight', dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H,
+                     ptr(self.hprev[d_]), a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, None, st)
+            if k > 0:
+                call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), 2 * H, ptr(self.dOUT[k - 1]), 2 * H, None, M, 8 * H,
+                     2 * H, 0, st)
+                if self.p_drop > 0 and training:
+                    call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+            elif dE_ptr:
+                call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), D, dE_ptr, D, ptr(self.ids_flat), M, 8 * H, D, 1, st)
+
+
+# ------------------------------------------------------------------------------------------------------
+class StepContext:
+    """All per-step scratch + the C descriptor for one (split tables, batch size, training flag)."""
+
+    def __init__(self, eng, tables, B, training):
+        hp, a, dev = eng.hp, eng.arena, eng.device
+        D, L = hp['node_embed_size'], hp['n_layers']
+        self.B, self.training, self.tables = B, training, tables
+        self.R_cap = B * tables.max_cc_per_sub
+        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
+        zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
+        h1, h2, K, hid = hp['linear_hidden_dim_1'], hp['linear_hidden_dim_2'], eng.num_classes, eng.hid_dim
+        self.batch_idx = zi(B)
+        self.batch_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+        self.b_rowptr, self.meta = zi(B + 1), zi(4)
+        A_pi, A_pb, A_s = eng.A['pi'], eng.A['pb'], eng.A['s']
+        # gradient-side scratch that must start at zero every step lives in ONE buffer (single fill)
+        n_dq = L * (B * A_pi + A_pb + 2 * A_s)
+        self.zero_scratch = z(_align(n_dq) + 8)
+        self.dq_pi = self.zero_scratch[:L * B * A_pi]
+        self.dq_pb = self.zero_scratch[L * B * A_pi:L * B * A_pi + L * A_pb]
+        self.dq_s = self.zero_scratch[L * (B * A_pi + A_pb):n_dq]
+        self.sumsq = self.zero_scratch[_align(n_dq):_align(n_dq) + 1]
+        self.q_pi, self.q_pb, self.q_s = z(max(L * B * A_pi, 1)), z(max(L * A_pb, 1)), z(max(L * 2 * A_s, 1))
+        self.n_wt = z(max(L * 2 * 2 * D * D, 1))
+        self.lin_wt = [z(h1 * hid), z(h2 * h1), z(K * h2)]
+        self.X0 = z(self.R_cap, D)
+        nN = L if hp['use_neighborhood'] else 0
+        self.Nh, self.Nagg, self.Ndpre = z((nN + 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D)
+        self.Z, self.H1, self.H2, self.logits, self.loss_b = z(B, hid), z(B, h1), z(B, h2), z(B, K), z(B)
+        self.dlogits, self.dH2, self.dH1, self.dZ = z(B, K), z(B, h2), z(B, h1), z(B, hid)
+        self.loss = z(1)
+        d = ModelDesc()
+        t = tables
+        P = lambda x: ptr(x) if x is not None else None
+        d.sub_ccptr, d.sub_maxlen, d.cc_nodeptr, d.cc_nodes = P(t.sub_ccptr), P(t.sub_maxlen), P(t.cc_nodeptr), P(t.cc_nodes)
+        for s in range(2):
+            d.n_ids[s], d.n_sim[s], d.p_sim[s], d.s_sim[s] = P(t.n_ids[s]), P(t.n_sim[s]), P(t.p_sim[s]), P(t.s_sim[s])
+        d.p_int_ids, d.p_bor_ids = P(t.p_int_ids), P(t.p_bor_ids)
+        if t.multilabel:
+            d.labels_multi = P(t.labels)
+        else:
+            d.labels = P(t.labels)
+        d.E = eng.E_ptr()
+        d.dE = eng.dE_ptr() if training else None
+        for ci, ch in enumerate(CHANNELS):
+            if ch in a.mpn_base:
+                d.mpn_params[ci] = a.base_addr(a.mpn_base[ch])
+                d.mpn_grads[ci] = a.base_addr(a.mpn_base[ch], 'grads') if training else None
+        if a.cc_tables:
+            tabs = eng.cc_tables_for(t)
+            for s in range(2):
+                d.cc_tab[s] = tabs[s][0]
+                d.cc_tab_grad[s] = tabs[s][1] if training else None
+        for i, nm in enumerate(('lin', 'lin2', 'lin3')):
+            d.lin_w[i], d.lin_b[i] = a.addr(nm + '.weight'), a.addr(nm + '.bias')
+            d.lin_gw[i] = a.addr(nm + '.weight', 'grads') if training else None
+            d.lin_gb[i] = a.addr(nm + '.bias', 'grads') if training else None
+            d.lin_wt[i] = ptr(self.lin_wt[i])
+        if eng.lstm is not None:
+            d.emb_s, d.d_emb_s = ptr(eng.lstm.EMB), ptr(eng.lstm.dEMB)
+        d.batch_idx, d.step_dev, d.b_rowptr, d.meta = ptr(self.batch_idx), ptr(eng.step_dev), ptr(self.b_rowptr), ptr(self.meta)
+        d.n_wt = ptr(self.n_wt)
+        d.q_pi, d.q_pb, d.q_s = ptr(self.q_pi), ptr(self.q_pb), ptr(self.q_s)
+        d.dq_pi, d.dq_pb, d.dq_s = (self.dq_pi.data_ptr(), self.dq_pb.data_ptr(), self.dq_s.data_ptr())
+        d.X0, d.Nh, d.Nagg, d.Ndpre = ptr(self.X0), ptr(self.Nh), ptr(self.Nagg), ptr(self.Ndpre)
+        d.Z, d.H1, d.H2, d.logits, d.loss_b = ptr(self.Z), ptr(self.H1), ptr(self.H2), ptr(self.logits), ptr(self.loss_b)
+        d.dlogits, d.dH2, d.dH1, d.dZ = ptr(self.dlogits), ptr(self.dH2), ptr(self.dH1), ptr(self.dZ)
+        d.seed = eng.seed
+        d.n_sub, d.n_cc, d.n_nodes = t.n_sub, t.n_cc, eng.n_nodes
+        d.D, d.L, d.hid, d.h1, d.h2, d.n_classes = D, L, hid, h1, h2, K
+        d.use_n, d.use_p, d.use_s = int(hp['use_neighborhood']), int(hp['use_position']), int(hp['use_structure'])
+        d.A_ni, d.A_nb, d.A_pi, d.A_pb, d.A_s = eng.A['ni'], eng.A['nb'], A_pi, A_pb, A_s
+        d.pool_max = 1 if hp['cc_aggregator'] == 'max' else 0
+        d.trainable_cc, d.C_pad = int(a.cc_tables), t.C_pad
+        d.multilabel, d.training, d.use_proj = int(t.multilabel), int(training), int(hp['use_mpn_projection'])
+        d.B, d.R_cap, d.step, d.lin_dropout = B, self.R_cap, 0, float(hp['lin_dropout'])
+        self.desc = d
+        self.dptr = C.addressof(d)
+        self.graph = None
+
+
+class Engine:
+    def __init__(self, hp, prepared, device='cuda', graph=None, seed=0, world_size=1):
+        self.hp = dict(hp)
+        hp = self.hp
+        if hp.get('batch_norm', False) or hp.get('ff_attn', False) or hp.get('norm_pos_struc_embed', False):
+            raise NotImplementedError('batch_norm / ff_attn / norm_pos_struc_embed are off in every shipped config and outside the fused path')
+        if hp['cc_aggregator'] not in ('sum', 'max'):
+            raise NotImplementedError(hp['cc_aggregator'])
+        self.device = torch.device(device)
+        self.prepared, self.graph = prepared, graph
+        self.seed, self.world_size = int(seed), world_size
+        D, L = hp['node_embed_size'], hp['n_layers']
+        self.n_nodes = int(np.asarray(prepared['embeddings']).shape[0]) - 1
+        self.num_classes = int(prepared['num_classes'])
+        self.A = {'ni': hp['n_anchor_patches_N_in'] if hp['use_neighborhood'] else 0, 'nb': hp['n_anchor_patches_N_out'] if hp['use_neighborhood'] else 0,
+                  'pi': hp['n_anchor_patches_pos_in'] if hp['use_position'] else 0, 'pb': hp['n_anchor_patches_pos_out'] if hp['use_position'] else 0,
+                  's': hp['n_anchor_patches_structure'] if hp['use_structure'] else 0}
+        self.hid_dim = D + L * ((2 * D if hp['use_neighborhood'] else 0) + self.A['pi'] + self.A['pb'] + 2 * self.A['s'])   # SubGNN.py:118-147
+        self.tables = {}
+        self.tables['train'] = SplitTables(prepared, 'train', hp, self.device, graph)
+        tt = self.tables['train']
+        self.arena = ParamArena(hp, self.n_nodes, self.num_classes, self.hid_dim, tt.n_sub, tt.C_pad, self.device)
+        emb = torch.as_tensor(np.asarray(prepared['embeddings']), dtype=torch.float32).to(self.device)
+        if self.arena.embed_trainable:
+            self.arena.view('node_embeddings.weight').copy_(emb)
+            self.E_frozen = None
+        else:
+            self.E_frozen = emb.contiguous()
+        self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self.lstm = None
+        if hp['use_structure']:
+            W, T = hp['n_triangular_walks'], hp['random_walk_len']
+            walks = []
+            for key in (2, 3):                                           # internal walks, then border walks (side-major)
+                for l in range(L):
+                    walks.append(np.asarray(prepared['anchors_structure'][l][key]).reshape(-1, T))
+            walks = torch.from_numpy(np.concatenate(walks).astype(np.int32)).to(self.device)
+            self.lstm = LstmRunner(self.arena, hp, walks, 2 * L * self.A['s'], self.device)
+        self.ctx = {}
+        self.eval_cc = {}
+        self.lr = float(hp['learning_rate'])
+        self.grad_clip = float(hp.get('grad_clip', 0.0) or 0.0)
+
+    # ---- pointers --------------------------------------------------------------------------------
+    def E_ptr(self):
+        return self.arena.addr('node_embeddings.weight') if self.arena.embed_trainable else self.E_frozen.data_ptr()
+
+    def dE_ptr(self):
+        return self.arena.addr('node_embeddings.weight', 'grads') if self.arena.embed_trainable else None
+
+    def cc_tables_for(self, tables):
+        a = self.arena
+        if tables is self.tables['train']:
+            return [(a.addr('train_N_I_cc_embed'), a.addr('train_N_I_cc_embed', 'grads')),
+                    (a.addr('train_N_B_cc_embed'), a.addr('train_N_B_cc_embed', 'grads'))]
+        snap = self.eval_cc[id(tables)]
+        return [(snap.data_ptr(), None), (snap.data_ptr(), None)]
+
+    def tables_for(self, split):
+        if split not in self.tables:
+            self.tables[split] = SplitTables(self.prepared, split, self.hp, self.device, self.graph)
+            if self.arena.cc_tables:
+                self.snapshot_eval_cc_tables(split)
+        return self.tables[split]
+
+    def snapshot_eval_cc_tables(self, split):
+        """SubGNN.py:659-668: val/test channel tables are pooled once (prepare_data time)."""
+        t = self.tables[split]
+        cc = torch.from_numpy(np.asarray(self.prepared['cc_ids'][split])).to(self.device)
+        E = self.arena.view('node_embeddings.weight') if self.arena.embed_trainable else self.E_frozen
+        e = E[cc]                                     # setup-time plumbing, not on the step path
+        self.eval_cc[id(t)] = (e.sum(dim=2) if self.hp['cc_aggregator'] == 'sum' else e.max(dim=2)[0]).contiguous()
+
+    def init_cc_tables_from_pooling(self):
+        """SubGNN.py:629-635: the six trainable tables start as the pooled component embeddings."""
+        if not self.arena.cc_tables:
+            return
+        cc = torch.from_numpy(np.asarray(self.prepared['cc_ids']['train'])).to(self.device)
+        E = self.arena.view('node_embeddings.weight') if self.arena.embed_trainable else self.E_frozen
+        e = E[cc]
+        pooled = e.sum(dim=2) if self.hp['cc_aggregator'] == 'sum' else e.max(dim=2)[0]
+        for nm in ('N_I', 'N_B', 'S_I', 'S_B', 'P_I', 'P_B'):
+            self.arena.view('train_%s_cc_embed' % nm).copy_(pooled)
+
+    def context(self, split, B, training):
+        key = (split, B, training)
+        if key not in self.ctx:
+            self.ctx[key] = StepContext(self, self.tables_for(split), B, training)
+        return self.ctx[key]
+
+    # ---- launches --------------------------------------------------------------------------------
+    def _forward_launches(self, c, st):
+        if self.lstm is not None:
+            self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
+        call('subgnn_model_prep', c.dptr, st)
+        call('subgnn_model_q_fwd', c.dptr, st)
+        call('subgnn_model_sub_fwd', c.dptr, st)
+        call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
+
+    def _backward_launches(self, c, st, external_dlogits=False):
+        if external_dlogits:
+            call('subgnn_model_mlp_bwd', c.dptr, st)
+        call('subgnn_model_sub_bwd', c.dptr, st)
+        call('subgnn_model_q_bwd', c.dptr, st)
+        if self.lstm is not None:
+            self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), st)
+        call('subgnn_model_wgrad', c.dptr, st)
+
+    def zero_grads(self, c, st):
+        call('subgnn_fill_zero', ptr(self.arena.grads), self.arena.size, st)
+        call('subgnn_fill_zero', ptr(c.zero_scratch), c.zero_scratch.numel(), st)
+
+    def _optimizer_launches(self, c, st):
+        a = self.arena
+        clip = self.grad_clip
+        call('subgnn_grad_sumsq', ptr(a.grads), a.size, c.sumsq.data_ptr(), st)
+        call('subgnn_adam_step', ptr(a.params), ptr(a.grads), ptr(a.m), ptr(a.v), a.size, self.lr, 0.9, 0.999, 1e-8, ptr(self.step_dev),
+             c.sumsq.data_ptr(), clip, 1.0 / self.world_size, st)
+
+    def set_batch(self, c, indices):
+        """host -> device copy of the step's only input: the subgraph indices."""
+        idx = torch.as_tensor(np.asarray(indices), dtype=torch.int32)
+        assert idx.numel() == c.B
+        c.batch_host.copy_(idx)
+        c.batch_idx.copy_(c.batch_host, non_blocking=True)
+
+    # ---- public API --------------------------------------------------------------------------------
+    def forward(self, split, indices, training=False):
+        """logits (B, K) for the subgraphs ``indices`` of ``split`` (SubGNN.forward)."""
+        c = self.context(split, len(indices), training)
+        self.set_batch(c, indices)
+        st = _abi.stream_ptr()
+        self._forward_launches(c, st)
+        return c.logits, c.loss
+
+    def backward(self, split, B, training=True, external_dlogits=None):
+        c = self.context(split, B, training)
+        st = _abi.stream_ptr()
+        if external_dlogits is not None:
+            c.dlogits.copy_(external_dlogits)
+        self.zero_grads(c, st)
+        self._backward_launches(c, st, external_dlogits is not None)
+
+    def allreduce_grads(self):
+        if self.world_size > 1:
+            import torch.distributed as dist
+            dist.all_reduce(self.arena.grads)
+
+    def train_step(self, indices, use_graph=False):
+        """one optimisation step on the train split: forward, loss, backward, clip, Adam (in place)."""
+        c = self.context('train', len(indices), True)
+        self.set_batch(c, indices)
+        st = _abi.stream_ptr()
+        if use_graph and self.world_size == 1:
+            if c.graph is None:
+                self._step_launches(c, st)                     # warm-up (sets function attributes) — counts as a step
+                torch.cuda.synchronize()
+                self.set_batch(c, indices)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._step_launches(c, _abi.stream_ptr())
+                c.graph = g
+                return c.loss
+            c.graph.replay()
+            return c.loss
+        self._step_launches(c, st)
+        return c.loss
+
+    def _step_launches(self, c, st):
+        call('subgnn_inc_step', ptr(self.step_dev), st)
+        self.zero_grads(c, st)
+        self._forward_launches(c, st)
+        self._backward_launches(c, st)
+        if self.world_size > 1:
+            self.allreduce_grads()
+        self._optimizer_launches(c, st)
