@@ -1,0 +1,388 @@
+#!/usr/bin/env python
+"""bench.py — subgraphs/sec per train step (all 3 channels) of the B200-native SubGNN hot path.
+
+    python bench.py --gpus N --steps K --warmup W [--workload ppi_bp] [--impl reference]
+
+One "step" = forward + loss + backward + gradient clipping + Adam on one batch of synthetic subgraphs
+(batch size from the reference's hyper-parameter file).  Default workload: the PPI-BP-shaped all-channel
+configuration (BASELINE.json configs[2], "all channels on 1 B200"); weak scaling for N > 1 (every rank
+steps its own batch, gradients all-reduced over NCCL).  Prints ONE JSON line on rank 0.
+
+--impl reference times the CPU oracle port of the reference's per-step path (oracle/model.py; the reference
+itself is pure Python and absent on the GPU box) on a bounded sample of the same workload.
+"""
+import argparse
+import contextlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+METRIC = 'subgraphs_per_sec_train_step_all_channels'
+UNIT = 'subgraphs/s'
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=50)
+    ap.add_argument('--warmup', type=int, default=5)
+    ap.add_argument('--workload', default='ppi_bp')
+    ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
+    ap.add_argument('--batch-size', type=int, default=0, help='override the per-GPU batch (default: reference hparams)')
+    ap.add_argument('--no-graph', action='store_true')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    return ap.parse_args()
+
+
+# ----------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region (B200_PROFILING.md recipe)."""
+    Q = 'index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,' \
+        'clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap'
+
+    def __init__(self, gpu_index):
+        self.gpu, self.rows, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.gpu), '--query-gpu=' + self.Q, '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(',')])
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 8 and r[1].replace('.', '').isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 8 and r[2].replace('.', '').isdigit()]
+        names = ['hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap']
+        reasons = [n for i, n in enumerate(names) if any(len(r) >= 8 and r[4 + i].lower().startswith('active') for r in self.rows)]
+        return {'sm_mhz': float(np.median(sm)) if sm else None, 'sm_max_mhz': max(mx) if mx else None, 'reasons': reasons,
+                'samples': len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------
+def build_workload(name, device, batch_override=0):
+    from subgnn_b200 import prepare as prep
+    from subgnn_b200 import synth
+    hp, g, subs, labs, emb = synth.make_workload(name, seed=42, device=device)
+    if batch_override:
+        hp['batch_size'] = batch_override
+    t0 = time.time()
+    prepared = prep.prepare(hp, g, subs, labs, emb, seed=0, splits=('train',), num_classes=synth.WORKLOADS[name]['n_classes'])
+    import torch
+    torch.cuda.synchronize()
+    return hp, g, prepared, time.time() - t0
+
+
+def batches_for(n_train, B, n_steps, rank, world, seed=0):
+    """contiguous per-rank shards of a shuffled epoch stream (drop_last, SubGNN.py:1126-1127)."""
+    rs = np.random.RandomState(seed)
+    per_step = B * world
+    out, perm, pos = [], rs.permutation(n_train), 0
+    for _ in range(n_steps):
+        if pos + per_step > n_train:
+            perm, pos = rs.permutation(n_train), 0
+        if per_step > n_train:                       # tiny data sets: sample with replacement across ranks
+            chunk = rs.randint(n_train, size=per_step)
+        else:
+            chunk = perm[pos:pos + per_step]
+            pos += per_step
+        out.append(np.sort(chunk[rank * B:(rank + 1) * B]))
+    return out
+
+
+# algorithmic bytes / flops per launch of the entry points that can dominate a step (DESIGN.md "Roofline")
+def algorithmic_work(eng, ctx):
+    hp, t = eng.hp, ctx.tables
+    D, L, B = hp['node_embed_size'], hp['n_layers'], ctx.B
+    R = int(ctx.meta[0].item())
+    idx = ctx.batch_idx.cpu().numpy()
+    ccptr, nodeptr = t.sub_ccptr.cpu().numpy(), t.cc_nodeptr.cpu().numpy()
+    n_nodes = int(sum(nodeptr[ccptr[i + 1]] - nodeptr[ccptr[i]] for i in idx))
+    A = eng.A
+    hid, h1, h2, K = eng.hid_dim, hp['linear_hidden_dim_1'], hp['linear_hidden_dim_2'], eng.num_classes
+    useN = 1 if hp['use_neighborhood'] else 0
+    mlp_w = 4 * (hid * h1 + h1 * h2 + h2 * K)
+    fwd = (n_nodes * (4 + 4 * D) + R * 4 * D                                             # pooling: ids + rows, X0 write
+           + useN * R * L * (A['ni'] + A['nb']) * (8 + 4 * D)                            # N gathers: id + sim + row
+           + useN * R * L * 2 * (2 * 4 * D) + useN * L * 2 * (2 * D * D + D) * 4         # Nagg/Nh writes, weights (once)
+           + R * L * (A['pi'] + A['pb'] + 2 * A['s']) * 4                                # P/S similarities
+           + L * (B * A['pi'] + A['pb'] + 2 * A['s']) * 4                                # q
+           + B * hid * 4 + mlp_w + B * (h1 + h2 + K) * 4 * 2)                            # Z, MLP weights (once), activations
+    bwd = (B * hid * 4
+           + useN * R * L * 2 * (3 * 4 * D) + useN * L * 2 * 2 * D * D * 4               # Nh read, dpre write, weights
+           + useN * R * L * (A['ni'] + A['nb']) * (8 + 8 * D)                            # scatter: id + sim + row RMW
+           + n_nodes * (4 + 8 * D)                                                        # pooling scatter RMW
+           + R * L * (A['pi'] + A['pb'] + 2 * A['s']) * 4 + L * (B * A['pi'] + A['pb'] + 2 * A['s']) * 8)
+    n_par = eng.arena.size
+    work = {'subgnn_model_sub_fwd': ('hbm', fwd), 'subgnn_model_sub_bwd': ('hbm', bwd),
+            'subgnn_adam_step': ('hbm', 28 * n_par), 'subgnn_grad_sumsq': ('hbm', 4 * n_par), 'subgnn_fill_zero': ('hbm', 4 * n_par)}
+    if eng.lstm is not None:
+        ls = eng.lstm
+        M, H = ls.n_seq * ls.T, ls.H
+        flops_in = sum(2 * M * 8 * H * (D if k == 0 else 2 * H) for k in range(ls.nl))
+        work['subgnn_linear_fwd'] = ('tensor', flops_in / ls.nl)
+        work['subgnn_linear_bwd_weight'] = ('tensor', flops_in / ls.nl)
+        work['subgnn_linear_bwd_input'] = ('tensor', flops_in / ls.nl)
+        work['subgnn_lstm_recur_fwd'] = ('tensor', 2 * 2 * M * 4 * H * H)
+        work['subgnn_lstm_recur_bwd'] = ('tensor', 2 * 2 * M * 4 * H * H)
+    return work, {'rows': R, 'component_nodes': n_nodes}
+
+
+def measured_peaks():
+    f = ROOT / 'MEASURED_PEAKS.json'
+    if f.exists():
+        p = json.loads(f.read_text())
+        return {'hbm': p['hbm_gbs'], 'tensor': p['bf16_tflops'], 'tensor_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'src': 'measured'}
+    return {'hbm': 6650.0, 'tensor': 1590.0, 'tensor_sustained': 1400.0, 'src': 'fallback'}
+
+
+# ----------------------------------------------------------------------------------------------------
+def cpu_baseline(hp, g, prepared, seconds, n_threads=None, anomaly=False):
+    """The oracle port of the reference step on a bounded sample: 4 batches of the workload's train split,
+    cycled for ~`seconds` of CPU work.  Returns (subgraphs/s incl. batch assembly, dict)."""
+    import torch
+    from oracle.model import OracleSubGNN
+    from subgnn_b200 import prepare as prep
+    if n_threads:
+        torch.set_num_threads(n_threads)
+    B = hp['batch_size']
+    n_train = len(prepared['labels']['train'])
+    n_sample = min(n_train, 4 * B)
+    sample = prep.prepared_subset(prepared, g, 'train', np.arange(n_sample))
+    torch.manual_seed(0)
+    model = OracleSubGNN(hp, sample)
+    opt = torch.optim.Adam(model.parameters(), lr=hp['learning_rate'])
+    model.train()
+    B = min(B, n_sample)
+    order = [np.arange(i, i + B) for i in range(0, n_sample - B + 1, B)]
+    n_done, t_used = 0, 0.0
+
+    def one(idx):
+        batch = model.make_batch('train', idx)                          # SubgraphDataset + _pad_collate
+        loss, _ = model.training_step(batch)
+        opt.zero_grad()
+        loss.backward(retain_graph=True)
+        torch.nn.utils.clip_grad_norm_(model.parameters(), hp['grad_clip'])
+        opt.step()
+        return float(loss.detach())
+
+    with torch.autograd.set_detect_anomaly(anomaly):
+        one(order[0])                                                   # warm-up
+        t0 = time.perf_counter()
+        i = 0
+        while True:
+            one(order[i % len(order)])
+            n_done += 1
+            i += 1
+            t_used = time.perf_counter() - t0
+            if t_used >= seconds or n_done >= 200:
+                break
+    value = n_done * B / t_used
+    info = {'value': value, 'unit': UNIT, 'cores': torch.get_num_threads(), 'kind': 'port',
+            'sample': '%d steps of batch %d over the first %d train subgraphs of %s (oracle/model.py: reference op sequence incl. '
+                      'SubgraphDataset/_pad_collate batch assembly, anomaly detection %s), %.1f s' %
+                      (n_done, B, n_sample, 'the workload', 'on' if anomaly else 'off', t_used),
+            'ms_per_step': 1e3 * t_used / n_done}
+    return value, info
+
+
+# ----------------------------------------------------------------------------------------------------
+def main():
+    args = parse()
+    rank = int(os.environ.get('RANK', 0))
+    local_rank = int(os.environ.get('LOCAL_RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    import torch
+
+    if args.impl == 'reference':
+        if rank != 0:
+            return 0
+        dev = 'cuda:0' if torch.cuda.is_available() else None
+        if dev is None:
+            print(json.dumps({'impl': 'reference', 'unavailable': 'workload preparation needs the CUDA setup kernels; no GPU visible'}))
+            return 0
+        torch.cuda.set_device(0)
+        hp, g, prepared, _ = build_workload(args.workload, dev, args.batch_size)
+        secs = min(120.0, max(5.0, 1.0 * args.steps)) if args.steps != 50 else 20.0
+        value, info = cpu_baseline(hp, g, prepared, secs, n_threads=os.cpu_count())
+        line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+                'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+                'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_gpu': hp['batch_size'], 'channels': 'N+P+S'},
+                'cpu_baseline': info, 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+        print(json.dumps(line))
+        return 0
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    torch.cuda.set_device(local_rank)
+    dev = 'cuda:%d' % local_rank
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group('nccl', device_id=torch.device(dev))
+    from subgnn_b200 import _abi
+    from subgnn_b200.engine import Engine
+
+    hp, g, prepared, prep_s = build_workload(args.workload, dev, args.batch_size)
+    B = hp['batch_size']
+    eng = Engine(hp, prepared, device=dev, graph=g, seed=1234, world_size=world)
+    eng.init_parameters(seed=7)
+    n_train = len(prepared['labels']['train'])
+    K, W = args.steps, max(args.warmup, 3)
+    use_graph = not args.no_graph
+    batches = batches_for(n_train, B, W + K + 2, rank, world)
+
+    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- warm-up (includes graph capture) ----
+    for i in range(W):
+        eng.train_step(batches[i], use_graph=use_graph)
+    if use_graph:
+        eng.train_step(batches[W], use_graph=True)
+    barrier()
+    # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between ----
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
+    n0 = _abi.lib.subgnn_launch_count()
+    barrier()
+    wall0 = time.perf_counter()
+    for i in range(K):
+        flush.zero_()
+        idx = batches[W + 1 + i]
+        evs[i][0].record()
+        eng.train_step(idx, use_graph=use_graph)
+        evs[i][1].record()
+    barrier()
+    wall = time.perf_counter() - wall0
+    clocks = sampler.stop()
+    step_ms = np.array([a.elapsed_time(b) for a, b in evs])
+    total_ms = float(step_ms.sum())
+    launches = int(_abi.lib.subgnn_launch_count() - n0)
+    if use_graph:
+        launches = int(getattr(eng, 'launches_per_step', 0)) * K
+    if world > 1:
+        tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        total_ms = float(tm.item())
+    value = world * B * K / (total_ms * 1e-3)
+    final_loss = float(eng.context('train', B, True).loss.item())
+
+    # ---- e2e: the user-facing call with host buffers; H2D of the step inputs + D2H of the loss inside the timed region ----
+    from subgnn_b200.SubGNN import SubGNN
+    model = SubGNN.from_engine(eng)
+    host_batches = [{'subgraph_idx': torch.from_numpy(b.astype(np.int64)).view(-1, 1).pin_memory()} for b in batches[W + 1:W + 1 + K]]
+    model.training_step_fused(host_batches[0], use_graph=use_graph)
+    barrier()
+    t0 = time.perf_counter()
+    for hb in host_batches:
+        out = model.training_step_fused(hb, use_graph=use_graph)
+        _ = float(out['loss'])                                        # device -> host read of the step result
+    barrier()
+    e2e_s = time.perf_counter() - t0
+    if world > 1:
+        tm = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
+        e2e_s = float(tm.item())
+    e2e = {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 4,
+           'note': 'SubGNN.training_step_fused(host batch dict): pinned H2D of the subgraph indices, fused step, loss.item(); all tables are '
+                   'device-resident after prepare_data (the reference re-uploads the dense similarity slab every step)'}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return 0
+
+    # ---- instrumented pass: per-entry-point device time with CUDA events (eager launches, same batches) ----
+    prof = {}
+
+    @contextlib.contextmanager
+    def hook(name):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        yield
+        b.record()
+        prof.setdefault(name, []).append((a, b))
+
+    n_prof = min(K, 10)
+    for i in range(n_prof):
+        flush.zero_()
+        torch.cuda.synchronize()
+        _abi._profile_hook = hook
+        eng.world_size_saved, eng.world_size = eng.world_size, 1
+        eng.train_step(batches[W + 1 + i], use_graph=False)
+        eng.world_size = eng.world_size_saved
+        _abi._profile_hook = None
+    torch.cuda.synchronize()
+    per_entry = {k: (sum(a.elapsed_time(b) for a, b in v) / n_prof, len(v) // n_prof) for k, v in prof.items()}
+    ctx = eng.context('train', B, True)
+    work, stats = algorithmic_work(eng, ctx)
+    peaks = measured_peaks()
+    top = max(per_entry, key=lambda k: per_entry[k][0])
+    breakdown = {k: {'ms_per_step': round(v[0], 4), 'calls_per_step': v[1]} for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1][0])}
+
+    def roof(name):
+        ms, calls = per_entry[name]
+        if name not in work:
+            return None
+        bound, amount = work[name]
+        per_launch_s = ms * 1e-3 / calls
+        if bound == 'hbm':
+            ach = amount / per_launch_s / 1e9
+            return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'],
+                    'traffic': None, 'algorithmic_bytes_per_launch': amount, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
+        ach = amount / per_launch_s / 1e12
+        return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
+                'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount,
+                'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'], 'note': 'fp32 FFMA kernel measured against the bf16 tensor peak'}
+
+    roofline = roof(top) or roof('subgnn_model_sub_fwd')
+    roofline['others'] = [r for r in (roof(k) for k in ('subgnn_model_sub_fwd', 'subgnn_model_sub_bwd', 'subgnn_adam_step') if k in per_entry and k != top) if r]
+
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        _, cpu = cpu_baseline(hp, g, prepared, args.cpu_seconds)
+
+    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': total_ms / K,
+            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': args.workload + '-shaped synthetic (SURVEY 8d), all channels N+P+S' if args.workload != 'cutratio' else 'cutratio-shaped, S only',
+                       'batch_per_gpu': B, 'global_batch': B * world, 'n_layers': hp['n_layers'], 'node_embed_size': hp['node_embed_size'],
+                       'graph_nodes': g.n_nodes, 'graph_edges': int(g.col.numel() // 2), 'train_subgraphs': n_train, 'parallelism': 'dp%d' % world,
+                       'l2': 'flushed between timed iterations (256 MB write)', 'cuda_graph': use_graph, 'rows_last_batch': stats['rows'],
+                       'prepare_data_s': round(prep_s, 2)},
+            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
+            'breakdown_ms': breakdown, 'final_loss': final_loss, 'wall_s_timed_region': wall}
+    print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == '__main__':
+    sys.exit(main())

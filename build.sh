@@ -10,9 +10,10 @@ for f in $SRC; do
   o=build/$(basename ${f%.cu}).o
   OBJS="$OBJS $o"
   if [ ! -f $o ] || [ $f -nt $o ] || [ subgnn_b200/csrc/common.cuh -nt $o ] || [ include/subgnn_b200.h -nt $o ]; then
-    nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA} -c $f -o $o &
+    rm -f $o; nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA} -c $f -o $o &
   fi
 done
 wait
+for o in $OBJS; do [ -f $o ] || { echo "compile failed: $o"; exit 1; }; done
 nvcc -shared -gencode arch=compute_100a,code=sm_100a -o $OUT $OBJS -lcudart
 echo built $OUT

@@ -30,6 +30,8 @@ extern "C" {
 const char* subgnn_last_error(void);
 int subgnn_abi_version(void);
 int subgnn_device_sm_count(void);
+/* number of kernels this library has launched (or recorded into a CUDA graph under capture) so far */
+unsigned long long subgnn_launch_count(void);
 
 /* ---- (1) anchor_patch_samplers.py ------------------------------------------------------------- */
 
@@ -88,6 +90,11 @@ int subgnn_degree_seq(const int* rowptr, const int* col, const int* rows, int n_
 int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
                      int max_len_a, int max_len_b, int mode, float* out, void* stream);
 
+
+/* prepare_dataset/precompute_graph_metrics.py:20-26 get_shortest_path for sources [src_begin, src_end): BFS hop counts
+ * into the uint8 table (0 = self / unreachable), i.e. the content of shortest_path_matrix.npy (SubGNN.py:848). */
+int subgnn_hop_table(const int* rowptr, const int* col, int n_nodes, int src_begin, int src_end, unsigned char* hop,
+                     long long hop_stride, void* stream);
 
 /* ---- dense building blocks (gemm.cu) ------------------------------------------------------------- */
 

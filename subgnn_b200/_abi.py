@@ -35,6 +35,7 @@ SIGNATURES = {
     'subgnn_sp_min_gather': [P, LL, P, P, I, P, P, I, P, P],
     'subgnn_degree_seq': [P, P, P, I, I, I, P, P, P],
     'subgnn_dtw_batch': [P, P, I, I, P, P, I, I, I, I, I, P, P],
+    'subgnn_hop_table': [P, P, I, I, I, P, LL, P],
     'subgnn_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],
     'subgnn_linear_bwd_input': [P, I, P, I, P, I, P, I, I, I, I, P],
     'subgnn_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P, P],
@@ -65,6 +66,7 @@ _OTHER = {
     'subgnn_abi_version': ([], I),
     'subgnn_device_sm_count': ([], I),
     'subgnn_model_desc_size': ([], I),
+    'subgnn_launch_count': ([], U64),
 }
 
 
@@ -102,8 +104,15 @@ def stream_ptr():
     return torch.cuda.current_stream().cuda_stream
 
 
+_profile_hook = None   # set by bench.py's instrumented pass: hook(name) -> context manager timing one entry point
+
+
 def call(name, *args):
-    rc = getattr(lib, name)(*args)
+    if _profile_hook is not None:
+        with _profile_hook(name):
+            rc = getattr(lib, name)(*args)
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise SubgnnError('%s failed (%d): %s' % (name, rc, lib.subgnn_last_error().decode()))
 

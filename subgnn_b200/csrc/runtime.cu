@@ -13,7 +13,10 @@ void subgnn_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+static unsigned long long g_launches = 0;
+
 int subgnn_check_launch(const char* what) {
+  ++g_launches;   // one call per kernel launch (also while a CUDA graph is being captured)
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     subgnn_set_error("%s: %s", what, cudaGetErrorString(e));
@@ -36,4 +39,5 @@ extern "C" {
 const char* subgnn_last_error(void) { return g_err; }
 int subgnn_abi_version(void) { return SUBGNN_ABI_VERSION; }
 int subgnn_device_sm_count(void) { return subgnn_sm_count(); }
+unsigned long long subgnn_launch_count(void) { return g_launches; }
 }

@@ -418,6 +418,26 @@ class Engine:
         self.lr = float(hp['learning_rate'])
         self.grad_clip = float(hp.get('grad_clip', 0.0) or 0.0)
 
+    def init_parameters(self, seed=0):
+        """Random initialisation with torch's default laws for the reference's modules: nn.Linear
+        U(-1/sqrt(fan_in), 1/sqrt(fan_in)) for weight and bias, nn.LSTM U(-1/sqrt(H), 1/sqrt(H)); the embedding
+        table keeps the supplied (pre-trained / synthetic) rows; trainable cc tables start from the pooling."""
+        gen = torch.Generator(device=self.device)
+        gen.manual_seed(int(seed))
+        a = self.arena
+        H = self.hp['node_embed_size']
+        for name, (off, shape) in a.entries.items():
+            if name == 'node_embeddings.weight' or name.endswith('_cc_embed'):
+                continue
+            if name.startswith('lstm.lstm.'):
+                bound = 1.0 / math.sqrt(H)
+            elif name.endswith('.weight'):
+                bound = 1.0 / math.sqrt(shape[-1])
+            else:                                           # bias: fan_in of the matching weight
+                bound = 1.0 / math.sqrt(a.entries[name[:-4] + 'weight'][1][-1])
+            a.view(name).copy_((torch.rand(shape, generator=gen, device=self.device) * 2 - 1) * bound)
+        self.init_cc_tables_from_pooling()
+
     # ---- pointers --------------------------------------------------------------------------------
     def E_ptr(self):
         return self.arena.addr('node_embeddings.weight') if self.arena.embed_trainable else self.E_frozen.data_ptr()
@@ -524,30 +544,43 @@ class Engine:
             dist.all_reduce(self.arena.grads)
 
     def train_step(self, indices, use_graph=False):
-        """one optimisation step on the train split: forward, loss, backward, clip, Adam (in place)."""
+        """one optimisation step on the train split: forward, loss, backward, [allreduce,] clip, Adam (in place).
+        With use_graph the launches are captured once into CUDA graphs (two halves around the NCCL allreduce when
+        data parallel) and replayed: the per-step host work is one pinned copy of the indices + graph launches."""
         c = self.context('train', len(indices), True)
         self.set_batch(c, indices)
         st = _abi.stream_ptr()
-        if use_graph and self.world_size == 1:
-            if c.graph is None:
-                self._step_launches(c, st)                     # warm-up (sets function attributes) — counts as a step
-                torch.cuda.synchronize()
-                self.set_batch(c, indices)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._step_launches(c, _abi.stream_ptr())
-                c.graph = g
-                return c.loss
-            c.graph.replay()
+        if not use_graph:
+            self._grad_launches(c, st)
+            self.allreduce_grads()
+            self._optimizer_launches(c, st)
             return c.loss
-        self._step_launches(c, st)
+        if c.graph is None:
+            self._grad_launches(c, st)                         # warm-up (sets function attributes) — a real step
+            self.allreduce_grads()
+            self._optimizer_launches(c, st)
+            torch.cuda.synchronize()
+            n0 = _abi.lib.subgnn_launch_count()
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._grad_launches(c, _abi.stream_ptr())
+            with torch.cuda.graph(g2):
+                self._optimizer_launches(c, _abi.stream_ptr())
+            c.graph = (g1, g2)
+            self.launches_per_step = int(_abi.lib.subgnn_launch_count() - n0)
+            return c.loss
+        c.graph[0].replay()
+        self.allreduce_grads()
+        c.graph[1].replay()
         return c.loss
 
-    def _step_launches(self, c, st):
+    def _grad_launches(self, c, st):
         call('subgnn_inc_step', ptr(self.step_dev), st)
         self.zero_grads(c, st)
         self._forward_launches(c, st)
         self._backward_launches(c, st)
-        if self.world_size > 1:
-            self.allreduce_grads()
+
+    def _step_launches(self, c, st):
+        self._grad_launches(c, st)
+        self.allreduce_grads()
         self._optimizer_launches(c, st)

@@ -69,7 +69,7 @@ def sp_min_dense(hop, cc_ptr, cc_nodes):
     n_rows = cc_ptr.numel() - 1
     N = hop.shape[1]
     out = torch.empty((n_rows, N), dtype=torch.float32, device=hop.device)
-    call('subgnn_sp_min_dense', ptr(hop), N, hop.stride(0), ptr(cc_ptr), ptr(cc_nodes), n_rows, ptr(out), stream_ptr())
+    call('subgnn_sp_min_dense', hop.data_ptr(), N, hop.stride(0), ptr(cc_ptr), ptr(cc_nodes), n_rows, ptr(out), stream_ptr())
     return out
 
 
@@ -78,7 +78,7 @@ def sp_min_gather(hop, cc_ptr, cc_nodes, anchors, anchor_row=None):
     n_rows = cc_ptr.numel() - 1
     A = anchors.shape[-1]
     out = torch.empty((n_rows, A), dtype=torch.float32, device=hop.device)
-    call('subgnn_sp_min_gather', ptr(hop), hop.stride(0), ptr(cc_ptr), ptr(cc_nodes), n_rows, ptr(anchors), ptr(anchor_row), A, ptr(out),
+    call('subgnn_sp_min_gather', hop.data_ptr(), hop.stride(0), ptr(cc_ptr), ptr(cc_nodes), n_rows, ptr(anchors), ptr(anchor_row), A, ptr(out),
          stream_ptr())
     return out
 
@@ -103,3 +103,13 @@ def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_l
     call('subgnn_dtw_batch', ptr(seqA), ptr(lenA), nA, sA, ptr(seqB), ptr(lenB), nB, sB, max_len_a, max_len_b, int(mode), ptr(out),
          stream_ptr())
     return out
+
+
+def hop_table(g):
+    """uint8 (N, N) BFS hop table on the device (0 = self / unreachable); also stored on the graph."""
+    N = g.n_nodes
+    stride = (N + 15) // 16 * 16
+    buf = torch.empty((N, stride), dtype=torch.uint8, device=g.device)
+    call('subgnn_hop_table', ptr(g.rowptr), ptr(g.col), N, 0, N, ptr(buf), stride, stream_ptr())
+    g.hop = buf[:, :N]
+    return g.hop
