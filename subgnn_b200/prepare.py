@@ -74,7 +74,7 @@ def structure_similarities(g, cc_ids, patches, mode=ops.DTW_FASTDTW_R1):
     cc = np.asarray(cc_ids)
     n_sub, C, Lcc = cc.shape
     flat = torch.from_numpy(cc.reshape(n_sub * C, Lcc)).to(dev)
-    pt = torch.as_tensor(np.asarray(patches)).to(dev)
+    pt = (patches if isinstance(patches, torch.Tensor) else torch.as_tensor(np.asarray(patches))).to(dev)
     out = []
     for internal in (True, False):
         sa, la = ops.degree_seq(g, flat, internal)
