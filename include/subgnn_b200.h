@@ -205,6 +205,16 @@ int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);
 /* weight gradients of the N-channel MPN projections and the MLP */
 int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream);
 
+/* ---- stand-alone SG_MPN.forward (mpn.cu): subgraph_mpn.py:36-131,176-231 on the reference's materialised inputs ----
+ * cc (R x D), anchor_embeds (R x A x D), sims (R x n_opt), mask (R x A, uint8).  Exactly one of anchor_ids (R x A: first node id
+ * of every anchor patch; similarity column = id - 1, N/P channels :92-94) and sim_index (A: similarity column per anchor, S channel
+ * :96-99) is non-NULL.  Outputs: cat (R x 2D) = [cc | agg], pos_lin (R x A) = w_p . msg + b_p, s_eff (R x A) = mask * sim. */
+int subgnn_mpn_fwd(const float* cc, const float* anchor_embeds, const float* sims, int n_opt, const int* anchor_ids, const int* sim_index,
+                   const unsigned char* mask, const float* wp, const float* bp, float* cat, float* pos_lin, float* s_eff, int R, int A,
+                   int D, void* stream);
+int subgnn_mpn_bwd(const float* anchor_embeds, const float* s_eff, const float* dcat, const float* dpos, const float* wp, float* dx, float* dwp,
+                   float* dbp, int R, int A, int D, void* stream);
+
 /* ---- optimizer (optim.cu): SubGNN.py:1156-1164 Adam + Lightning's clip_grad_norm_ ---------------------- */
 int subgnn_fill_zero(float* p, long long n, void* stream);
 int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq /* [1], accumulated */, void* stream);

@@ -20,7 +20,8 @@ import numpy as np
 import torch
 import torch.nn as nn
 
-from . import PAD_VALUE
+from . import PAD_VALUE, _abi
+from ._abi import call, ptr
 from .engine import Engine
 from .graph import DeviceGraph
 
@@ -48,6 +49,80 @@ def read_subgraphs(sub_f):
     if len(out['val'][0]) < len(out['test'][0]):                       # subgraph_utils.py:89-90
         out['val'], out['test'] = out['test'], out['val']
     return out, multilabel, len(labels)
+
+
+class _LSTMFunction(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, module, x, *params):
+        runner, arena = module._runner_for(x.shape[0], x.shape[1])
+        module._pack(arena, params)
+        xc = x.contiguous().float()
+        st = _abi.stream_ptr()
+        call('subgnn_inc_step', ptr(module._step), st)
+        runner.forward(None, module.training, module._seed, ptr(module._step), st, dense_x=xc.view(-1, x.shape[2]))
+        ctx.module, ctx.runner, ctx.arena, ctx.training = module, runner, arena, module.training
+        ctx.x_shape = x.shape
+        return runner.Y.clone()
+
+    @staticmethod
+    def backward(ctx, dy):
+        m, runner, arena = ctx.module, ctx.runner, ctx.arena
+        st = _abi.stream_ptr()
+        call('subgnn_fill_zero', ptr(arena.grads), arena.size, st)
+        runner.dEMB.copy_(dy.contiguous())
+        dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dy.device)
+        runner.backward(None, None, ctx.training, m._seed, ptr(m._step), st, dense_dx=dx.view(-1, ctx.x_shape[2]))
+        return (None, dx) + tuple(arena.view(n, 'grads').clone() for n in m._arena_names)
+
+
+class LSTM(nn.Module):
+    """SubGNN.py:60-88 — bidirectional LSTM walk encoder with a linear head, same constructor and parameter names
+    (``lstm.weight_ih_l0`` ... ``linear.weight``); the computation runs on csrc/lstm.cu + csrc/gemm.cu."""
+
+    def __init__(self, n_features, h, dropout=0.0, num_layers=1, batch_first=True, aggregator='last'):
+        super().__init__()
+        if h != n_features:
+            raise NotImplementedError('the walk encoder is built for h == n_features (SubGNN.py:175)')
+        if aggregator not in ('last', 'sum'):
+            raise NotImplementedError                                                              # SubGNN.py:86-87
+        self.num_layers, self.aggregator, self.dropout, self.h = num_layers, aggregator, dropout, h
+        self.lstm = nn.LSTM(n_features, h, num_layers=num_layers, batch_first=batch_first, dropout=dropout, bidirectional=True)   # parameters only
+        self.linear = nn.Linear(h * 2, n_features)
+        self._runners = {}
+        self._seed = 0x5eed
+        self._step = None
+        self._arena_names = []
+        for k in range(num_layers):
+            for nm in ('weight_ih', 'weight_hh', 'bias_ih', 'bias_hh'):
+                self._arena_names += ['lstm.lstm.%s_l%d' % (nm, k), 'lstm.lstm.%s_l%d_reverse' % (nm, k)]
+        self._arena_names += ['lstm.linear.weight', 'lstm.linear.bias']
+
+    def _module_params(self):
+        return [self.get_parameter(n[len('lstm.'):]) for n in self._arena_names]
+
+    def _runner_for(self, n_seq, T):
+        from .engine import LstmRunner, ParamArena
+        # a fresh runner per call: its buffers hold the activations saved for this call's backward (the reference calls the
+        # shared LSTM several times per step — internal / border side of every layer — before loss.backward())
+        key = (n_seq, T, len(self._runners))
+        if key not in self._runners:
+            self._runners.clear()
+            dev = self.linear.weight.device
+            hp = {'node_embed_size': self.h, 'n_layers': 1, 'freeze_node_embeds': True, 'use_neighborhood': False, 'use_position': False,
+                  'use_structure': False, 'lstm_n_layers': self.num_layers, 'linear_hidden_dim_1': 1, 'linear_hidden_dim_2': 1, 'trainable_cc': False,
+                  'n_triangular_walks': 1, 'lstm_aggregator': self.aggregator, 'lstm_dropout': self.dropout}
+            arena = ParamArena(hp, 0, 1, 1, device=dev)
+            self._runners[key] = (LstmRunner(arena, hp, None, n_seq, dev, n_seq=n_seq, T=T), arena)
+            if self._step is None:
+                self._step = torch.zeros(1, dtype=torch.int32, device=dev)
+        return self._runners[key]
+
+    def _pack(self, arena, params):
+        for name, p in zip(self._arena_names, params):
+            arena.view(name).copy_(p.detach())
+
+    def forward(self, input):
+        return _LSTMFunction.apply(self, input, *self._module_params())
 
 
 class _EngineFunction(torch.autograd.Function):

@@ -55,6 +55,8 @@ SIGNATURES = {
     'subgnn_model_sub_bwd': [P, P],
     'subgnn_model_q_bwd': [P, P],
     'subgnn_model_wgrad': [P, P],
+    'subgnn_mpn_fwd': [P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, P],
+    'subgnn_mpn_bwd': [P, P, P, P, P, P, P, P, I, I, I, P],
     'subgnn_fill_zero': [P, LL, P],
     'subgnn_grad_sumsq': [P, LL, P, P],
     'subgnn_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],

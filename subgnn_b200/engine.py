@@ -195,16 +195,17 @@ class LstmRunner:
     """Sequences the LSTM kernels for the structure anchor patches (all layers / sides in one batch:
     the reference shares one LSTM across them, SubGNN.py:175)."""
 
-    def __init__(self, arena, hp, walks, n_groups, device):
-        """walks: int32 device tensor (n_groups * W, T)."""
+    def __init__(self, arena, hp, walks, n_groups, device, n_seq=None, T=None):
+        """walks: int32 device tensor (n_groups * W, T), or None for dense inputs of shape (n_seq, T, D)
+        (module-level LSTM.forward, SubGNN.py:76-88)."""
         self.arena, self.hp = arena, hp
         self.dev = torch.device(device)
         self.D = self.H = hp['node_embed_size']
         self.nl = hp['lstm_n_layers']
         self.W = hp['n_triangular_walks']
         self.n_groups = n_groups
-        self.walks = walks.contiguous()
-        self.n_seq, self.T = walks.shape
+        self.walks = walks.contiguous() if walks is not None else None
+        self.n_seq, self.T = walks.shape if walks is not None else (n_seq, T)
         self.sum_mode = 1 if hp['lstm_aggregator'] == 'sum' else 0
         if hp['lstm_aggregator'] not in ('sum', 'last'):
             raise NotImplementedError(hp['lstm_aggregator'])                       # SubGNN.py:86-87
@@ -226,20 +227,24 @@ class LstmRunner:
         zero_row = torch.full_like(t, M)
         self.hprev = [torch.where(tt > 0, t - 1, zero_row).to(torch.int32).contiguous(),
                       torch.where(tt < self.T - 1, t + 1, zero_row).to(torch.int32).contiguous()]
-        self.ids_flat = self.walks.reshape(-1).contiguous()
+        self.ids_flat = self.walks.reshape(-1).contiguous() if walks is not None else None
+        self.dense_x = None
 
     def steps(self, k):
         top = k == self.nl - 1
         return (self.T, 1) if (top and not self.sum_mode) else (self.T, self.T)
 
-    def forward(self, E_ptr, training, seed, step_dev, st):
+    def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None):
         a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        self.dense_x = dense_x
+        if dense_x is not None:
+            E_ptr = ptr(dense_x)
         for k in range(self.nl):
             o = a.lstm_off[k]
             call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
                  ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
             if k == 0:
-                call('subgnn_linear_fwd', E_ptr, D, ptr(self.ids_flat), a.base_addr(o['weight_ih']), D, ptr(self.bsum[k]),
+                call('subgnn_linear_fwd', E_ptr, D, ptr(self.ids_flat) if dense_x is None else None, a.base_addr(o['weight_ih']), D, ptr(self.bsum[k]),
                      ptr(self.G[k]), 8 * H, M, 8 * H, D, 0, st)
             else:
                 x = self.OUT[k - 1]
@@ -256,9 +261,12 @@ class LstmRunner:
              ptr(self.Y), D, self.n_seq, D, 2 * H, 0, st)
         call('subgnn_group_sum', ptr(self.Y), ptr(self.EMB), self.n_groups, self.W, D, st)
 
-    def backward(self, E_ptr, dE_ptr, training, seed, step_dev, st):
-        """consumes self.dEMB; accumulates into the gradient arena (and dE)."""
+    def backward(self, E_ptr, dE_ptr, training, seed, step_dev, st, dense_dx=None):
+        """consumes self.dEMB; accumulates into the gradient arena (and dE, or writes dense_dx for dense inputs)."""
         a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        dense = self.dense_x is not None
+        if dense:
+            E_ptr = ptr(self.dense_x)
         g = 'grads'
         call('subgnn_group_bcast', ptr(self.dEMB), ptr(self.dY), self.n_groups, self.W, D, st)
         call('subgnn_linear_bwd_weight', ptr(self.dY), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
@@ -274,7 +282,7 @@ class LstmRunner:
             dG = ptr(self.G[k])
             din = D if k == 0 else 2 * H
             if k == 0:
-                x_ptr, ldx, ids = E_ptr, D, ptr(self.ids_flat)
+                x_ptr, ldx, ids = E_ptr, D, (None if dense else ptr(self.ids_flat))
             else:
                 xin = self.X[k] if (self.p_drop > 0 and training) else self.OUT[k - 1]
                 x_ptr, ldx, ids = ptr(xin), 2 * H, None
@@ -289,6 +297,9 @@ class LstmRunner:
                      2 * H, 0, st)
                 if self.p_drop > 0 and training:
                     call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+            elif dense:
+                if dense_dx is not None:
+                    call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), D, ptr(dense_dx), D, None, M, 8 * H, D, 0, st)
             elif dE_ptr:
                 call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), D, dE_ptr, D, ptr(self.ids_flat), M, 8 * H, D, 1, st)
 

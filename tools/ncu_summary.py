@@ -1,0 +1,30 @@
+#!/usr/bin/env python
+"""Key metrics of an .ncu-rep (ncu -i ... --page raw --csv) as a short text table for profiles/."""
+import csv
+import subprocess
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
+        'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
+        'l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
+        'launch__waves_per_multiprocessor', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
+        'sm__maximum_warps_per_active_cycle_pct']
+
+
+def main(path):
+    out = subprocess.run(['ncu', '-i', path, '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+    rows = list(csv.reader(out.splitlines()))
+    hdr, units = rows[0], rows[1]
+    for r in rows[2:]:
+        print('== ' + r[hdr.index('Kernel Name')])
+        for w in WANT:
+            if w in hdr:
+                i = hdr.index(w)
+                print('   %-86s %s %s' % (w, r[i], units[i]))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
