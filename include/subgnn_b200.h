@@ -166,6 +166,7 @@ typedef struct subgnn_model_desc {
   const int* step_dev;       /* [1] optimizer step counter on the device (dropout salt; graph-replay safe) */
   int* b_rowptr;             /* [B+1] */
   int* meta;                 /* [0] = R (rows in the batch), [1] = max component length in the batch */
+  int* row_b; int* row_g;    /* [R_cap] batch slot and global component id of every row */
   float* n_wt;               /* [L][2][2D][D] transposed MPN weights (N channel) */
   float* lin_wt[3];          /* transposed MLP weights */
   float* q_pi; float* q_pb; float* q_s;          /* [L][B][A_pi], [L][A_pb], [L][2][A_s] */

@@ -14,67 +14,7 @@
 #include "common.cuh"
 #include "../../include/subgnn_b200.h"
 
-#define BM 64
-#define BN 64
-#define BK 16
-#define TM 4
-#define TN 4
-
-// Generic tile engine.  a(m, k) / b(k, n) fetch operand elements (bounds already checked by the caller),
-// epi(m, n, acc) consumes one output element.  A_KC / B_KC: operand is contiguous along k (choose the
-// thread->element map so that global loads coalesce).
-template <bool A_KC, bool B_KC, class AF, class BF, class EF>
-__device__ __forceinline__ void gemm_tile(int M, int N, int k0, int k1, AF a, BF b, EF epi) {
-  __shared__ float As[BK][BM + 4];
-  __shared__ float Bs[BK][BN + 4];
-  const int tid = threadIdx.x;
-  const int tx = tid % 16, ty = tid / 16;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  float acc[TM][TN];
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) acc[i][j] = 0.f;
-  for (int kb = k0; kb < k1; kb += BK) {
-#pragma unroll
-    for (int p = 0; p < (BM * BK) / 256; ++p) {
-      const int e = p * 256 + tid;
-      int mm, kk;
-      if (A_KC) { kk = e % BK; mm = e / BK; } else { mm = e % BM; kk = e / BM; }
-      const int m = m0 + mm, k = kb + kk;
-      As[kk][mm] = (m < M && k < k1) ? a(m, k) : 0.f;
-    }
-#pragma unroll
-    for (int p = 0; p < (BN * BK) / 256; ++p) {
-      const int e = p * 256 + tid;
-      int nn, kk;
-      if (B_KC) { kk = e % BK; nn = e / BK; } else { nn = e % BN; kk = e / BN; }
-      const int n = n0 + nn, k = kb + kk;
-      Bs[kk][nn] = (n < N && k < k1) ? b(k, n) : 0.f;
-    }
-    __syncthreads();
-#pragma unroll
-    for (int kk = 0; kk < BK; ++kk) {
-      float av[TM], bv[TN];
-#pragma unroll
-      for (int i = 0; i < TM; ++i) av[i] = As[kk][ty * TM + i];
-#pragma unroll
-      for (int j = 0; j < TN; ++j) bv[j] = Bs[kk][tx * TN + j];
-#pragma unroll
-      for (int i = 0; i < TM; ++i)
-#pragma unroll
-        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
-    }
-    __syncthreads();
-  }
-#pragma unroll
-  for (int i = 0; i < TM; ++i)
-#pragma unroll
-    for (int j = 0; j < TN; ++j) {
-      const int m = m0 + ty * TM + i, n = n0 + tx * TN + j;
-      if (m < M && n < N) epi(m, n, acc[i][j]);
-    }
-}
+#include "gemm_tile.cuh"
 
 // y[m][n] = act( sum_k X[row(m)][k] * W[n][k] + bias[n] )
 __global__ void __launch_bounds__(256)
@@ -115,11 +55,20 @@ linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __re
 // dW[n][k] += sum_m dy[m][n] * X[row(m)][k]   (split over m across blockIdx.z, atomic accumulate)
 __global__ void __launch_bounds__(256)
 linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
-                         float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk, const int* __restrict__ m_dev) {
+                         float* __restrict__ dw, int lddw, float* __restrict__ db, int M, int N, int K, int m_chunk,
+                         const int* __restrict__ m_dev) {
   if (m_dev) M = min(M, *m_dev);
   const int m_beg = blockIdx.z * m_chunk;
   const int m_end = min(M, m_beg + m_chunk);
   if (m_beg >= m_end) return;
+  if (db && blockIdx.x == 0) {                                   // fused bias gradient: column sums of this tile's rows of dy^T
+    const int n = blockIdx.y * BM + (threadIdx.x % BM), part = threadIdx.x / BM;
+    if (n < N) {
+      float s = 0.f;
+      for (int m = m_beg + part; m < m_end; m += 256 / BM) s += dy[(long long)m * ldy + n];
+      if (s != 0.f) atomicAdd(db + n, s);
+    }
+  }
   gemm_tile<false, false>(
       N, K, m_beg, m_end,
       [&](int n, int m) { return __ldg(dy + (long long)m * ldy + n); },
@@ -172,17 +121,8 @@ int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, 
   const int m_chunk = sg_div_up(sg_div_up(M, splits), BK) * BK;
   splits = sg_div_up(M, m_chunk);
   dim3 grid(sg_div_up(K, BN), sg_div_up(N, BM), splits);
-  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk, m_dev);
-  int rc = subgnn_check_launch("linear_bwd_weight_kernel");
-  if (rc) return rc;
-  if (db) {
-    const int cs = sg_div_up(M, 64) > 64 ? 64 : sg_div_up(M, 64);
-    const int chunk = sg_div_up(M, cs);
-    dim3 g2(sg_div_up(N, 128), sg_div_up(M, chunk));
-    colsum_kernel<<<g2, 128, 0, (cudaStream_t)stream>>>(dy, ldy, db, M, N, chunk, m_dev);
-    rc = subgnn_check_launch("colsum_kernel");
-  }
-  return rc;
+  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, db, M, N, K, m_chunk, m_dev);
+  return subgnn_check_launch("linear_bwd_weight_kernel");
 }
 
 int subgnn_colsum(const float* dy, int ldy, float* db, int M, int N, const int* m_dev, void* stream) {

@@ -68,7 +68,9 @@ __global__ void __launch_bounds__(256) prep_batch_kernel(Desc d) {
   for (int b = beg; b < end; ++b) {
     const int sub = d.batch_idx[b];
     d.b_rowptr[b] = run;
-    run += d.sub_ccptr[sub + 1] - d.sub_ccptr[sub];
+    const int g0 = d.sub_ccptr[sub], n = d.sub_ccptr[sub + 1] - g0;
+    for (int i = 0; i < n; ++i) { d.row_b[run + i] = b; d.row_g[run + i] = g0 + i; }
+    run += n;
   }
 }
 
@@ -239,10 +241,26 @@ __device__ void mlp_forward(const Desc& d, int b, const float* zs, float* work) 
   float* h2s = h1s + d.h1;
   float* lg = h2s + d.h2;
   const int tid = threadIdx.x;
+  // lin: hid is large (up to ~2k) and h1 small: split the reduction over blockDim / h1 thread groups
+  float* psum = lg + d.n_classes + 4;                       // [parts][h1] scratch (fits: see mlp_smem)
+  const int parts = d.h1 <= (int)blockDim.x ? (int)blockDim.x / d.h1 : 1;
+  if (tid < parts * d.h1) {
+    const int j = tid % d.h1, part = tid / d.h1;
+    const int i0 = (int)((long long)d.hid * part / parts), i1 = (int)((long long)d.hid * (part + 1) / parts);
+    float acc = 0.f;
+    const float* wt = d.lin_wt[0] + j;
+    for (int i = i0; i < i1; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
+    psum[part * d.h1 + j] = acc;
+  }
+  __syncthreads();
   for (int j = tid; j < d.h1; j += blockDim.x) {
     float acc = d.lin_b[0][j];
-    const float* wt = d.lin_wt[0] + j;
-    for (int i = 0; i < d.hid; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
+    if (d.h1 <= (int)blockDim.x) {
+      for (int p_ = 0; p_ < parts; ++p_) acc += psum[p_ * d.h1 + j];
+    } else {
+      const float* wt = d.lin_wt[0] + j;
+      for (int i = 0; i < d.hid; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
+    }
     acc = fmaxf(acc, 0.f);
     if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
     h1s[j] = acc;
@@ -334,382 +352,385 @@ __device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// forward over the rows of one subgraph
+// ROW kernels: one CTA per connected component (row) of the batch, 8 warps cooperate on it:
+// warps 0-3 own the internal side, warps 4-7 the border side of the N channel; inside a side the four warps
+// split the anchor gathers (16 independent row gathers in flight per side) and the 2D x D projection.
+// The subgraph readout is a global atomicAdd into Z[b] (zeroed every step); the per-sample MLP is its own
+// small kernel (grid = B) after all rows are done.
+#define ROW_THREADS 256
+#define SIDE_THREADS 128
+#define SIDE_WARPS 4
+
+struct RowSmem {
+  float* x0;      // [D]
+  float* h;       // [2][D]
+  float* in;      // [2][2D]   [h ; agg]
+  float* part;    // [2][SIDE_WARPS][D] partial aggregates / partial matvec sums
+};
+
+__device__ __forceinline__ RowSmem row_smem(float* sm, int D) {
+  RowSmem r;
+  r.x0 = sm;
+  r.h = r.x0 + D;
+  r.in = r.h + 2 * D;
+  r.part = r.in + 4 * D;
+  return r;
+}
+static size_t row_smem_bytes(int D) { return (size_t)(D + 2 * D + 4 * D + 2 * SIDE_WARPS * D + 16) * sizeof(float); }
+
 template <int DPL>
-__global__ void __launch_bounds__(SUB_THREADS) sub_fwd_kernel(Desc d) {
+__global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
   extern __shared__ float sm[];
-  float* zs = sm;                               // [hid]
-  float* in_all = zs + d.hid;                   // [SUB_WARPS][2D]
-  float* work = in_all + SUB_WARPS * 2 * d.D;   // MLP scratch
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x;
   const int D = d.D;
-  const int sub = d.batch_idx[b];
-  const int g0 = d.sub_ccptr[sub], g1 = d.sub_ccptr[sub + 1];
-  const int r0 = d.b_rowptr[b];
-  const int maxlen = d.meta[1];
+  const RowSmem S = row_smem(sm, D);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int side = warp / SIDE_WARPS, sw = warp % SIDE_WARPS, st = tid % SIDE_THREADS;
+  const int R = d.meta[0], maxlen = d.meta[1];
   const int blk = 2 * D * D + 2 * D + 1;
-  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) zs[i] = 0.f;
-  __syncthreads();
-  float* in_s = in_all + warp * 2 * D;
-  for (int g = g0 + warp; g < g1; g += SUB_WARPS) {
-    const int r = r0 + (g - g0);
-    // ---- pooling (SubGNN.py:609-622) ----
-    const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
-    float x0[DPL];
-#pragma unroll
-    for (int q = 0; q < DPL; ++q) x0[q] = d.pool_max ? -INFINITY : 0.f;
-    for (int i = nb; i < ne; ++i) {
-      const float* row = d.E + (size_t)d.cc_nodes[i] * D;
-#pragma unroll
-      for (int q = 0; q < DPL; ++q) {
-        const int k = lane + 32 * q;
-        if (k < D) x0[q] = d.pool_max ? fmaxf(x0[q], row[k]) : x0[q] + row[k];
-      }
-    }
-    if (d.pool_max && (ne - nb) < maxlen) {       // PAD rows (zero vectors) take part in the max (F: SubGNN.py:622)
-#pragma unroll
-      for (int q = 0; q < DPL; ++q) x0[q] = fmaxf(x0[q], 0.f);
-    }
-#pragma unroll
-    for (int q = 0; q < DPL; ++q) {
-      const int k = lane + 32 * q;
-      if (k < D) {
-        d.X0[(size_t)r * D + k] = x0[q];
-        atomicAdd(&zs[k], x0[q]);
-      }
-    }
-    // ---- neighbourhood channel: L chained MPN layers per side ----
-    if (d.use_n) {
-      for (int side = 0; side < 2; ++side) {
-        const int A = side ? d.A_nb : d.A_ni;
-        float h[DPL];
-#pragma unroll
-        for (int q = 0; q < DPL; ++q) {
-          const int k = lane + 32 * q;
-          if (k < D) {
-            h[q] = d.trainable_cc ? d.cc_tab[side][((size_t)sub * d.C_pad + (g - g0)) * D + k] : x0[q];
-            d.Nh[((size_t)(0 * 2 + side) * d.R_cap + r) * D + k] = h[q];
-          } else h[q] = 0.f;
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const int b = d.row_b[r], g = d.row_g[r];
+    const int sub = d.batch_idx[b];
+    float* zrow = d.Z + (size_t)b * d.hid;
+    __syncthreads();
+    // ---- pooling (SubGNN.py:609-622): threads (k, part) split the component's nodes ----
+    {
+      const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
+      const int parts = D <= ROW_THREADS ? ROW_THREADS / D : 1;
+      float* ps = S.part;                                   // reuse: [parts][D] <= 8 * D floats when parts <= 8 ... guard below
+      const int pmax = 2 * SIDE_WARPS;                      // capacity of S.part in units of D
+      const int np = parts < pmax ? parts : pmax;
+      if (tid < np * D) {
+        const int k = tid % D, part = tid / D;
+        float acc = d.pool_max ? -INFINITY : 0.f;
+        for (int i = nb + part; i < ne; i += np) {
+          const float v = d.E[(size_t)d.cc_nodes[i] * D + k];
+          acc = d.pool_max ? fmaxf(acc, v) : acc + v;
         }
-        for (int l = 0; l < d.L; ++l) {
-          const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
-          const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
-          float agg[DPL];
+        ps[part * D + k] = acc;
+      }
+      __syncthreads();
+      for (int k = tid; k < D; k += ROW_THREADS) {
+        float acc = ps[k];
+        for (int p_ = 1; p_ < np; ++p_) acc = d.pool_max ? fmaxf(acc, ps[p_ * D + k]) : acc + ps[p_ * D + k];
+        if (d.pool_max && (ne - nb) < maxlen) acc = fmaxf(acc, 0.f);     // PAD rows (zero vectors) take part in the max
+        S.x0[k] = acc;
+        d.X0[(size_t)r * D + k] = acc;
+        atomicAdd(zrow + k, acc);
+      }
+      __syncthreads();
+    }
+    // ---- neighbourhood channel ----
+    if (d.use_n) {
+      const int A = side ? d.A_nb : d.A_ni;
+      for (int k = st; k < D; k += SIDE_THREADS) {
+        const float v = d.trainable_cc ? d.cc_tab[side][((size_t)sub * d.C_pad + (g - d.sub_ccptr[sub])) * D + k] : S.x0[k];
+        S.h[side * D + k] = v;
+        d.Nh[((size_t)(0 * 2 + side) * d.R_cap + r) * D + k] = v;
+      }
+      __syncthreads();
+      for (int l = 0; l < d.L; ++l) {
+        const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
+        const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
+        float agg[DPL];
 #pragma unroll
-          for (int q = 0; q < DPL; ++q) agg[q] = 0.f;
-          int a = 0;
-          for (; a + 4 <= A; a += 4) {               // 4 independent row gathers in flight
-            const int i0 = ids[a], i1 = ids[a + 1], i2 = ids[a + 2], i3 = ids[a + 3];
-            const float s0 = sims[a], s1 = sims[a + 1], s2 = sims[a + 2], s3 = sims[a + 3];
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) {
-              const int k = lane + 32 * q;
-              if (k < D) {
-                const float v0 = i0 ? d.E[(size_t)i0 * D + k] : 0.f, v1 = i1 ? d.E[(size_t)i1 * D + k] : 0.f;
-                const float v2 = i2 ? d.E[(size_t)i2 * D + k] : 0.f, v3 = i3 ? d.E[(size_t)i3 * D + k] : 0.f;
-                agg[q] = fmaf(s0, v0, agg[q]); agg[q] = fmaf(s1, v1, agg[q]);
-                agg[q] = fmaf(s2, v2, agg[q]); agg[q] = fmaf(s3, v3, agg[q]);
-              }
-            }
-          }
-          for (; a < A; ++a) {
-            const int i0 = ids[a];
-            const float s0 = sims[a];
-            if (i0)
-#pragma unroll
-              for (int q = 0; q < DPL; ++q) {
-                const int k = lane + 32 * q;
-                if (k < D) agg[q] = fmaf(s0, d.E[(size_t)i0 * D + k], agg[q]);
-              }
-          }
-          float out[DPL];
-          if (d.use_proj) {
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) {
-              const int k = lane + 32 * q;
-              if (k < D) { in_s[k] = h[q]; in_s[D + k] = agg[q]; }
-            }
-            __syncwarp();
-            const float* wt = d.n_wt + (size_t)(2 * l + side) * 2 * D * D;       // [2D][D]
-            const float* bias = d.mpn_params[0] + (size_t)(2 * l + side) * blk + 2 * D * D;
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; out[q] = k < D ? bias[k] : 0.f; }
-            for (int kk = 0; kk < 2 * D; ++kk) {
-              const float xv = in_s[kk];
-#pragma unroll
-              for (int q = 0; q < DPL; ++q) {
-                const int k = lane + 32 * q;
-                if (k < D) out[q] = fmaf(xv, __ldg(wt + (size_t)kk * D + k), out[q]);
-              }
-            }
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) out[q] = fmaxf(out[q], 0.f);
-          } else {
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) out[q] = agg[q];                       // subgraph_mpn.py:240-241
-          }
-          const int zc = col_n(d, l, side);
+        for (int q = 0; q < DPL; ++q) agg[q] = 0.f;
+        int a = sw;
+        for (; a + 3 * SIDE_WARPS < A; a += 4 * SIDE_WARPS) {       // 4 gathers in flight per warp, 16 per side
+          const int i0 = ids[a], i1 = ids[a + SIDE_WARPS], i2 = ids[a + 2 * SIDE_WARPS], i3 = ids[a + 3 * SIDE_WARPS];
+          const float s0 = sims[a], s1 = sims[a + SIDE_WARPS], s2 = sims[a + 2 * SIDE_WARPS], s3 = sims[a + 3 * SIDE_WARPS];
 #pragma unroll
           for (int q = 0; q < DPL; ++q) {
             const int k = lane + 32 * q;
             if (k < D) {
-              d.Nagg[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = agg[q];
-              d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + k] = out[q];
-              atomicAdd(&zs[zc + k], out[q]);
-              h[q] = out[q];
+              const float v0 = i0 ? d.E[(size_t)i0 * D + k] : 0.f, v1 = i1 ? d.E[(size_t)i1 * D + k] : 0.f;
+              const float v2 = i2 ? d.E[(size_t)i2 * D + k] : 0.f, v3 = i3 ? d.E[(size_t)i3 * D + k] : 0.f;
+              agg[q] = fmaf(s0, v0, agg[q]); agg[q] = fmaf(s1, v1, agg[q]);
+              agg[q] = fmaf(s2, v2, agg[q]); agg[q] = fmaf(s3, v3, agg[q]);
             }
           }
         }
+        for (; a < A; a += SIDE_WARPS) {
+          const int i0 = ids[a];
+          const float s0 = sims[a];
+          if (i0)
+#pragma unroll
+            for (int q = 0; q < DPL; ++q) {
+              const int k = lane + 32 * q;
+              if (k < D) agg[q] = fmaf(s0, d.E[(size_t)i0 * D + k], agg[q]);
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < DPL; ++q) {
+          const int k = lane + 32 * q;
+          if (k < D) S.part[(side * SIDE_WARPS + sw) * D + k] = agg[q];
+        }
+        __syncthreads();
+        for (int k = st; k < D; k += SIDE_THREADS) {
+          float v = 0.f;
+#pragma unroll
+          for (int w = 0; w < SIDE_WARPS; ++w) v += S.part[(side * SIDE_WARPS + w) * D + k];
+          S.in[side * 2 * D + k] = S.h[side * D + k];
+          S.in[side * 2 * D + D + k] = v;
+          d.Nagg[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = v;
+        }
+        __syncthreads();
+        if (d.use_proj) {
+          // out[j] = b[j] + sum_kk in[kk] * WT[kk][j]; (j, part) split of the 2D-long reduction over the side's threads
+          const float* wt = d.n_wt + (size_t)(2 * l + side) * 2 * D * D;
+          const int parts = (D <= SIDE_THREADS && SIDE_THREADS % D == 0) ? min(SIDE_THREADS / D, SIDE_WARPS) : 1;
+          const float* inp = S.in + side * 2 * D;
+          for (int idx = st; idx < parts * D; idx += SIDE_THREADS) {
+            const int j = idx % D, part = idx / D;
+            const int k0 = 2 * D * part / parts, k1 = 2 * D * (part + 1) / parts;
+            float acc = 0.f;
+#pragma unroll 4
+            for (int kk = k0; kk < k1; ++kk) acc = fmaf(inp[kk], __ldg(wt + (size_t)kk * D + j), acc);
+            S.part[(side * SIDE_WARPS + part) * D + j] = acc;
+          }
+          __syncthreads();
+          const float* bias = d.mpn_params[0] + (size_t)(2 * l + side) * blk + 2 * D * D;
+          for (int j = st; j < D; j += SIDE_THREADS) {
+            float acc = bias[j];
+            for (int p_ = 0; p_ < parts; ++p_) acc += S.part[(side * SIDE_WARPS + p_) * D + j];
+            S.h[side * D + j] = fmaxf(acc, 0.f);
+          }
+        } else {
+          for (int j = st; j < D; j += SIDE_THREADS) S.h[side * D + j] = S.in[side * 2 * D + D + j];   // subgraph_mpn.py:240-241
+        }
+        __syncthreads();
+        const int zc = col_n(d, l, side);
+        for (int j = st; j < D; j += SIDE_THREADS) {
+          const float v = S.h[side * D + j];
+          d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + j] = v;
+          atomicAdd(zrow + zc + j, v);
+        }
       }
     }
-    // ---- position / structure channels: property-aware outputs ----
-    for (int l = 0; l < d.L; ++l) {
-      if (d.use_p) {
-        for (int side = 0; side < 2; ++side) {
-          const int A = side ? d.A_pb : d.A_pi;
-          const float* sims = d.p_sim[side] + ((size_t)l * d.n_cc + g) * A;
-          const float* q = side ? d.q_pb + (size_t)l * A : d.q_pi + ((size_t)l * d.B + b) * A;
-          const float bp = d.mpn_params[1][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
-          const int zc = col_p(d, l, side);
-          for (int a = lane; a < A; a += 32) atomicAdd(&zs[zc + a], fmaxf(fmaf(sims[a], q[a], bp), 0.f));
+    // ---- position / structure channels: property-aware outputs relu(s q + b_p) ----
+    {
+      const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
+      const int per_layer = wp_ + ws_;
+      for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
+        const int l = e / per_layer;
+        int o = e % per_layer;
+        float s, q, bp;
+        int zc;
+        if (o < wp_) {
+          const int sd = o >= d.A_pi ? 1 : 0, a = sd ? o - d.A_pi : o, A = sd ? d.A_pb : d.A_pi;
+          s = d.p_sim[sd][((size_t)l * d.n_cc + g) * A + a];
+          q = sd ? d.q_pb[(size_t)l * A + a] : d.q_pi[((size_t)l * d.B + b) * A + a];
+          bp = d.mpn_params[1][(size_t)(2 * l + sd) * blk + 2 * D * D + 2 * D];
+          zc = col_p(d, l, sd) + a;
+        } else {
+          o -= wp_;
+          const int sd = o / d.A_s, a = o % d.A_s;
+          s = d.s_sim[sd][((size_t)l * d.n_cc + g) * d.A_s + a];
+          q = d.q_s[((size_t)l * 2 + sd) * d.A_s + a];
+          bp = d.mpn_params[2][(size_t)(2 * l + sd) * blk + 2 * D * D + 2 * D];
+          zc = col_s(d, l, sd) + a;
         }
-      }
-      if (d.use_s) {
-        for (int side = 0; side < 2; ++side) {
-          const int A = d.A_s;
-          const float* sims = d.s_sim[side] + ((size_t)l * d.n_cc + g) * A;
-          const float* q = d.q_s + ((size_t)l * 2 + side) * A;
-          const float bp = d.mpn_params[2][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
-          const int zc = col_s(d, l, side);
-          for (int a = lane; a < A; a += 32) atomicAdd(&zs[zc + a], fmaxf(fmaf(sims[a], q[a], bp), 0.f));
-        }
+        const float v = fmaxf(fmaf(s, q, bp), 0.f);
+        if (v != 0.f) atomicAdd(zrow + zc, v);
       }
     }
   }
+}
+
+// per-sample MLP + loss (+ MLP backward when training): grid = B
+static size_t mlp_smem(const Desc& d) {
+  const int parts = d.h1 <= ROW_THREADS ? ROW_THREADS / d.h1 : 1;
+  return (size_t)(d.hid + 2 * (d.h1 + d.h2) + d.n_classes + 8 + parts * d.h1 + 8) * sizeof(float);
+}
+__global__ void __launch_bounds__(ROW_THREADS) mlp_kernel(Desc d) {
+  extern __shared__ float sm[];
+  float* zs = sm;
+  float* work = zs + d.hid;
+  const int b = blockIdx.x;
+  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) zs[i] = d.Z[(size_t)b * d.hid + i];
   __syncthreads();
-  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) d.Z[(size_t)b * d.hid + i] = zs[i];
   mlp_forward(d, b, zs, work);
   if (d.training && d.dZ) mlp_backward(d, b, zs, work);
 }
-
-__global__ void __launch_bounds__(SUB_THREADS) mlp_bwd_kernel(Desc d) {
+__global__ void __launch_bounds__(ROW_THREADS) mlp_bwd_kernel(Desc d) {
   extern __shared__ float sm[];
   mlp_backward(d, blockIdx.x, sm, sm + d.hid);
 }
 
-// ------------------------------------------------------------------------------------------------
-// backward over the rows of one subgraph
 template <int DPL>
-__global__ void __launch_bounds__(SUB_THREADS) sub_bwd_kernel(Desc d) {
+__global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d) {
   extern __shared__ float sm[];
   const int D = d.D;
-  float* dzs = sm;                                   // [hid]
-  float* dpre_all = dzs + d.hid;                     // [SUB_WARPS][D]
-  float* acc_q = dpre_all + SUB_WARPS * D;           // [L][A_pi + A_pb + 2 A_s] dq accumulators
-  const int qw = (d.use_p ? d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
-  float* acc_bp = acc_q + d.L * qw;                  // [L][4] d b_p (P int, P bor, S int, S bor)
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int b = blockIdx.x;
-  const int sub = d.batch_idx[b];
-  const int g0 = d.sub_ccptr[sub], g1 = d.sub_ccptr[sub + 1];
-  const int r0 = d.b_rowptr[b];
+  float* dx0 = sm;                  // [D]
+  float* dpre = dx0 + D;            // [2][D]
+  float* din = dpre + 2 * D;        // [2][2D]  [dh ; dagg]
+  float* acc_bp = din + 4 * D;      // [L][4]
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int side = warp / SIDE_WARPS, sw = warp % SIDE_WARPS, st = tid % SIDE_THREADS;
+  const int R = d.meta[0];
   const int blk = 2 * D * D + 2 * D + 1;
-  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) dzs[i] = d.dZ[(size_t)b * d.hid + i];
-  for (int i = threadIdx.x; i < d.L * qw + d.L * 4; i += blockDim.x) acc_q[i] = 0.f;
-  __syncthreads();
-  float* dpre_s = dpre_all + warp * D;
-  for (int g = g0 + warp; g < g1; g += SUB_WARPS) {
-    const int r = r0 + (g - g0);
-    float dx0[DPL];                                  // gradient w.r.t. the pooled embedding
-#pragma unroll
-    for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; dx0[q] = k < D ? dzs[k] : 0.f; }
+  for (int r = blockIdx.x; r < R; r += gridDim.x) {
+    const int b = d.row_b[r], g = d.row_g[r];
+    const int sub = d.batch_idx[b];
+    const float* dz = d.dZ + (size_t)b * d.hid;
+    __syncthreads();
+    for (int k = tid; k < D; k += ROW_THREADS) dx0[k] = dz[k];
+    for (int k = tid; k < d.L * 4; k += ROW_THREADS) acc_bp[k] = 0.f;
+    for (int k = st; k < D; k += SIDE_THREADS) din[side * 2 * D + k] = 0.f;          // dh carried between layers
+    __syncthreads();
     if (d.use_n) {
-      for (int side = 0; side < 2; ++side) {
-        const int A = side ? d.A_nb : d.A_ni;
-        float dh[DPL];
-#pragma unroll
-        for (int q = 0; q < DPL; ++q) dh[q] = 0.f;
-        for (int l = d.L - 1; l >= 0; --l) {
-          const int zc = col_n(d, l, side);
-          float dagg[DPL];
-          if (d.use_proj) {
-            __syncwarp();
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) {
-              const int k = lane + 32 * q;
-              if (k < D) {
-                const float outv = d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + k];
-                const float g_ = outv > 0.f ? dzs[zc + k] + dh[q] : 0.f;
-                dpre_s[k] = g_;
-                d.Ndpre[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = g_;
-              }
-            }
-            __syncwarp();
-            const float* w = d.mpn_params[0] + (size_t)(2 * l + side) * blk;      // [D][2D]
-            float dlo[DPL], dhi[DPL];
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) { dlo[q] = 0.f; dhi[q] = 0.f; }
-            for (int j = 0; j < D; ++j) {
-              const float gj = dpre_s[j];
-              const float* wr = w + (size_t)j * 2 * D;
+      const int A = side ? d.A_nb : d.A_ni;
+      for (int l = d.L - 1; l >= 0; --l) {
+        const int zc = col_n(d, l, side);
+        if (d.use_proj) {
+          for (int k = st; k < D; k += SIDE_THREADS) {
+            const float outv = d.Nh[((size_t)((l + 1) * 2 + side) * d.R_cap + r) * D + k];
+            const float g_ = outv > 0.f ? dz[zc + k] + din[side * 2 * D + k] : 0.f;
+            dpre[side * D + k] = g_;
+            d.Ndpre[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = g_;
+          }
+          __syncthreads();
+          const float* w = d.mpn_params[0] + (size_t)(2 * l + side) * blk;            // [D][2D]
+          const float* gp = dpre + side * D;
+          for (int kk = st; kk < 2 * D; kk += SIDE_THREADS) {
+            float acc = 0.f;
+#pragma unroll 4
+            for (int j = 0; j < D; ++j) acc = fmaf(gp[j], __ldg(w + (size_t)j * 2 * D + kk), acc);
+            din[side * 2 * D + kk] = acc;
+          }
+        } else {
+          __syncthreads();
+          for (int k = st; k < D; k += SIDE_THREADS) {
+            din[side * 2 * D + D + k] = dz[zc + k] + din[side * 2 * D + k];
+          }
+          __syncthreads();
+          for (int k = st; k < D; k += SIDE_THREADS) din[side * 2 * D + k] = 0.f;      // update() ignores x without projection
+        }
+        __syncthreads();
+        if (d.dE) {
+          const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
+          const float* dagg = din + side * 2 * D + D;
+          for (int a = sw; a < A; a += SIDE_WARPS) {
+            const int id = ids[a];
+            const float s = sims[a];
+            if (id != 0 && s != 0.f)
 #pragma unroll
               for (int q = 0; q < DPL; ++q) {
                 const int k = lane + 32 * q;
-                if (k < D) { dlo[q] = fmaf(gj, __ldg(wr + k), dlo[q]); dhi[q] = fmaf(gj, __ldg(wr + D + k), dhi[q]); }
+                if (k < D) atomicAdd(d.dE + (size_t)id * D + k, s * dagg[k]);
               }
-            }
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) { dh[q] = dlo[q]; dagg[q] = dhi[q]; }
-          } else {
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) {
-              const int k = lane + 32 * q;
-              dagg[q] = k < D ? dzs[zc + k] + dh[q] : 0.f;
-              dh[q] = 0.f;                                                        // update() ignores x without projection
-            }
-          }
-          // scatter d agg into the embedding gradient of every valid anchor
-          if (d.dE) {
-            const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
-            const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
-            for (int a = 0; a < A; ++a) {
-              const int id = ids[a];
-              const float s = sims[a];
-              if (id != 0 && s != 0.f)
-#pragma unroll
-                for (int q = 0; q < DPL; ++q) {
-                  const int k = lane + 32 * q;
-                  if (k < D) atomicAdd(d.dE + (size_t)id * D + k, s * dagg[q]);
-                }
-            }
-          }
-        }
-        // gradient of the layer-0 input
-#pragma unroll
-        for (int q = 0; q < DPL; ++q) {
-          const int k = lane + 32 * q;
-          if (k < D) {
-            if (d.trainable_cc) {
-              if (d.cc_tab_grad[side]) atomicAdd(d.cc_tab_grad[side] + ((size_t)sub * d.C_pad + (g - g0)) * D + k, dh[q]);
-            } else {
-              dx0[q] += dh[q];
-            }
           }
         }
       }
+      __syncthreads();
+      // gradient of the layer-0 input of both sides
+      if (d.trainable_cc) {
+        for (int k = st; k < D; k += SIDE_THREADS)
+          if (d.cc_tab_grad[side]) atomicAdd(d.cc_tab_grad[side] + ((size_t)sub * d.C_pad + (g - d.sub_ccptr[sub])) * D + k, din[side * 2 * D + k]);
+      } else {
+        for (int k = tid; k < D; k += ROW_THREADS) dx0[k] += din[k] + din[2 * D + k];
+      }
+      __syncthreads();
     }
     // ---- pooling backward ----
     if (d.dE) {
       const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
       if (!d.pool_max) {
-        for (int i = nb; i < ne; ++i) {
-          float* row = d.dE + (size_t)d.cc_nodes[i] * D;
-#pragma unroll
-          for (int q = 0; q < DPL; ++q) { const int k = lane + 32 * q; if (k < D) atomicAdd(row + k, dx0[q]); }
+        for (int e = tid; e < (ne - nb) * D; e += ROW_THREADS) {
+          const int i = nb + e / D, k = e % D;
+          atomicAdd(d.dE + (size_t)d.cc_nodes[i] * D + k, dx0[k]);
         }
       } else {
-#pragma unroll
-        for (int q = 0; q < DPL; ++q) {
-          const int k = lane + 32 * q;
-          if (k < D) {
-            const float mx = d.X0[(size_t)r * D + k];
-            for (int i = nb; i < ne; ++i) {
-              const int id = d.cc_nodes[i];
-              if (d.E[(size_t)id * D + k] == mx) { atomicAdd(d.dE + (size_t)id * D + k, dx0[q]); break; }
-            }
+        for (int k = tid; k < D; k += ROW_THREADS) {
+          const float mx = d.X0[(size_t)r * D + k];
+          for (int i = nb; i < ne; ++i) {
+            const int id = d.cc_nodes[i];
+            if (d.E[(size_t)id * D + k] == mx) { atomicAdd(d.dE + (size_t)id * D + k, dx0[k]); break; }
           }
         }
       }
     }
-    // ---- property-aware outputs backward: d q and d b_p ----
-    for (int l = 0; l < d.L; ++l) {
-      float* aq = acc_q + l * qw;
-      if (d.use_p) {
-        for (int side = 0; side < 2; ++side) {
-          const int A = side ? d.A_pb : d.A_pi;
-          const float* sims = d.p_sim[side] + ((size_t)l * d.n_cc + g) * A;
-          const float* q = side ? d.q_pb + (size_t)l * A : d.q_pi + ((size_t)l * d.B + b) * A;
-          const float bp = d.mpn_params[1][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
-          const int zc = col_p(d, l, side);
-          float* dst = aq + (side ? d.A_pi : 0);
-          float dbp = 0.f;
-          for (int a = lane; a < A; a += 32) {
-            const float s = sims[a];
-            if (fmaf(s, q[a], bp) > 0.f) {
-              const float g_ = dzs[zc + a];
-              dbp += g_;
-              atomicAdd(dst + a, s * g_);
-            }
-          }
-          dbp = warp_sum(dbp);
-          if (lane == 0) atomicAdd(acc_bp + l * 4 + side, dbp);
+    // ---- property-aware outputs backward: d q (global atomics) and d b_p (CTA reduction) ----
+    {
+      const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
+      const int per_layer = wp_ + ws_;
+      for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
+        const int l = e / per_layer;
+        int o = e % per_layer;
+        float s, q, bp, g_;
+        float* dq;
+        int slot;
+        if (o < wp_) {
+          const int sd = o >= d.A_pi ? 1 : 0, a = sd ? o - d.A_pi : o, A = sd ? d.A_pb : d.A_pi;
+          s = d.p_sim[sd][((size_t)l * d.n_cc + g) * A + a];
+          q = sd ? d.q_pb[(size_t)l * A + a] : d.q_pi[((size_t)l * d.B + b) * A + a];
+          bp = d.mpn_params[1][(size_t)(2 * l + sd) * blk + 2 * D * D + 2 * D];
+          g_ = dz[col_p(d, l, sd) + a];
+          dq = sd ? d.dq_pb + (size_t)l * A + a : d.dq_pi + ((size_t)l * d.B + b) * A + a;
+          slot = sd;
+        } else {
+          o -= wp_;
+          const int sd = o / d.A_s, a = o % d.A_s;
+          s = d.s_sim[sd][((size_t)l * d.n_cc + g) * d.A_s + a];
+          q = d.q_s[((size_t)l * 2 + sd) * d.A_s + a];
+          bp = d.mpn_params[2][(size_t)(2 * l + sd) * blk + 2 * D * D + 2 * D];
+          g_ = dz[col_s(d, l, sd) + a];
+          dq = d.dq_s + ((size_t)l * 2 + sd) * d.A_s + a;
+          slot = 2 + sd;
+        }
+        if (fmaf(s, q, bp) > 0.f && g_ != 0.f) {
+          if (s != 0.f) atomicAdd(dq, s * g_);
+          atomicAdd(acc_bp + l * 4 + slot, g_);
         }
       }
-      if (d.use_s) {
-        for (int side = 0; side < 2; ++side) {
-          const int A = d.A_s;
-          const float* sims = d.s_sim[side] + ((size_t)l * d.n_cc + g) * A;
-          const float* q = d.q_s + ((size_t)l * 2 + side) * A;
-          const float bp = d.mpn_params[2][(size_t)(2 * l + side) * blk + 2 * D * D + 2 * D];
-          const int zc = col_s(d, l, side);
-          float* dst = aq + (d.use_p ? d.A_pi + d.A_pb : 0) + side * A;
-          float dbp = 0.f;
-          for (int a = lane; a < A; a += 32) {
-            const float s = sims[a];
-            if (fmaf(s, q[a], bp) > 0.f) {
-              const float g_ = dzs[zc + a];
-              dbp += g_;
-              atomicAdd(dst + a, s * g_);
-            }
-          }
-          dbp = warp_sum(dbp);
-          if (lane == 0) atomicAdd(acc_bp + l * 4 + 2 + side, dbp);
-        }
+      __syncthreads();
+      for (int e = tid; e < d.L * 4; e += ROW_THREADS) {
+        const int l = e / 4, slot = e % 4;
+        const int ch = slot < 2 ? 1 : 2, sd = slot & 1;
+        const bool on = ch == 1 ? d.use_p : d.use_s;
+        const float v = acc_bp[e];
+        if (on && d.mpn_grads[ch] && v != 0.f) atomicAdd(d.mpn_grads[ch] + (size_t)(2 * l + sd) * blk + 2 * D * D + 2 * D, v);
       }
     }
   }
-  __syncthreads();
-  // flush the CTA-level accumulators
-  for (int l = 0; l < d.L; ++l) {
-    const float* aq = acc_q + l * qw;
-    if (d.use_p) {
-      for (int a = threadIdx.x; a < d.A_pi; a += blockDim.x) d.dq_pi[((size_t)l * d.B + b) * d.A_pi + a] = aq[a];   // unique owner
-      for (int a = threadIdx.x; a < d.A_pb; a += blockDim.x) {
-        const float v = aq[d.A_pi + a];
-        if (v != 0.f) atomicAdd(d.dq_pb + (size_t)l * d.A_pb + a, v);
-      }
-    }
-    if (d.use_s) {
-      const float* as = aq + (d.use_p ? d.A_pi + d.A_pb : 0);
-      for (int a = threadIdx.x; a < 2 * d.A_s; a += blockDim.x) {
-        const float v = as[a];
-        if (v != 0.f) atomicAdd(d.dq_s + (size_t)l * 2 * d.A_s + a, v);
-      }
-    }
-    if (threadIdx.x < 4) {
-      const int ch = threadIdx.x < 2 ? 1 : 2, side = threadIdx.x & 1;
-      const bool on = ch == 1 ? d.use_p : d.use_s;
-      const float v = acc_bp[l * 4 + threadIdx.x];
-      if (on && d.mpn_grads[ch] && v != 0.f) atomicAdd(d.mpn_grads[ch] + (size_t)(2 * l + side) * blk + 2 * D * D + 2 * D, v);
+}
+
+// weight gradients of all N-channel projections in ONE launch: grid (2D/64, D/64, L*2*splits);
+// dW[z] (D x 2D) += dpre[z]^T [Nh[z] | Nagg[z]] over the valid rows; db[z] += column sums of dpre[z]
+#include "gemm_tile.cuh"
+__global__ void __launch_bounds__(256) n_wgrad_kernel(Desc d, int splits, int m_chunk) {
+  const int D = d.D;
+  const int z = blockIdx.z / splits, sp = blockIdx.z % splits;
+  const int R = d.meta[0];
+  const int m_beg = sp * m_chunk, m_end = min(R, m_beg + m_chunk);
+  if (m_beg >= m_end) return;
+  const int blk = 2 * D * D + 2 * D + 1;
+  const float* dpre = d.Ndpre + (size_t)z * d.R_cap * D;
+  const float* hin = d.Nh + (size_t)z * d.R_cap * D;            // input of layer l == Nh[l] (z = 2 l + side)
+  const float* agg = d.Nagg + (size_t)z * d.R_cap * D;
+  float* gw = d.mpn_grads[0] + (size_t)z * blk;
+  gemm_tile<false, false>(
+      D, 2 * D, m_beg, m_end,
+      [&](int n, int m) { return dpre[(size_t)m * D + n]; },
+      [&](int m, int k) { return k < D ? hin[(size_t)m * D + k] : agg[(size_t)m * D + (k - D)]; },
+      [&](int n, int k, float v) { atomicAdd(gw + (size_t)n * 2 * D + k, v); });
+  if (blockIdx.x == 0) {                                         // bias gradient for this tile's rows
+    const int n = blockIdx.y * 64 + (threadIdx.x % 64), part = threadIdx.x / 64;
+    if (n < D) {
+      float s = 0.f;
+      for (int m = m_beg + part; m < m_end; m += 4) s += dpre[(size_t)m * D + n];
+      if (s != 0.f) atomicAdd(gw + 2 * D * D + n, s);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------
-static size_t fwd_smem(const Desc& d) {
-  return (size_t)(d.hid + SUB_WARPS * 2 * d.D + 2 * (d.h1 + d.h2) + d.n_classes + 8) * sizeof(float);
-}
-static size_t bwd_smem(const Desc& d) {
-  const int qw = (d.use_p ? d.A_pi + d.A_pb : 0) + (d.use_s ? 2 * d.A_s : 0);
-  return (size_t)(d.hid + SUB_WARPS * d.D + d.L * qw + d.L * 4 + 8) * sizeof(float);
-}
+static size_t bwd_smem(const Desc& d) { return (size_t)(d.D + 2 * d.D + 4 * d.D + d.L * 4 + 16) * sizeof(float); }
 static int check_desc(const Desc* d) {
   if (!d) { subgnn_set_error("null descriptor"); return SUBGNN_ERR_ARG; }
   if (d->D < 1 || d->D > 32 * MAXDPL) { subgnn_set_error("node_embed_size must be in [1, %d]", 32 * MAXDPL); return SUBGNN_ERR_ARG; }
   if (d->B < 1 || d->L < 1) { subgnn_set_error("bad batch / layer count"); return SUBGNN_ERR_ARG; }
-  if (fwd_smem(*d) > 200 * 1024 || bwd_smem(*d) > 200 * 1024) { subgnn_set_error("hidden dimension too large for shared memory"); return SUBGNN_ERR_ARG; }
+  if (mlp_smem(*d) > 200 * 1024) { subgnn_set_error("hidden dimension too large for shared memory"); return SUBGNN_ERR_ARG; }
   return SUBGNN_OK;
 }
 
@@ -722,9 +743,9 @@ static int check_desc(const Desc* d) {
     else { KERNEL<8> __VA_ARGS__; }                                    \
   } while (0)
 
-template <int DPL> static void set_smem_attr(size_t f, size_t b) {
-  cudaFuncSetAttribute(sub_fwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)f);
-  cudaFuncSetAttribute(sub_bwd_kernel<DPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b);
+static int row_grid(const Desc* d) {
+  const int cap = subgnn_sm_count() * 8;
+  return d->R_cap < cap ? d->R_cap : cap;
 }
 
 extern "C" {
@@ -754,32 +775,30 @@ int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream) {
 int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  const size_t smem = fwd_smem(*d);
-  const int dpl = (d->D + 31) / 32;
-  if (dpl <= 1) set_smem_attr<1>(smem, bwd_smem(*d)); else if (dpl <= 2) set_smem_attr<2>(smem, bwd_smem(*d));
-  else if (dpl <= 4) set_smem_attr<4>(smem, bwd_smem(*d)); else set_smem_attr<8>(smem, bwd_smem(*d));
-  DISPATCH_DPL(d->D, sub_fwd_kernel, <<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d));
-  return subgnn_check_launch("sub_fwd_kernel");
+  const size_t smem = row_smem_bytes(d->D);
+  DISPATCH_DPL(d->D, row_fwd_kernel, <<<row_grid(d), ROW_THREADS, smem, (cudaStream_t)stream>>>(*d));
+  rc = subgnn_check_launch("row_fwd_kernel");
+  if (rc) return rc;
+  const size_t ms = mlp_smem(*d);
+  if (ms > 48 * 1024) cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms);
+  mlp_kernel<<<d->B, ROW_THREADS, ms, (cudaStream_t)stream>>>(*d);
+  return subgnn_check_launch("mlp_kernel");
 }
 
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   const size_t smem = (size_t)(d->hid + d->h1 + d->h2 + d->n_classes + 8) * sizeof(float);
-  cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mlp_bwd_kernel<<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d);
+  if (smem > 48 * 1024) cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  mlp_bwd_kernel<<<d->B, ROW_THREADS, smem, (cudaStream_t)stream>>>(*d);
   return subgnn_check_launch("mlp_bwd_kernel");
 }
 
 int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  const size_t smem = bwd_smem(*d);
-  const int dpl = (d->D + 31) / 32;
-  if (dpl <= 1) set_smem_attr<1>(fwd_smem(*d), smem); else if (dpl <= 2) set_smem_attr<2>(fwd_smem(*d), smem);
-  else if (dpl <= 4) set_smem_attr<4>(fwd_smem(*d), smem); else set_smem_attr<8>(fwd_smem(*d), smem);
-  DISPATCH_DPL(d->D, sub_bwd_kernel, <<<d->B, SUB_THREADS, smem, (cudaStream_t)stream>>>(*d));
-  return subgnn_check_launch("sub_bwd_kernel");
+  DISPATCH_DPL(d->D, row_bwd_kernel, <<<row_grid(d), ROW_THREADS, bwd_smem(*d), (cudaStream_t)stream>>>(*d));
+  return subgnn_check_launch("row_bwd_kernel");
 }
 
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
@@ -796,19 +815,14 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   const int D = d->D;
-  const int blk = 2 * D * D + 2 * D + 1;
   if (d->use_n && d->use_proj && d->mpn_grads[0]) {
-    for (int l = 0; l < d->L; ++l)
-      for (int side = 0; side < 2; ++side) {
-        const float* dpre = d->Ndpre + (size_t)(l * 2 + side) * d->R_cap * D;
-        const float* hin = d->Nh + (size_t)(l * 2 + side) * d->R_cap * D;
-        const float* agg = d->Nagg + (size_t)(l * 2 + side) * d->R_cap * D;
-        float* gw = d->mpn_grads[0] + (size_t)(2 * l + side) * blk;
-        rc = subgnn_linear_bwd_weight(dpre, D, hin, D, nullptr, gw, 2 * D, gw + 2 * D * D, d->R_cap, D, D, d->meta, stream);
-        if (rc) return rc;
-        rc = subgnn_linear_bwd_weight(dpre, D, agg, D, nullptr, gw + D, 2 * D, nullptr, d->R_cap, D, D, d->meta, stream);
-        if (rc) return rc;
-      }
+    int splits = sg_div_up(d->R_cap, 512);
+    const int m_chunk = sg_div_up(sg_div_up(d->R_cap, splits), 16) * 16;
+    splits = sg_div_up(d->R_cap, m_chunk);
+    dim3 grid(sg_div_up(2 * D, 64), sg_div_up(D, 64), d->L * 2 * splits);
+    n_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, splits, m_chunk);
+    rc = subgnn_check_launch("n_wgrad_kernel");
+    if (rc) return rc;
   }
   if (d->lin_gw[0]) {
     // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)

@@ -319,6 +319,7 @@ class StepContext:
         self.batch_idx = zi(B)
         self.batch_host = torch.zeros(B, dtype=torch.int32).pin_memory()
         self.b_rowptr, self.meta = zi(B + 1), zi(4)
+        self.row_b, self.row_g = zi(self.R_cap), zi(self.R_cap)
         A_pi, A_pb, A_s = eng.A['pi'], eng.A['pb'], eng.A['s']
         # gradient-side scratch that must start at zero every step lives in ONE buffer (single fill)
         n_dq = L * (B * A_pi + A_pb + 2 * A_s)
@@ -333,7 +334,7 @@ class StepContext:
         self.X0 = z(self.R_cap, D)
         nN = L if hp['use_neighborhood'] else 0
         self.Nh, self.Nagg, self.Ndpre = z((nN + 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D)
-        self.Z, self.H1, self.H2, self.logits, self.loss_b = z(B, hid), z(B, h1), z(B, h2), z(B, K), z(B)
+        self.Z, self.H1, self.H2, self.logits, self.loss_b = z(_align(B * hid)), z(B, h1), z(B, h2), z(B, K), z(B)   # Z: atomic readout target, zeroed per step
         self.dlogits, self.dH2, self.dH1, self.dZ = z(B, K), z(B, h2), z(B, h1), z(B, hid)
         self.loss = z(1)
         d = ModelDesc()
@@ -366,6 +367,7 @@ class StepContext:
         if eng.lstm is not None:
             d.emb_s, d.d_emb_s = ptr(eng.lstm.EMB), ptr(eng.lstm.dEMB)
         d.batch_idx, d.step_dev, d.b_rowptr, d.meta = ptr(self.batch_idx), ptr(eng.step_dev), ptr(self.b_rowptr), ptr(self.meta)
+        d.row_b, d.row_g = ptr(self.row_b), ptr(self.row_g)
         d.n_wt = ptr(self.n_wt)
         d.q_pi, d.q_pb, d.q_s = ptr(self.q_pi), ptr(self.q_pb), ptr(self.q_s)
         d.dq_pi, d.dq_pb, d.dq_s = (self.dq_pi.data_ptr(), self.dq_pb.data_ptr(), self.dq_s.data_ptr())
@@ -498,6 +500,7 @@ class Engine:
 
     # ---- launches --------------------------------------------------------------------------------
     def _forward_launches(self, c, st):
+        call('subgnn_fill_zero', ptr(c.Z), c.Z.numel(), st)
         if self.lstm is not None:
             self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
         call('subgnn_model_prep', c.dptr, st)
