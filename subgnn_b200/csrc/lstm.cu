@@ -22,7 +22,11 @@
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
-// grid (ceil(n_seq / S_TILE), 2 directions); block = 4H rounded up to 32
+// grid (ceil(n_seq / S_TILE), 2 directions); block = 4H rounded up to 32.
+// W_SMEM: the transposed recurrent weights of this direction (H x 4H fp32) are staged once in shared memory
+// (H <= 64: 64 KB); otherwise they are streamed from L1/L2 every step.  The gate pre-activations of step t+1 are
+// prefetched into registers while step t's matvec runs.
+template <bool W_SMEM>
 __global__ void __launch_bounds__(1024)
 lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2][H][4H]*/, float* __restrict__ OUT,
                       float* __restrict__ CS, int n_seq, int T, int H, int steps_fwd, int steps_rev) {
@@ -30,6 +34,7 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
   float* hbuf = sm;                       // [S_TILE][H]
   float* cbuf = hbuf + S_TILE * H;        // [S_TILE][H]
   float* gates = cbuf + S_TILE * H;       // [S_TILE][4H]
+  float* wsm = gates + S_TILE * 4 * H;    // [H][4H] (W_SMEM only)
   const int dir = blockIdx.y;
   const int seq0 = blockIdx.x * S_TILE;
   const int ns = min(S_TILE, n_seq - seq0);
@@ -38,18 +43,34 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
   const float* wt = WhhT + (size_t)dir * H * H4;
   const int n_steps = dir == 0 ? steps_fwd : steps_rev;
   for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { hbuf[e] = 0.f; cbuf[e] = 0.f; }
+  if (W_SMEM) {
+    for (int e = threadIdx.x; e < H * H4; e += blockDim.x) wsm[e] = wt[e];
+    wt = wsm;
+  }
+  float gnext[S_TILE];
+  if (j < H4 && n_steps > 0) {
+    const int t0 = dir == 0 ? 0 : T - 1;
+#pragma unroll
+    for (int s = 0; s < S_TILE; ++s) gnext[s] = s < ns ? G[(((size_t)(seq0 + s) * T + t0) * 2 + dir) * H4 + j] : 0.f;
+  }
   __syncthreads();
   for (int st = 0; st < n_steps; ++st) {
     const int t = dir == 0 ? st : T - 1 - st;
     if (j < H4) {
       float acc[S_TILE];
 #pragma unroll
-      for (int s = 0; s < S_TILE; ++s)
-        acc[s] = s < ns ? G[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + j] : 0.f;
+      for (int s = 0; s < S_TILE; ++s) acc[s] = gnext[s];
+      if (st + 1 < n_steps) {
+        const int tn = dir == 0 ? st + 1 : T - 2 - st;
+#pragma unroll
+        for (int s = 0; s < S_TILE; ++s) gnext[s] = s < ns ? G[(((size_t)(seq0 + s) * T + tn) * 2 + dir) * H4 + j] : 0.f;
+      }
       if ((H & 3) == 0) {
         for (int k = 0; k < H; k += 4) {
-          const float w0 = __ldg(wt + (size_t)k * H4 + j), w1 = __ldg(wt + (size_t)(k + 1) * H4 + j);
-          const float w2 = __ldg(wt + (size_t)(k + 2) * H4 + j), w3 = __ldg(wt + (size_t)(k + 3) * H4 + j);
+          float w0, w1, w2, w3;
+          if (W_SMEM) { w0 = wt[k * H4 + j]; w1 = wt[(k + 1) * H4 + j]; w2 = wt[(k + 2) * H4 + j]; w3 = wt[(k + 3) * H4 + j]; }
+          else { w0 = __ldg(wt + (size_t)k * H4 + j); w1 = __ldg(wt + (size_t)(k + 1) * H4 + j);
+                 w2 = __ldg(wt + (size_t)(k + 2) * H4 + j); w3 = __ldg(wt + (size_t)(k + 3) * H4 + j); }
 #pragma unroll
           for (int s = 0; s < S_TILE; ++s) {
             const float4 h4 = *reinterpret_cast<const float4*>(hbuf + s * H + k);
@@ -59,7 +80,7 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
         }
       } else {
         for (int k = 0; k < H; ++k) {
-          const float w = __ldg(wt + (size_t)k * H4 + j);
+          const float w = W_SMEM ? wt[k * H4 + j] : __ldg(wt + (size_t)k * H4 + j);
 #pragma unroll
           for (int s = 0; s < S_TILE; ++s) acc[s] = fmaf(hbuf[s * H + k], w, acc[s]);
         }
@@ -90,20 +111,26 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
 
 // BPTT.  dOUT [n_seq*T][2H] gradient w.r.t. this layer's outputs; G holds gate activations on entry and
 // d(pre-activation) on exit (zero for steps that were not taken).  Whh [2][4H][H] native layout.
+template <bool W_SMEM>
 __global__ void __launch_bounds__(1024)
 lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT,
                       const float* __restrict__ CS, const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd,
-                      int steps_rev) {
+                      int steps_rev, int zero_untaken) {
   extern __shared__ float sm[];
   const int H4 = 4 * H;
   float* dgate = sm;                        // [S_TILE][4H]
   float* dh_rec = dgate + S_TILE * H4;      // [S_TILE][H]
   float* dc_rec = dh_rec + S_TILE * H;      // [S_TILE][H]
   float* red = dc_rec + S_TILE * H;         // [4][S_TILE][H]
+  float* wsm = red + 4 * S_TILE * H;        // [4H][H] (W_SMEM only)
   const int dir = blockIdx.y;
   const int seq0 = blockIdx.x * S_TILE;
   const int ns = min(S_TILE, n_seq - seq0);
   const float* w = Whh + (size_t)dir * H4 * H;
+  if (W_SMEM) {
+    for (int e = threadIdx.x; e < H4 * H; e += blockDim.x) wsm[e] = w[e];
+    w = wsm;
+  }
   const int n_steps = dir == 0 ? steps_fwd : steps_rev;
   for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { dh_rec[e] = 0.f; dc_rec[e] = 0.f; }
   for (int e = threadIdx.x; e < S_TILE * H4; e += blockDim.x) dgate[e] = 0.f;
@@ -137,8 +164,8 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
       for (int s = 0; s < S_TILE; ++s) acc[s] = 0.f;
       if ((H & 3) == 0) {
         for (int jj = part * H; jj < (part + 1) * H; jj += 4) {
-          const float w0 = __ldg(w + (size_t)jj * H + k), w1 = __ldg(w + (size_t)(jj + 1) * H + k);
-          const float w2 = __ldg(w + (size_t)(jj + 2) * H + k), w3 = __ldg(w + (size_t)(jj + 3) * H + k);
+          const float w0 = w[(size_t)jj * H + k], w1 = w[(size_t)(jj + 1) * H + k];
+          const float w2 = w[(size_t)(jj + 2) * H + k], w3 = w[(size_t)(jj + 3) * H + k];
 #pragma unroll
           for (int s = 0; s < S_TILE; ++s) {
             const float4 g4 = *reinterpret_cast<const float4*>(dgate + s * H4 + jj);
@@ -148,7 +175,7 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
         }
       } else {
         for (int jj = part * H; jj < (part + 1) * H; ++jj) {
-          const float wv = __ldg(w + (size_t)jj * H + k);
+          const float wv = w[(size_t)jj * H + k];
 #pragma unroll
           for (int s = 0; s < S_TILE; ++s) acc[s] = fmaf(dgate[s * H4 + jj], wv, acc[s]);
         }
@@ -161,8 +188,9 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
       dh_rec[e] = red[e] + red[S_TILE * H + e] + red[2 * S_TILE * H + e] + red[3 * S_TILE * H + e];
     __syncthreads();
   }
-  // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations)
-  for (int st = n_steps; st < T; ++st) {
+  // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations) unless the
+  // caller never reads them (zero_untaken == 0)
+  for (int st = n_steps; zero_untaken && st < T; ++st) {
     const int t = dir == 0 ? st : T - 1 - st;
     for (int e = threadIdx.x; e < ns * H4; e += blockDim.x) {
       const int s = e / H4, jg = e % H4;
@@ -240,7 +268,17 @@ __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __r
   }
 }
 
+__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
+}
+
 extern "C" {
+
+int subgnn_add_inplace(float* dst, const float* src, int n, void* stream) {
+  if (n <= 0) return SUBGNN_OK;
+  add_inplace_kernel<<<sg_grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(dst, src, n);
+  return subgnn_check_launch("add_inplace_kernel");
+}
 
 static int lstm_block(int H) { return ((4 * H + 31) / 32) * 32; }
 
@@ -255,21 +293,39 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   SG_REQUIRE(steps_fwd >= 0 && steps_fwd <= T && steps_rev >= 0 && steps_rev <= T, "bad step counts");
   if (n_seq == 0) return SUBGNN_OK;
-  const size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
+  const size_t wbytes = (size_t)4 * H * H * sizeof(float);
+  const bool w_smem = smem + wbytes <= 100 * 1024;          // two CTAs per SM stay resident
   dim3 grid(sg_div_up(n_seq, S_TILE), 2);
-  lstm_recur_fwd_kernel<<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
+  if (w_smem) {
+    smem += wbytes;
+    cudaFuncSetAttribute(lstm_recur_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_recur_fwd_kernel<true><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_recur_fwd_kernel<false><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
+  }
   return subgnn_check_launch("lstm_recur_fwd_kernel");
 }
 
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
-                          int steps_fwd, int steps_rev, void* stream) {
+                          int steps_fwd, int steps_rev, int zero_untaken, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
-  const size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
-  if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
+  const size_t wbytes = (size_t)4 * H * H * sizeof(float);
+  const bool w_smem = smem + wbytes <= 100 * 1024;
   dim3 grid(sg_div_up(n_seq, S_TILE), 2);
-  lstm_recur_bwd_kernel<<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev);
+  if (w_smem) {
+    smem += wbytes;
+    cudaFuncSetAttribute(lstm_recur_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_recur_bwd_kernel<true><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev,
+                                                                                  zero_untaken);
+  } else {
+    if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_recur_bwd_kernel<false><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev,
+                                                                                   zero_untaken);
+  }
   return subgnn_check_launch("lstm_recur_bwd_kernel");
 }
 

@@ -228,6 +228,7 @@ class LstmRunner:
         self.hprev = [torch.where(tt > 0, t - 1, zero_row).to(torch.int32).contiguous(),
                       torch.where(tt < self.T - 1, t + 1, zero_row).to(torch.int32).contiguous()]
         self.ids_flat = self.walks.reshape(-1).contiguous() if walks is not None else None
+        self.ids_last = self.walks[:, -1].contiguous() if walks is not None else None
         self.dense_x = None
 
     def steps(self, k):
@@ -235,7 +236,7 @@ class LstmRunner:
         return (self.T, 1) if (top and not self.sum_mode) else (self.T, self.T)
 
     def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None):
-        a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
         self.dense_x = dense_x
         if dense_x is not None:
             E_ptr = ptr(dense_x)
@@ -243,27 +244,46 @@ class LstmRunner:
             o = a.lstm_off[k]
             call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
                  ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
-            if k == 0:
-                call('subgnn_linear_fwd', E_ptr, D, ptr(self.ids_flat) if dense_x is None else None, a.base_addr(o['weight_ih']), D, ptr(self.bsum[k]),
-                     ptr(self.G[k]), 8 * H, M, 8 * H, D, 0, st)
-            else:
-                x = self.OUT[k - 1]
-                if self.p_drop > 0 and training:
-                    call('subgnn_dropout', ptr(x), ptr(self.X[k]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
-                    x = self.X[k]
-                call('subgnn_linear_fwd', ptr(x), 2 * H, None, a.base_addr(o['weight_ih']), 2 * H, ptr(self.bsum[k]),
-                     ptr(self.G[k]), 8 * H, M, 8 * H, 2 * H, 0, st)
+            x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st)
             sf, sr = self.steps(k)
-            call('subgnn_lstm_recur_fwd', ptr(self.G[k]), ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, self.T, H,
-                 sf, sr, st)
-        call('subgnn_lstm_agg_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_seq, self.T, 2 * H, self.sum_mode, st)
+            w_ih, G = a.base_addr(o['weight_ih']), ptr(self.G[k])
+            if sr == T:
+                call('subgnn_linear_fwd', x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 8 * H, din, 0, st)
+            else:
+                # 'last' aggregator, top layer: the reverse direction is only ever read at t = T-1 (SubGNN.py:83), so its
+                # input projection is computed for those n_seq rows only
+                call('subgnn_linear_fwd', x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
+                xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
+                call('subgnn_linear_fwd', xl, ldxl, idsl, w_ih + 4 * (4 * H * din), din, self.bsum[k].data_ptr() + 4 * 4 * H,
+                     G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, st)
+            call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
+        call('subgnn_lstm_agg_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_seq, T, 2 * H, self.sum_mode, st)
         call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, a.addr('lstm.linear.bias'),
              ptr(self.Y), D, self.n_seq, D, 2 * H, 0, st)
         call('subgnn_group_sum', ptr(self.Y), ptr(self.EMB), self.n_groups, self.W, D, st)
 
+    def _layer_input(self, k, E_ptr, training, seed, step_dev, st, make=True):
+        """(x pointer, leading dim, gather ids, K) of layer k's input rows (all n_seq*T of them)."""
+        H, D, M = self.H, self.D, self.n_seq * self.T
+        if k == 0:
+            return E_ptr, D, (ptr(self.ids_flat) if self.dense_x is None else None), D
+        x = self.OUT[k - 1]
+        if self.p_drop > 0 and training:
+            if make:
+                call('subgnn_dropout', ptr(x), ptr(self.X[k]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+            x = self.X[k]
+        return ptr(x), 2 * H, None, 2 * H
+
+    def _last_rows(self, k, x_ptr, ldx, ids):
+        """the n_seq input rows at t = T-1: strided view of a dense input, or the last id of every walk."""
+        T = self.T
+        if ids is not None:
+            return x_ptr, ldx, ptr(self.ids_last)
+        return x_ptr + 4 * ((T - 1) * ldx), T * ldx, None
+
     def backward(self, E_ptr, dE_ptr, training, seed, step_dev, st, dense_dx=None):
         """consumes self.dEMB; accumulates into the gradient arena (and dE, or writes dense_dx for dense inputs)."""
-        a, H, D, M = self.arena, self.H, self.D, self.n_seq * self.T
+        a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
         dense = self.dense_x is not None
         if dense:
             E_ptr = ptr(self.dense_x)
@@ -273,35 +293,48 @@ class LstmRunner:
              a.addr('lstm.linear.bias', g), self.n_seq, D, 2 * H, None, st)
         call('subgnn_linear_bwd_input', ptr(self.dY), D, a.addr('lstm.linear.weight'), 2 * H, ptr(self.dAGG), 2 * H, None, self.n_seq, D,
              2 * H, 0, st)
-        call('subgnn_lstm_agg_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_seq, self.T, 2 * H, self.sum_mode, st)
+        call('subgnn_lstm_agg_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_seq, T, 2 * H, self.sum_mode, st)
         for k in range(self.nl - 1, -1, -1):
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
+            full = sr == T
             call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
-                 self.n_seq, self.T, H, sf, sr, st)
+                 self.n_seq, T, H, sf, sr, 0 if not full else 1, st)
             dG = ptr(self.G[k])
-            din = D if k == 0 else 2 * H
-            if k == 0:
-                x_ptr, ldx, ids = E_ptr, D, (None if dense else ptr(self.ids_flat))
-            else:
-                xin = self.X[k] if (self.p_drop > 0 and training) else self.OUT[k - 1]
-                x_ptr, ldx, ids = ptr(xin), 2 * H, None
-            call('subgnn_linear_bwd_weight', dG, 8 * H, x_ptr, ldx, ids, a.base_addr(o['weight_ih'], g), din, a.base_addr(o['bias_ih'], g),
-                 M, 8 * H, din, None, st)
-            call('subgnn_colsum', dG, 8 * H, a.base_addr(o['bias_hh'], g), M, 8 * H, None, st)
-            for d_ in range(2):
+            x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=False)
+            w_ih, gw_ih, gb_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g), a.base_addr(o['bias_ih'], g)
+            n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
+            dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
+            call('subgnn_linear_bwd_weight', dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, gb_ih, M, n_out, din, None, st)
+            if not full:
+                xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
+                call('subgnn_linear_bwd_weight', dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, gb_ih + 4 * 4 * H,
+                     self.n_seq, 4 * H, din, None, st)
+            call('subgnn_add_inplace', a.base_addr(o['bias_hh'], g), gb_ih, 8 * H, st)      # d b_hh == d b_ih
+            for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
                 call('subgnn_linear_bwd_weight', dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H,
                      ptr(self.hprev[d_]), a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, None, st)
             if k > 0:
-                call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), 2 * H, ptr(self.dOUT[k - 1]), 2 * H, None, M, 8 * H,
-                     2 * H, 0, st)
-                if self.p_drop > 0 and training:
-                    call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+                dx_ptr, lddx, scat = ptr(self.dOUT[k - 1]), 2 * H, None
             elif dense:
-                if dense_dx is not None:
-                    call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), D, ptr(dense_dx), D, None, M, 8 * H, D, 0, st)
+                if dense_dx is None:
+                    continue
+                dx_ptr, lddx, scat = ptr(dense_dx), D, None
             elif dE_ptr:
-                call('subgnn_linear_bwd_input', dG, 8 * H, a.base_addr(o['weight_ih']), D, dE_ptr, D, ptr(self.ids_flat), M, 8 * H, D, 1, st)
+                dx_ptr, lddx, scat = dE_ptr, D, ptr(self.ids_flat)
+            else:
+                continue
+            acc = 1 if scat is not None else 0
+            call('subgnn_linear_bwd_input', dG, 8 * H, w_ih, din, dx_ptr, lddx, scat, M, n_out, din, acc, st)
+            if not full:
+                if scat is not None:
+                    call('subgnn_linear_bwd_input', dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr, lddx, ptr(self.ids_last),
+                         self.n_seq, 4 * H, din, 1, st)
+                else:
+                    call('subgnn_linear_bwd_input', dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx,
+                         None, self.n_seq, 4 * H, din, 1, st)
+            if k > 0 and self.p_drop > 0 and training:
+                call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
 
 
 # ------------------------------------------------------------------------------------------------------
