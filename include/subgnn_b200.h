@@ -112,6 +112,11 @@ int subgnn_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, f
 int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
                              int M, int N, int K, const int* m_dev, void* stream);
 
+/* tcgen05 (kind::tf32, 3xTF32 error-compensated => fp32-accurate) versions of the three dense entry points above, same contracts
+ * (tcgemm.cu).  Rows must be 16-byte aligned (ld % 4 == 0). */
+int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const float* w, int ldw, const float* bias, float* y, int ldy,
+                         int M, int N, int K, int relu, void* stream);
+
 /* ---- walk-encoder LSTM (lstm.cu): SubGNN.py:60-88, anchor_patch_samplers.py:413-433 ------------------ */
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
