@@ -116,6 +116,10 @@ int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, 
  * (tcgemm.cu).  Rows must be 16-byte aligned (ld % 4 == 0). */
 int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const float* w, int ldw, const float* bias, float* y, int ldy,
                          int M, int N, int K, int relu, void* stream);
+int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx, const int* scatter_ids, int M, int N,
+                               int K, int accumulate, void* stream);
+int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
+                                int M, int N, int K, void* stream);
 
 /* ---- walk-encoder LSTM (lstm.cu): SubGNN.py:60-88, anchor_patch_samplers.py:413-433 ------------------ */
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);

@@ -38,6 +38,8 @@ SIGNATURES = {
     'subgnn_hop_table': [P, P, I, I, I, P, LL, P],
     'subgnn_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],
     'subgnn_tc_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],
+    'subgnn_tc_linear_bwd_input': [P, I, P, I, P, I, P, I, I, I, I, P],
+    'subgnn_tc_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P],
     'subgnn_linear_bwd_input': [P, I, P, I, P, I, P, I, I, I, I, P],
     'subgnn_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P, P],
     'subgnn_colsum': [P, I, P, I, I, P, P],

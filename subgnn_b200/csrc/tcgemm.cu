@@ -96,12 +96,43 @@ __device__ __forceinline__ void stage_kmajor(unsigned char* hi, unsigned char* l
   }
 }
 
+// stage ROWS x 32 from an "MN-major" source: for reduction index kk the tile rows are contiguous in memory
+// (colptr(kk) -> pointer to tile row 0 at reduction index kk, or nullptr).  Lanes run along the reduction index, so the
+// 4-byte shared-memory stores of a warp fall into one 128-byte row: conflict free; the 16-byte global loads of neighbouring
+// row chunks share 32-byte sectors through L1.
+template <int ROWS, class ColPtr>
+__device__ __forceinline__ void stage_mnmajor(unsigned char* hi, unsigned char* lo, int rows_valid, ColPtr colptr) {
+#pragma unroll
+  for (int i = 0; i < (ROWS * 8) / TC_THREADS; ++i) {
+    const int idx = i * TC_THREADS + threadIdx.x;
+    const int kk = idx & 31, rc = idx >> 5;            // reduction index inside the block, chunk of 4 tile rows
+    const int r0 = rc * 4;
+    const float* src = colptr(kk);
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (src) {
+      if (r0 + 3 < rows_valid) v = __ldg(reinterpret_cast<const float4*>(src + r0));
+      else {
+        if (r0 < rows_valid) v.x = src[r0];
+        if (r0 + 1 < rows_valid) v.y = src[r0 + 1];
+        if (r0 + 2 < rows_valid) v.z = src[r0 + 2];
+      }
+    }
+    float4 h, l;
+    split4(v, h, l);
+    const int c = kk >> 2, w4 = (kk & 3) * 4;
+    *reinterpret_cast<float*>(hi + sw128(r0, c) + w4) = h.x;     *reinterpret_cast<float*>(lo + sw128(r0, c) + w4) = l.x;
+    *reinterpret_cast<float*>(hi + sw128(r0 + 1, c) + w4) = h.y; *reinterpret_cast<float*>(lo + sw128(r0 + 1, c) + w4) = l.y;
+    *reinterpret_cast<float*>(hi + sw128(r0 + 2, c) + w4) = h.z; *reinterpret_cast<float*>(lo + sw128(r0 + 2, c) + w4) = l.z;
+    *reinterpret_cast<float*>(hi + sw128(r0 + 3, c) + w4) = h.w; *reinterpret_cast<float*>(lo + sw128(r0 + 3, c) + w4) = l.w;
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
-// y[m][n] = act(sum_k X[row(m)][k] W[n][k] + bias[n])      (same contract as subgnn_linear_fwd)
-template <int N_TILE>
-__global__ void __launch_bounds__(TC_THREADS)
-tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
-                     const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
+// Tile engine: D[128 x N_TILE] = sum over reduction blocks [kr0, kr1) of A_tile B_tile^T, 3xTF32, accumulator in TMEM.
+// stage_a(hi, lo, k0) / stage_b(hi, lo, k0) fill the operand tiles of the 32-wide reduction block starting at k0;
+// epi(row_in_tile, col_in_tile, float4 of 4 consecutive columns) consumes the result (16-byte stores / vector atomics).
+template <int N_TILE, class StageA, class StageB, class Epi>
+__device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB stage_b, Epi epi) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* a_hi = base;
@@ -111,7 +142,6 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * N_TILE;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(N_TILE) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -125,19 +155,11 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_M, N_TILE);
-  const int n_kb = (K + TC_KB - 1) / TC_KB;
+  const int n_kb = (kr1 - kr0 + TC_KB - 1) / TC_KB;
   for (int kb = 0; kb < n_kb; ++kb) {
     if (kb > 0) mbar_wait(&mma_bar, (uint32_t)((kb - 1) & 1));        // MMAs of the previous block have consumed the tiles
-    stage_kmajor<TC_M>(a_hi, a_lo, kb * TC_KB, K, [&](int r) -> const float* {
-      const int m = m0 + r;
-      if (m >= M) return nullptr;
-      const long long row = ids ? (long long)ids[m] : m;
-      return x + row * ldx;
-    });
-    stage_kmajor<N_TILE>(b_hi, b_lo, kb * TC_KB, K, [&](int r) -> const float* {
-      const int n = n0 + r;
-      return n < N ? w + (long long)n * ldw : nullptr;
-    });
+    stage_a(a_hi, a_lo, kr0 + kb * TC_KB);
+    stage_b(b_hi, b_lo, kr0 + kb * TC_KB);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -154,12 +176,11 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
       umma_commit(&mma_bar);                                            // arrives when every MMA issued so far has completed
     }
   }
-  mbar_wait(&mma_bar, (uint32_t)((n_kb - 1) & 1));
+  if (n_kb > 0) mbar_wait(&mma_bar, (uint32_t)((n_kb - 1) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // epilogue: warp w owns TMEM lanes (= output rows) 32w .. 32w+31, 32 columns per tcgen05.ld
-  const int m = m0 + warp * 32 + lane;
+  // epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31, 32 columns per tcgen05.ld
 #pragma unroll 1
-  for (int c0 = 0; c0 < N_TILE; c0 += 32) {
+  for (int c0 = 0; c0 < N_TILE && n_kb > 0; c0 += 32) {
     uint32_t r[32];
     const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)c0;
     asm volatile(
@@ -172,38 +193,183 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
           "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
         : "r"(taddr));
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-    if (m < M) {
-      float* dst = y + (long long)m * ldy + n0 + c0;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        const int n = n0 + c0 + j;
-        if (n < N) {
-          float v = __uint_as_float(r[j]);
-          if (bias) v += bias[n];
-          if (relu) v = fmaxf(v, 0.f);
-          dst[j] = v;
-        }
-      }
-    }
+    for (int j = 0; j < 32; j += 4)
+      epi(warp * 32 + lane, c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(N_TILE) : "memory");
 }
 
+// y[m][n] = act(sum_k X[row(m)][k] W[n][k] + bias[n])      (same contract as subgnn_linear_fwd)
+template <int N_TILE>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
+                     const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
+  const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * N_TILE;
+  tc_tile<N_TILE>(
+      0, K,
+      [&](unsigned char* hi, unsigned char* lo, int k0) {
+        stage_kmajor<TC_M>(hi, lo, k0, K, [&](int r) -> const float* {
+          const int m = m0 + r;
+          if (m >= M) return nullptr;
+          const long long row = ids ? (long long)ids[m] : m;
+          return x + row * ldx;
+        });
+      },
+      [&](unsigned char* hi, unsigned char* lo, int k0) {
+        stage_kmajor<N_TILE>(hi, lo, k0, K, [&](int r) -> const float* { return n0 + r < N ? w + (long long)(n0 + r) * ldw : nullptr; });
+      },
+      [&](int r, int c, float4 v) {
+        const int m = m0 + r, n = n0 + c;
+        if (m >= M || n >= N) return;
+        float* dst = y + (long long)m * ldy + n;
+        float t[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (bias && n + j < N) t[j] += bias[n + j];
+          if (relu) t[j] = fmaxf(t[j], 0.f);
+        }
+        if (n + 3 < N && (((size_t)dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
+        else for (int j = 0; j < 4 && n + j < N; ++j) dst[j] = t[j];
+      });
+}
+
+// dx[row(m)][k] (+)= sum_n dy[m][n] W[n][k]       (same contract as subgnn_linear_bwd_input)
+template <int N_TILE>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w, int ldw, float* __restrict__ dx, int lddx,
+                           const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate) {
+  const int m0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;      // output tile: rows m, columns k
+  tc_tile<N_TILE>(
+      0, N,
+      [&](unsigned char* hi, unsigned char* lo, int n0) {
+        stage_kmajor<TC_M>(hi, lo, n0, N, [&](int r) -> const float* { return m0 + r < M ? dy + (long long)(m0 + r) * ldy : nullptr; });
+      },
+      [&](unsigned char* hi, unsigned char* lo, int n0) {             // B[k][n] = W[n][k]: rows k contiguous in memory for fixed n
+        stage_mnmajor<N_TILE>(hi, lo, K - k0o, [&](int kk) -> const float* { return n0 + kk < N ? w + (long long)(n0 + kk) * ldw + k0o : nullptr; });
+      },
+      [&](int r, int c, float4 v) {
+        const int m = m0 + r, k = k0o + c;
+        if (m >= M || k >= K) return;
+        const float t[4] = {v.x, v.y, v.z, v.w};
+        if (scatter_ids) {
+          const int row = scatter_ids[m];
+          if (row == 0) return;
+          float* dst = dx + (long long)row * lddx + k;
+          if (k + 3 < K && (((size_t)dst) & 15) == 0) atomicAdd(reinterpret_cast<float4*>(dst), v);     // red.global.add.v4.f32
+          else for (int j = 0; j < 4 && k + j < K; ++j) atomicAdd(dst + j, t[j]);
+          return;
+        }
+        float* dst = dx + (long long)m * lddx + k;
+        if (k + 3 < K && (((size_t)dst) & 15) == 0) {
+          float4 o = v;
+          if (accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
+          *reinterpret_cast<float4*>(dst) = o;
+        } else {
+          for (int j = 0; j < 4 && k + j < K; ++j) dst[j] = accumulate ? dst[j] + t[j] : t[j];
+        }
+      });
+}
+
+// dW[n][k] += sum_m dy[m][n] X[row(m)][k]          (same contract as subgnn_linear_bwd_weight, bias gradient excluded)
+template <int N_TILE>
+__global__ void __launch_bounds__(TC_THREADS)
+tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
+                            float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk) {
+  const int n0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;       // output tile: rows n, columns k
+  const int mr0 = blockIdx.z * m_chunk, mr1 = min(M, mr0 + m_chunk);
+  if (mr0 >= mr1) return;
+  tc_tile<N_TILE>(
+      mr0, mr1,
+      [&](unsigned char* hi, unsigned char* lo, int mb) {             // A[n][m] = dy[m][n]
+        stage_mnmajor<TC_M>(hi, lo, N - n0, [&](int kk) -> const float* { return mb + kk < mr1 ? dy + (long long)(mb + kk) * ldy + n0 : nullptr; });
+      },
+      [&](unsigned char* hi, unsigned char* lo, int mb) {             // B[k][m] = X[row(m)][k]
+        stage_mnmajor<N_TILE>(hi, lo, K - k0o, [&](int kk) -> const float* {
+          const int m = mb + kk;
+          if (m >= mr1) return nullptr;
+          const long long row = ids ? (long long)ids[m] : m;
+          return x + row * ldx + k0o;
+        });
+      },
+      [&](int r, int c, float4 v) {
+        const int n = n0 + r, k = k0o + c;
+        if (n >= N || k >= K) return;
+        float* dst = dw + (long long)n * lddw + k;
+        if (k + 3 < K && (((size_t)dst) & 15) == 0) atomicAdd(reinterpret_cast<float4*>(dst), v);
+        else {
+          const float t[4] = {v.x, v.y, v.z, v.w};
+          for (int j = 0; j < 4 && k + j < K; ++j) atomicAdd(dst + j, t[j]);
+        }
+      });
+}
+
+static bool tc_aligned(const void* p, int ld) { return (ld % 4) == 0 && (((size_t)p) & 15) == 0; }
+template <int NT> static size_t tc_smem() { return (size_t)(2 * TC_M * 128 + 2 * NT * 128) + 1024; }
+
 extern "C" {
 
 int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const float* w, int ldw, const float* bias, float* y, int ldy,
                          int M, int N, int K, int relu, void* stream) {
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
-  SG_REQUIRE((ldx % 4) == 0 && (ldw % 4) == 0 && (((size_t)x | (size_t)w) & 15) == 0, "tensor-core path needs 16-byte aligned rows");
+  SG_REQUIRE(tc_aligned(x, ldx) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
-  constexpr int NT = 128;
-  const size_t smem = (size_t)(2 * TC_M * 128 + 2 * NT * 128) + 1024;
-  cudaFuncSetAttribute(tc_linear_fwd_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  dim3 grid(sg_div_up(N, NT), sg_div_up(M, TC_M));
-  tc_linear_fwd_kernel<NT><<<grid, TC_THREADS, smem, (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+  if (N <= 64) {
+    cudaFuncSetAttribute(tc_linear_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
+    dim3 grid(sg_div_up(N, 64), sg_div_up(M, TC_M));
+    tc_linear_fwd_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+  } else {
+    cudaFuncSetAttribute(tc_linear_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
+    dim3 grid(sg_div_up(N, 128), sg_div_up(M, TC_M));
+    tc_linear_fwd_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+  }
   return subgnn_check_launch("tc_linear_fwd_kernel");
+}
+
+int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx, const int* scatter_ids, int M, int N,
+                               int K, int accumulate, void* stream) {
+  SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
+  SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
+  if (M == 0) return SUBGNN_OK;
+  if (K <= 64) {
+    cudaFuncSetAttribute(tc_linear_bwd_input_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
+    dim3 grid(sg_div_up(K, 64), sg_div_up(M, TC_M));
+    tc_linear_bwd_input_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate);
+  } else {
+    cudaFuncSetAttribute(tc_linear_bwd_input_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
+    dim3 grid(sg_div_up(K, 128), sg_div_up(M, TC_M));
+    tc_linear_bwd_input_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate);
+  }
+  return subgnn_check_launch("tc_linear_bwd_input_kernel");
+}
+
+int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
+                                int M, int N, int K, void* stream) {
+  SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
+  SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(x, ldx), "tensor-core path needs 16-byte aligned rows");
+  if (M == 0) return SUBGNN_OK;
+  const int nt = K <= 64 ? 64 : 128;
+  const int tiles = sg_div_up(K, nt) * sg_div_up(N, TC_M);
+  int splits = (3 * subgnn_sm_count() + tiles - 1) / tiles;          // ~3 resident CTAs per SM
+  const int max_splits = sg_div_up(M, 4 * TC_KB);
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  const int m_chunk = sg_div_up(sg_div_up(M, splits), TC_KB) * TC_KB;
+  splits = sg_div_up(M, m_chunk);
+  dim3 grid(sg_div_up(K, nt), sg_div_up(N, TC_M), splits);
+  if (nt == 64) {
+    cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
+    tc_linear_bwd_weight_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+  } else {
+    cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
+    tc_linear_bwd_weight_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+  }
+  int rc = subgnn_check_launch("tc_linear_bwd_weight_kernel");
+  if (rc) return rc;
+  if (db) rc = subgnn_colsum(dy, ldy, db, M, N, nullptr, stream);
+  return rc;
 }
 
 }  // extern "C"

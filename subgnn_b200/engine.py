@@ -230,6 +230,10 @@ class LstmRunner:
         self.ids_flat = self.walks.reshape(-1).contiguous() if walks is not None else None
         self.ids_last = self.walks[:, -1].contiguous() if walks is not None else None
         self.dense_x = None
+        # tensor-core (tcgen05, 3xTF32) projections need 16-byte aligned rows; otherwise the FFMA tiles are used
+        self.use_tc = (self.D % 4 == 0) and hp.get('b200_tensor_core_gemm', True)
+        self.fwd_fn = 'subgnn_tc_linear_fwd' if self.use_tc else 'subgnn_linear_fwd'
+        self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
 
     def steps(self, k):
         top = k == self.nl - 1
@@ -248,19 +252,25 @@ class LstmRunner:
             sf, sr = self.steps(k)
             w_ih, G = a.base_addr(o['weight_ih']), ptr(self.G[k])
             if sr == T:
-                call('subgnn_linear_fwd', x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 8 * H, din, 0, st)
+                call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 8 * H, din, 0, st)
             else:
                 # 'last' aggregator, top layer: the reverse direction is only ever read at t = T-1 (SubGNN.py:83), so its
                 # input projection is computed for those n_seq rows only
-                call('subgnn_linear_fwd', x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
+                call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
                 xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
-                call('subgnn_linear_fwd', xl, ldxl, idsl, w_ih + 4 * (4 * H * din), din, self.bsum[k].data_ptr() + 4 * 4 * H,
+                call(self.fwd_fn, xl, ldxl, idsl, w_ih + 4 * (4 * H * din), din, self.bsum[k].data_ptr() + 4 * 4 * H,
                      G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, st)
             call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
         call('subgnn_lstm_agg_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_seq, T, 2 * H, self.sum_mode, st)
         call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, a.addr('lstm.linear.bias'),
              ptr(self.Y), D, self.n_seq, D, 2 * H, 0, st)
         call('subgnn_group_sum', ptr(self.Y), ptr(self.EMB), self.n_groups, self.W, D, st)
+
+    def _wgrad(self, dy, ldy, x, ldx, ids, dw, lddw, db, M, N, K, st):
+        if self.use_tc and M >= 256:
+            call('subgnn_tc_linear_bwd_weight', dy, ldy, x, ldx, ids, dw, lddw, db, M, N, K, st)
+        else:
+            call('subgnn_linear_bwd_weight', dy, ldy, x, ldx, ids, dw, lddw, db, M, N, K, None, st)
 
     def _layer_input(self, k, E_ptr, training, seed, step_dev, st, make=True):
         """(x pointer, leading dim, gather ids, K) of layer k's input rows (all n_seq*T of them)."""
@@ -305,15 +315,14 @@ class LstmRunner:
             w_ih, gw_ih, gb_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g), a.base_addr(o['bias_ih'], g)
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
-            call('subgnn_linear_bwd_weight', dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, gb_ih, M, n_out, din, None, st)
+            self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, gb_ih, M, n_out, din, st)
             if not full:
                 xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
-                call('subgnn_linear_bwd_weight', dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, gb_ih + 4 * 4 * H,
-                     self.n_seq, 4 * H, din, None, st)
+                self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, gb_ih + 4 * 4 * H, self.n_seq, 4 * H, din, st)
             call('subgnn_add_inplace', a.base_addr(o['bias_hh'], g), gb_ih, 8 * H, st)      # d b_hh == d b_ih
             for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
-                call('subgnn_linear_bwd_weight', dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H,
-                     ptr(self.hprev[d_]), a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, None, st)
+                self._wgrad(dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H, ptr(self.hprev[d_]),
+                            a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, st)
             if k > 0:
                 dx_ptr, lddx, scat = ptr(self.dOUT[k - 1]), 2 * H, None
             elif dense:
@@ -325,13 +334,13 @@ class LstmRunner:
             else:
                 continue
             acc = 1 if scat is not None else 0
-            call('subgnn_linear_bwd_input', dG, 8 * H, w_ih, din, dx_ptr, lddx, scat, M, n_out, din, acc, st)
+            call(self.bwi_fn, dG, 8 * H, w_ih, din, dx_ptr, lddx, scat, M, n_out, din, acc, st)
             if not full:
                 if scat is not None:
-                    call('subgnn_linear_bwd_input', dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr, lddx, ptr(self.ids_last),
+                    call(self.bwi_fn, dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr, lddx, ptr(self.ids_last),
                          self.n_seq, 4 * H, din, 1, st)
                 else:
-                    call('subgnn_linear_bwd_input', dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx,
+                    call(self.bwi_fn, dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx,
                          None, self.n_seq, 4 * H, din, 1, st)
             if k > 0 and self.p_drop > 0 and training:
                 call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
