@@ -125,8 +125,9 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
                           void* stream);
+/* db_ih / db_hh (optional, [2][4H]): += column sums of d(pre-activation), the gradient of both bias vectors */
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
-                          int steps_fwd, int steps_rev, int zero_untaken, void* stream);
+                          int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream);
 int subgnn_add_inplace(float* dst, const float* src, int n, void* stream);
 int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
 int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);

@@ -45,7 +45,7 @@ SIGNATURES = {
     'subgnn_colsum': [P, I, P, I, I, P, P],
     'subgnn_lstm_prep': [P, P, P, P, P, I, P],
     'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
-    'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P],
+    'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'subgnn_add_inplace': [P, P, I, P],
     'subgnn_lstm_agg_fwd': [P, P, I, I, I, I, P],
     'subgnn_lstm_agg_bwd': [P, P, I, I, I, I, P],

@@ -22,12 +22,36 @@
 
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.f / (1.f + expf(-x)); }
 
+// One-instruction staging of the recurrent weights: a 1-D TMA bulk copy (cp.async.bulk, SASS UBLKCP) global -> shared that
+// completes on an mbarrier, issued by one thread while the CTA sets up its state.  The round-1 profile showed 25% of the
+// recurrence kernels' stall samples on the per-thread load -> st.shared staging loop this replaces.
+__device__ __forceinline__ uint32_t lstm_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void bulk_g2s_issue(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(lstm_smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(lstm_smem_u32(bar)), "r"(bytes) : "memory");
+  // chunks of at most 32 KB keep every copy well inside the instruction's size field
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(lstm_smem_u32(reinterpret_cast<const char*>(dst) + off)), "l"(reinterpret_cast<const char*>(src) + off), "r"(n),
+                    "r"(lstm_smem_u32(bar)) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_g2s_wait(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLSTM_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+      "@P1 bra LSTM_DONE;\n\tbra LSTM_WAIT;\n\tLSTM_DONE:\n\t}\n"
+      :: "r"(lstm_smem_u32(bar)) : "memory");
+}
+
 // grid (ceil(n_seq / S_TILE), 2 directions); block = 4H rounded up to 32.
 // W_SMEM: the transposed recurrent weights of this direction (H x 4H fp32) are staged once in shared memory
 // (H <= 64: 64 KB); otherwise they are streamed from L1/L2 every step.  The gate pre-activations of step t+1 are
 // prefetched into registers while step t's matvec runs.
-template <bool W_SMEM>
-__global__ void __launch_bounds__(1024)
+template <bool W_SMEM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2][H][4H]*/, float* __restrict__ OUT,
                       float* __restrict__ CS, int n_seq, int T, int H, int steps_fwd, int steps_rev) {
   extern __shared__ float sm[];
@@ -42,18 +66,20 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
   const int H4 = 4 * H;
   const float* wt = WhhT + (size_t)dir * H * H4;
   const int n_steps = dir == 0 ? steps_fwd : steps_rev;
-  for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { hbuf[e] = 0.f; cbuf[e] = 0.f; }
+  __shared__ uint64_t wbar;
   if (W_SMEM) {
-    for (int e = threadIdx.x; e < H * H4; e += blockDim.x) wsm[e] = wt[e];
+    if (threadIdx.x == 0) bulk_g2s_issue(wsm, wt, (uint32_t)(H * H4 * sizeof(float)), &wbar);
     wt = wsm;
   }
+  for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { hbuf[e] = 0.f; cbuf[e] = 0.f; }
   float gnext[S_TILE];
   if (j < H4 && n_steps > 0) {
     const int t0 = dir == 0 ? 0 : T - 1;
 #pragma unroll
     for (int s = 0; s < S_TILE; ++s) gnext[s] = s < ns ? G[(((size_t)(seq0 + s) * T + t0) * 2 + dir) * H4 + j] : 0.f;
   }
-  __syncthreads();
+  __syncthreads();                       // also publishes the mbarrier initialisation to the waiting threads
+  if (W_SMEM) bulk_g2s_wait(&wbar);
   for (int st = 0; st < n_steps; ++st) {
     const int t = dir == 0 ? st : T - 1 - st;
     if (j < H4) {
@@ -111,11 +137,13 @@ lstm_recur_fwd_kernel(float* __restrict__ G, const float* __restrict__ WhhT /*[2
 
 // BPTT.  dOUT [n_seq*T][2H] gradient w.r.t. this layer's outputs; G holds gate activations on entry and
 // d(pre-activation) on exit (zero for steps that were not taken).  Whh [2][4H][H] native layout.
-template <bool W_SMEM>
-__global__ void __launch_bounds__(1024)
+// db_ih / db_hh (optional, [2][4H]): the bias gradients (column sums of d(pre-activation) over every row this CTA owns,
+// identical for the two bias vectors) are accumulated in registers along the recurrence and added once per CTA.
+template <bool W_SMEM, int BLOCK>
+__global__ void __launch_bounds__(BLOCK)
 lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT,
                       const float* __restrict__ CS, const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd,
-                      int steps_rev, int zero_untaken) {
+                      int steps_rev, int zero_untaken, float* __restrict__ db_ih, float* __restrict__ db_hh) {
   extern __shared__ float sm[];
   const int H4 = 4 * H;
   float* dgate = sm;                        // [S_TILE][4H]
@@ -127,14 +155,17 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
   const int seq0 = blockIdx.x * S_TILE;
   const int ns = min(S_TILE, n_seq - seq0);
   const float* w = Whh + (size_t)dir * H4 * H;
+  __shared__ uint64_t wbar;
   if (W_SMEM) {
-    for (int e = threadIdx.x; e < H4 * H; e += blockDim.x) wsm[e] = w[e];
+    if (threadIdx.x == 0) bulk_g2s_issue(wsm, w, (uint32_t)(H4 * H * sizeof(float)), &wbar);
     w = wsm;
   }
   const int n_steps = dir == 0 ? steps_fwd : steps_rev;
   for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x) { dh_rec[e] = 0.f; dc_rec[e] = 0.f; }
   for (int e = threadIdx.x; e < S_TILE * H4; e += blockDim.x) dgate[e] = 0.f;
+  float bias_acc = 0.f;
   __syncthreads();
+  if (W_SMEM) bulk_g2s_wait(&wbar);
   for (int st = n_steps - 1; st >= 0; --st) {
     const int t = dir == 0 ? st : T - 1 - st;
     const int t_prev = dir == 0 ? t - 1 : t + 1;
@@ -158,6 +189,12 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
     __syncthreads();
     // dh_rec[s][k] = sum_j dgate[s][j] * Whh[j][k]; thread -> (k, quarter of j)
     if (threadIdx.x < H4) {
+      {
+        float bs = 0.f;                                         // rows s >= ns of dgate stay zero
+#pragma unroll
+        for (int s = 0; s < S_TILE; ++s) bs += dgate[s * H4 + threadIdx.x];
+        bias_acc += bs;
+      }
       const int k = threadIdx.x % H, part = threadIdx.x / H;
       float acc[S_TILE];
 #pragma unroll
@@ -187,6 +224,10 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
     for (int e = threadIdx.x; e < S_TILE * H; e += blockDim.x)
       dh_rec[e] = red[e] + red[S_TILE * H + e] + red[2 * S_TILE * H + e] + red[3 * S_TILE * H + e];
     __syncthreads();
+  }
+  if (threadIdx.x < H4 && bias_acc != 0.f) {
+    if (db_ih) atomicAdd(db_ih + (size_t)dir * H4 + threadIdx.x, bias_acc);
+    if (db_hh) atomicAdd(db_hh + (size_t)dir * H4 + threadIdx.x, bias_acc);
   }
   // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations) unless the
   // caller never reads them (zero_untaken == 0)
@@ -295,37 +336,48 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
   if (n_seq == 0) return SUBGNN_OK;
   size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
-  const bool w_smem = smem + wbytes <= 100 * 1024;          // two CTAs per SM stay resident
+  const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh_t) & 15) == 0;   // two CTAs per SM stay resident; bulk copy: 16-byte granules
   dim3 grid(sg_div_up(n_seq, S_TILE), 2);
+  const int block = lstm_block(H);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LSTM_FWD_LAUNCH(WS, BL)                                                                                               \
+  do {                                                                                                                        \
+    cudaFuncSetAttribute(lstm_recur_fwd_kernel<WS, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    lstm_recur_fwd_kernel<WS, BL><<<grid, block, smem, st>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);           \
+  } while (0)
   if (w_smem) {
     smem += wbytes;
-    cudaFuncSetAttribute(lstm_recur_fwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_recur_fwd_kernel<true><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_fwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_recur_fwd_kernel<false><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev);
-  }
+    LSTM_FWD_LAUNCH(true, 256);                               // w_smem implies H <= 64, i.e. at most 256 threads
+  } else if (block <= 256) LSTM_FWD_LAUNCH(false, 256);
+  else if (block <= 512) LSTM_FWD_LAUNCH(false, 512);
+  else LSTM_FWD_LAUNCH(false, 1024);
+#undef LSTM_FWD_LAUNCH
   return subgnn_check_launch("lstm_recur_fwd_kernel");
 }
 
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
-                          int steps_fwd, int steps_rev, int zero_untaken, void* stream) {
+                          int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
   size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
-  const bool w_smem = smem + wbytes <= 100 * 1024;
+  const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh) & 15) == 0;
   dim3 grid(sg_div_up(n_seq, S_TILE), 2);
+  const int block = lstm_block(H);
+  cudaStream_t st = (cudaStream_t)stream;
+#define LSTM_BWD_LAUNCH(WS, BL)                                                                                               \
+  do {                                                                                                                        \
+    cudaFuncSetAttribute(lstm_recur_bwd_kernel<WS, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);              \
+    lstm_recur_bwd_kernel<WS, BL><<<grid, block, smem, st>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev,        \
+                                                             zero_untaken, db_ih, db_hh);                                     \
+  } while (0)
   if (w_smem) {
     smem += wbytes;
-    cudaFuncSetAttribute(lstm_recur_bwd_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_recur_bwd_kernel<true><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev,
-                                                                                  zero_untaken);
-  } else {
-    if (smem > 48 * 1024) cudaFuncSetAttribute(lstm_recur_bwd_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    lstm_recur_bwd_kernel<false><<<grid, lstm_block(H), smem, (cudaStream_t)stream>>>(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev,
-                                                                                   zero_untaken);
-  }
+    LSTM_BWD_LAUNCH(true, 256);
+  } else if (block <= 256) LSTM_BWD_LAUNCH(false, 256);
+  else if (block <= 512) LSTM_BWD_LAUNCH(false, 512);
+  else LSTM_BWD_LAUNCH(false, 1024);
+#undef LSTM_BWD_LAUNCH
   return subgnn_check_launch("lstm_recur_bwd_kernel");
 }
 

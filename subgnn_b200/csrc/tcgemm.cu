@@ -70,69 +70,108 @@ __device__ __forceinline__ void split4(const float4 v, float4& hi, float4& lo) {
 // byte offset of (row r, 16-byte chunk c) inside a K-major SWIZZLE_128B tile
 __device__ __forceinline__ uint32_t sw128(int r, int c) { return (uint32_t)(r * 128 + ((c ^ (r & 7)) << 4)); }
 
-// stage ROWS x 32 floats (K-contiguous source rows) into hi / lo tiles; fetch(row, k) -> const float* or nullptr
-template <int ROWS, class RowPtr>
-__device__ __forceinline__ void stage_kmajor(unsigned char* hi, unsigned char* lo, int k0, int K, RowPtr rowptr) {
-#pragma unroll
-  for (int i = 0; i < (ROWS * 8) / TC_THREADS; ++i) {
-    const int idx = i * TC_THREADS + threadIdx.x;
-    const int r = idx >> 3, c = idx & 7;
-    const int k = k0 + c * 4;
-    const float* src = rowptr(r);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src) {
-      if (k + 3 < K) v = __ldg(reinterpret_cast<const float4*>(src + k));
-      else {
-        if (k < K) v.x = src[k];
-        if (k + 1 < K) v.y = src[k + 1];
-        if (k + 2 < K) v.z = src[k + 2];
-      }
-    }
-    float4 h, l;
-    split4(v, h, l);
-    const uint32_t off = sw128(r, c);
-    *reinterpret_cast<float4*>(hi + off) = h;
-    *reinterpret_cast<float4*>(lo + off) = l;
-  }
-}
+// ------------------------------------------------------------------------------------------------
+// Operand stagers.  A stager first ISSUES all of a thread's global loads for one 32-wide reduction block into
+// registers (load), and later splits them into hi / lo and writes the SWIZZLE_128B tiles (store).  Keeping the two
+// phases apart lets the tile loop issue block kb+1's loads before it waits on block kb's MMAs, and keeps the 8-16
+// loads of one thread in flight together instead of one load -> use chain per row (the round-1 profile showed the
+// kernels stalled on exactly those chains).
 
-// stage ROWS x 32 from an "MN-major" source: for reduction index kk the tile rows are contiguous in memory
-// (colptr(kk) -> pointer to tile row 0 at reduction index kk, or nullptr).  Lanes run along the reduction index, so the
-// 4-byte shared-memory stores of a warp fall into one 128-byte row: conflict free; the 16-byte global loads of neighbouring
-// row chunks share 32-byte sectors through L1.
-template <int ROWS, class ColPtr>
-__device__ __forceinline__ void stage_mnmajor(unsigned char* hi, unsigned char* lo, int rows_valid, ColPtr colptr) {
+// K-major source: tile row r is a K-contiguous row in memory.  rowptr(r) -> const float* or nullptr (zero row).
+template <int ROWS>
+struct KMajorStager {
+  static constexpr int IT = (ROWS * 8) / TC_THREADS;
+  const float* rp[IT];
+  float4 v[IT];
+  int K;
+  template <class RowPtr>
+  __device__ __forceinline__ void init(int K_, RowPtr rowptr) {
+    K = K_;
 #pragma unroll
-  for (int i = 0; i < (ROWS * 8) / TC_THREADS; ++i) {
-    const int idx = i * TC_THREADS + threadIdx.x;
-    const int kk = idx & 31, rc = idx >> 5;            // reduction index inside the block, chunk of 4 tile rows
-    const int r0 = rc * 4;
-    const float* src = colptr(kk);
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (src) {
-      if (r0 + 3 < rows_valid) v = __ldg(reinterpret_cast<const float4*>(src + r0));
-      else {
-        if (r0 < rows_valid) v.x = src[r0];
-        if (r0 + 1 < rows_valid) v.y = src[r0 + 1];
-        if (r0 + 2 < rows_valid) v.z = src[r0 + 2];
-      }
-    }
-    float4 h, l;
-    split4(v, h, l);
-    const int c = kk >> 2, w4 = (kk & 3) * 4;
-    *reinterpret_cast<float*>(hi + sw128(r0, c) + w4) = h.x;     *reinterpret_cast<float*>(lo + sw128(r0, c) + w4) = l.x;
-    *reinterpret_cast<float*>(hi + sw128(r0 + 1, c) + w4) = h.y; *reinterpret_cast<float*>(lo + sw128(r0 + 1, c) + w4) = l.y;
-    *reinterpret_cast<float*>(hi + sw128(r0 + 2, c) + w4) = h.z; *reinterpret_cast<float*>(lo + sw128(r0 + 2, c) + w4) = l.z;
-    *reinterpret_cast<float*>(hi + sw128(r0 + 3, c) + w4) = h.w; *reinterpret_cast<float*>(lo + sw128(r0 + 3, c) + w4) = l.w;
+    for (int i = 0; i < IT; ++i) rp[i] = rowptr((i * TC_THREADS + (int)threadIdx.x) >> 3);
   }
-}
+  __device__ __forceinline__ void load(int k0) {
+    const int k = k0 + ((int)threadIdx.x & 7) * 4;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rp[i]) {
+        if (k + 3 < K) t = __ldg(reinterpret_cast<const float4*>(rp[i] + k));
+        else {
+          if (k < K) t.x = rp[i][k];
+          if (k + 1 < K) t.y = rp[i][k + 1];
+          if (k + 2 < K) t.z = rp[i][k + 2];
+        }
+      }
+      v[i] = t;
+    }
+  }
+  __device__ __forceinline__ void store(unsigned char* hi, unsigned char* lo) const {
+    const int c = (int)threadIdx.x & 7;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const int r = (i * TC_THREADS + (int)threadIdx.x) >> 3;
+      float4 h, l;
+      split4(v[i], h, l);
+      const uint32_t off = sw128(r, c);
+      *reinterpret_cast<float4*>(hi + off) = h;
+      *reinterpret_cast<float4*>(lo + off) = l;
+    }
+  }
+};
+
+// "MN-major" source: for reduction index kk the tile rows are contiguous in memory (colptr(k) -> pointer to tile row 0
+// at absolute reduction index k, or nullptr).  Lanes run along the reduction index, so the 4-byte shared-memory stores
+// of a warp fall into one 128-byte row: conflict free; the 16-byte global loads of neighbouring row chunks share
+// 32-byte sectors through L1.
+template <int ROWS>
+struct MNMajorStager {
+  static constexpr int IT = (ROWS * 8) / TC_THREADS;
+  float4 v[IT];
+  template <class ColPtr>
+  __device__ __forceinline__ void load(int k0, int rows_valid, ColPtr colptr) {
+    const int kk = (int)threadIdx.x & 31;
+    const float* src = colptr(k0 + kk);
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const int r0 = (i * (TC_THREADS / 32) + ((int)threadIdx.x >> 5)) * 4;
+      float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src) {
+        if (r0 + 3 < rows_valid) t = __ldg(reinterpret_cast<const float4*>(src + r0));
+        else {
+          if (r0 < rows_valid) t.x = src[r0];
+          if (r0 + 1 < rows_valid) t.y = src[r0 + 1];
+          if (r0 + 2 < rows_valid) t.z = src[r0 + 2];
+        }
+      }
+      v[i] = t;
+    }
+  }
+  __device__ __forceinline__ void store(unsigned char* hi, unsigned char* lo) const {
+    const int kk = (int)threadIdx.x & 31;
+    const int c = kk >> 2, w4 = (kk & 3) * 4;
+#pragma unroll
+    for (int i = 0; i < IT; ++i) {
+      const int r0 = (i * (TC_THREADS / 32) + ((int)threadIdx.x >> 5)) * 4;
+      float4 h, l;
+      split4(v[i], h, l);
+      *reinterpret_cast<float*>(hi + sw128(r0, c) + w4) = h.x;     *reinterpret_cast<float*>(lo + sw128(r0, c) + w4) = l.x;
+      *reinterpret_cast<float*>(hi + sw128(r0 + 1, c) + w4) = h.y; *reinterpret_cast<float*>(lo + sw128(r0 + 1, c) + w4) = l.y;
+      *reinterpret_cast<float*>(hi + sw128(r0 + 2, c) + w4) = h.z; *reinterpret_cast<float*>(lo + sw128(r0 + 2, c) + w4) = l.z;
+      *reinterpret_cast<float*>(hi + sw128(r0 + 3, c) + w4) = h.w; *reinterpret_cast<float*>(lo + sw128(r0 + 3, c) + w4) = l.w;
+    }
+  }
+};
 
 // ------------------------------------------------------------------------------------------------
 // Tile engine: D[128 x N_TILE] = sum over reduction blocks [kr0, kr1) of A_tile B_tile^T, 3xTF32, accumulator in TMEM.
-// stage_a(hi, lo, k0) / stage_b(hi, lo, k0) fill the operand tiles of the 32-wide reduction block starting at k0;
-// epi(row_in_tile, col_in_tile, float4 of 4 consecutive columns) consumes the result (16-byte stores / vector atomics).
-template <int N_TILE, class StageA, class StageB, class Epi>
-__device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB stage_b, Epi epi) {
+// load_a(k0) / load_b(k0) issue the global loads of the 32-wide reduction block starting at k0 into the stagers'
+// registers, store_a / store_b write the operand tiles; epi(row_in_tile, col_in_tile, float4 of 4 consecutive columns)
+// consumes the result.  The epilogue transposes each warp's 32 x 32 TMEM slab through shared memory so that 8 lanes
+// cover 128 contiguous bytes of one output row (coalesced 16-byte stores / vector atomics).
+#define TC_EPI_LD 36      // padded row length (floats) of the per-warp transposition slab: conflict-free float4 in both directions
+template <int N_TILE, class LoadA, class LoadB, class StoreA, class StoreB, class Epi>
+__device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB load_b, StoreA store_a, StoreB store_b, Epi epi) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   unsigned char* a_hi = base;
@@ -142,8 +181,10 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB
   __shared__ uint64_t mma_bar;
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kb = (kr1 - kr0 + TC_KB - 1) / TC_KB;
+  if (n_kb > 0) { load_a(kr0); load_b(kr0); }                           // first block's loads fly during the TMEM allocation
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(N_TILE) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(&tmem_base_s)), "n"(N_TILE < 32 ? 32 : N_TILE) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
@@ -155,11 +196,11 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_M, N_TILE);
-  const int n_kb = (kr1 - kr0 + TC_KB - 1) / TC_KB;
   for (int kb = 0; kb < n_kb; ++kb) {
     if (kb > 0) mbar_wait(&mma_bar, (uint32_t)((kb - 1) & 1));        // MMAs of the previous block have consumed the tiles
-    stage_a(a_hi, a_lo, kr0 + kb * TC_KB);
-    stage_b(b_hi, b_lo, kr0 + kb * TC_KB);
+    store_a(a_hi, a_lo);
+    store_b(b_hi, b_lo);
+    if (kb + 1 < n_kb) { load_a(kr0 + (kb + 1) * TC_KB); load_b(kr0 + (kb + 1) * TC_KB); }   // in flight while the tensor core works
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");       // generic-proxy smem writes -> visible to the tensor core
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -178,7 +219,8 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB
   }
   if (n_kb > 0) mbar_wait(&mma_bar, (uint32_t)((n_kb - 1) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-  // epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31, 32 columns per tcgen05.ld
+  // epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31, 32 columns per tcgen05.ld; the operand tiles are free now
+  float* slab = reinterpret_cast<float*>(base) + warp * (32 * TC_EPI_LD);
 #pragma unroll 1
   for (int c0 = 0; c0 < N_TILE && n_kb > 0; c0 += 32) {
     uint32_t r[32];
@@ -195,11 +237,19 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, StageA stage_a, StageB
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
     for (int j = 0; j < 32; j += 4)
-      epi(warp * 32 + lane, c0 + j, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+      *reinterpret_cast<float4*>(slab + lane * TC_EPI_LD + j) =
+          make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+    __syncwarp();
+#pragma unroll
+    for (int it = 0; it < 8; ++it) {
+      const int row = it * 4 + (lane >> 3), cc = (lane & 7) * 4;
+      if (c0 + cc < N_TILE) epi(warp * 32 + row, c0 + cc, *reinterpret_cast<const float4*>(slab + row * TC_EPI_LD + cc));
+    }
+    __syncwarp();
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
-  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(N_TILE) : "memory");
+  if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(tmem_d), "n"(N_TILE < 32 ? 32 : N_TILE) : "memory");
 }
 
 // y[m][n] = act(sum_k X[row(m)][k] W[n][k] + bias[n])      (same contract as subgnn_linear_fwd)
@@ -207,29 +257,30 @@ template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
                      const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
+  __shared__ __align__(16) float s_bias[N_TILE];
   const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * N_TILE;
+  for (int i = threadIdx.x; i < N_TILE; i += TC_THREADS) s_bias[i] = (bias && n0 + i < N) ? bias[n0 + i] : 0.f;   // visible after tc_tile's barriers
+  KMajorStager<TC_M> sa;
+  KMajorStager<N_TILE> sb;
+  sa.init(K, [&](int r) -> const float* {
+    const int m = m0 + r;
+    if (m >= M) return nullptr;
+    const long long row = ids ? (long long)ids[m] : m;
+    return x + row * ldx;
+  });
+  sb.init(K, [&](int r) -> const float* { return n0 + r < N ? w + (long long)(n0 + r) * ldw : nullptr; });
   tc_tile<N_TILE>(
-      0, K,
-      [&](unsigned char* hi, unsigned char* lo, int k0) {
-        stage_kmajor<TC_M>(hi, lo, k0, K, [&](int r) -> const float* {
-          const int m = m0 + r;
-          if (m >= M) return nullptr;
-          const long long row = ids ? (long long)ids[m] : m;
-          return x + row * ldx;
-        });
-      },
-      [&](unsigned char* hi, unsigned char* lo, int k0) {
-        stage_kmajor<N_TILE>(hi, lo, k0, K, [&](int r) -> const float* { return n0 + r < N ? w + (long long)(n0 + r) * ldw : nullptr; });
-      },
+      0, K, [&](int k0) { sa.load(k0); }, [&](int k0) { sb.load(k0); },
+      [&](unsigned char* hi, unsigned char* lo) { sa.store(hi, lo); }, [&](unsigned char* hi, unsigned char* lo) { sb.store(hi, lo); },
       [&](int r, int c, float4 v) {
         const int m = m0 + r, n = n0 + c;
         if (m >= M || n >= N) return;
         float* dst = y + (long long)m * ldy + n;
-        float t[4] = {v.x, v.y, v.z, v.w};
+        const float4 bq = *reinterpret_cast<const float4*>(s_bias + c);
+        float t[4] = {v.x + bq.x, v.y + bq.y, v.z + bq.z, v.w + bq.w};
+        if (relu) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (bias && n + j < N) t[j] += bias[n + j];
-          if (relu) t[j] = fmaxf(t[j], 0.f);
+          for (int j = 0; j < 4; ++j) t[j] = fmaxf(t[j], 0.f);
         }
         if (n + 3 < N && (((size_t)dst) & 15) == 0) *reinterpret_cast<float4*>(dst) = make_float4(t[0], t[1], t[2], t[3]);
         else for (int j = 0; j < 4 && n + j < N; ++j) dst[j] = t[j];
@@ -237,32 +288,40 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
 }
 
 // dx[row(m)][k] (+)= sum_n dy[m][n] W[n][k]       (same contract as subgnn_linear_bwd_input)
+// grid.z splits the reduction over n; with more than one split every output is added atomically (dx must then hold the
+// value to accumulate onto: the host wrapper only splits in scatter / accumulate mode).
 template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w, int ldw, float* __restrict__ dx, int lddx,
-                           const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate) {
+                           const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
   const int m0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;      // output tile: rows m, columns k
+  const int nr0 = blockIdx.z * n_chunk, nr1 = min(N, nr0 + n_chunk);
+  if (nr0 >= nr1) return;
+  const bool atomic_out = gridDim.z > 1;
+  KMajorStager<TC_M> sa;
+  MNMajorStager<N_TILE> sb;
+  sa.init(nr1, [&](int r) -> const float* { return m0 + r < M ? dy + (long long)(m0 + r) * ldy : nullptr; });
   tc_tile<N_TILE>(
-      0, N,
-      [&](unsigned char* hi, unsigned char* lo, int n0) {
-        stage_kmajor<TC_M>(hi, lo, n0, N, [&](int r) -> const float* { return m0 + r < M ? dy + (long long)(m0 + r) * ldy : nullptr; });
+      nr0, nr1, [&](int n0) { sa.load(n0); },
+      [&](int n0) {                                                    // B[k][n] = W[n][k]: rows k contiguous in memory for fixed n
+        sb.load(n0, K - k0o, [&](int n) -> const float* { return n < nr1 ? w + (long long)n * ldw + k0o : nullptr; });
       },
-      [&](unsigned char* hi, unsigned char* lo, int n0) {             // B[k][n] = W[n][k]: rows k contiguous in memory for fixed n
-        stage_mnmajor<N_TILE>(hi, lo, K - k0o, [&](int kk) -> const float* { return n0 + kk < N ? w + (long long)(n0 + kk) * ldw + k0o : nullptr; });
-      },
+      [&](unsigned char* hi, unsigned char* lo) { sa.store(hi, lo); }, [&](unsigned char* hi, unsigned char* lo) { sb.store(hi, lo); },
       [&](int r, int c, float4 v) {
         const int m = m0 + r, k = k0o + c;
         if (m >= M || k >= K) return;
         const float t[4] = {v.x, v.y, v.z, v.w};
+        long long row = m;
         if (scatter_ids) {
-          const int row = scatter_ids[m];
+          row = scatter_ids[m];
           if (row == 0) return;
-          float* dst = dx + (long long)row * lddx + k;
+        }
+        float* dst = dx + row * lddx + k;
+        if (scatter_ids || atomic_out) {
           if (k + 3 < K && (((size_t)dst) & 15) == 0) atomicAdd(reinterpret_cast<float4*>(dst), v);     // red.global.add.v4.f32
           else for (int j = 0; j < 4 && k + j < K; ++j) atomicAdd(dst + j, t[j]);
           return;
         }
-        float* dst = dx + (long long)m * lddx + k;
         if (k + 3 < K && (((size_t)dst) & 15) == 0) {
           float4 o = v;
           if (accumulate) { const float4 p = *reinterpret_cast<const float4*>(dst); o.x += p.x; o.y += p.y; o.z += p.z; o.w += p.w; }
@@ -281,19 +340,21 @@ tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* 
   const int n0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;       // output tile: rows n, columns k
   const int mr0 = blockIdx.z * m_chunk, mr1 = min(M, mr0 + m_chunk);
   if (mr0 >= mr1) return;
+  MNMajorStager<TC_M> sa;
+  MNMajorStager<N_TILE> sb;
   tc_tile<N_TILE>(
       mr0, mr1,
-      [&](unsigned char* hi, unsigned char* lo, int mb) {             // A[n][m] = dy[m][n]
-        stage_mnmajor<TC_M>(hi, lo, N - n0, [&](int kk) -> const float* { return mb + kk < mr1 ? dy + (long long)(mb + kk) * ldy + n0 : nullptr; });
+      [&](int mb) {                                                    // A[n][m] = dy[m][n]
+        sa.load(mb, N - n0, [&](int m) -> const float* { return m < mr1 ? dy + (long long)m * ldy + n0 : nullptr; });
       },
-      [&](unsigned char* hi, unsigned char* lo, int mb) {             // B[k][m] = X[row(m)][k]
-        stage_mnmajor<N_TILE>(hi, lo, K - k0o, [&](int kk) -> const float* {
-          const int m = mb + kk;
+      [&](int mb) {                                                    // B[k][m] = X[row(m)][k]
+        sb.load(mb, K - k0o, [&](int m) -> const float* {
           if (m >= mr1) return nullptr;
           const long long row = ids ? (long long)ids[m] : m;
           return x + row * ldx + k0o;
         });
       },
+      [&](unsigned char* hi, unsigned char* lo) { sa.store(hi, lo); }, [&](unsigned char* hi, unsigned char* lo) { sb.store(hi, lo); },
       [&](int r, int c, float4 v) {
         const int n = n0 + r, k = k0o + c;
         if (n >= N || k >= K) return;
@@ -308,6 +369,13 @@ tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* 
 
 static bool tc_aligned(const void* p, int ld) { return (ld % 4) == 0 && (((size_t)p) & 15) == 0; }
 template <int NT> static size_t tc_smem() { return (size_t)(2 * TC_M * 128 + 2 * NT * 128) + 1024; }
+
+template <int NT>
+static void launch_bwd_input(dim3 grid, cudaStream_t st, const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx,
+                             const int* scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
+  cudaFuncSetAttribute(tc_linear_bwd_input_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<NT>());
+  tc_linear_bwd_input_kernel<NT><<<grid, TC_THREADS, tc_smem<NT>(), st>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+}
 
 extern "C" {
 
@@ -333,15 +401,26 @@ int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
-  if (K <= 64) {
-    cudaFuncSetAttribute(tc_linear_bwd_input_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
-    dim3 grid(sg_div_up(K, 64), sg_div_up(M, TC_M));
-    tc_linear_bwd_input_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate);
-  } else {
-    cudaFuncSetAttribute(tc_linear_bwd_input_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
-    dim3 grid(sg_div_up(K, 128), sg_div_up(M, TC_M));
-    tc_linear_bwd_input_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate);
+  // output tile width: the widest that still gives every SM a CTA
+  const int sms = subgnn_sm_count(), m_tiles = sg_div_up(M, TC_M);
+  int nt = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
+  while (nt > 32 && sg_div_up(K, nt) * m_tiles < sms) nt >>= 1;
+  // reduction splits (atomic output) only where the destination already holds the value to add onto
+  int splits = 1;
+  if (scatter_ids || accumulate) {
+    const int ctas = sg_div_up(K, nt) * m_tiles;
+    splits = sg_div_up(2 * sms, ctas);
+    const int max_splits = sg_div_up(N, 4 * TC_KB);
+    if (splits > max_splits) splits = max_splits;
+    if (splits < 1) splits = 1;
   }
+  const int n_chunk = sg_div_up(sg_div_up(N, splits), TC_KB) * TC_KB;
+  splits = sg_div_up(N, n_chunk);
+  dim3 grid(sg_div_up(K, nt), m_tiles, splits);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (nt == 32) launch_bwd_input<32>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+  else if (nt == 64) launch_bwd_input<64>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+  else launch_bwd_input<128>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
   return subgnn_check_launch("tc_linear_bwd_input_kernel");
 }
 

@@ -308,18 +308,18 @@ class LstmRunner:
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
             full = sr == T
+            # the bias gradients (d b_ih == d b_hh == column sums of dG) are accumulated inside the recurrence kernel
             call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
-                 self.n_seq, T, H, sf, sr, 0 if not full else 1, st)
+                 self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g), a.base_addr(o['bias_hh'], g), st)
             dG = ptr(self.G[k])
             x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=False)
-            w_ih, gw_ih, gb_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g), a.base_addr(o['bias_ih'], g)
+            w_ih, gw_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g)
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
-            self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, gb_ih, M, n_out, din, st)
+            self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, None, M, n_out, din, st)
             if not full:
                 xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
-                self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, gb_ih + 4 * 4 * H, self.n_seq, 4 * H, din, st)
-            call('subgnn_add_inplace', a.base_addr(o['bias_hh'], g), gb_ih, 8 * H, st)      # d b_hh == d b_ih
+                self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, None, self.n_seq, 4 * H, din, st)
             for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
                 self._wgrad(dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H, ptr(self.hprev[d_]),
                             a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, st)
