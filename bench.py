@@ -152,17 +152,25 @@ def algorithmic_work(eng, ctx):
            + n_nodes * (4 + 8 * D)                                                        # pooling scatter RMW
            + R * L * (A['pi'] + A['pb'] + 2 * A['s']) * 4 + L * (B * A['pi'] + A['pb'] + 2 * A['s']) * 8)
     n_par = eng.arena.size
-    work = {'subgnn_model_sub_fwd': ('hbm', fwd), 'subgnn_model_sub_bwd': ('hbm', bwd),
+    # amounts are PER STEP (all launches of the entry point in one step together)
+    work = {'subgnn_model_rows_fwd': ('hbm', fwd), 'subgnn_model_rows_bwd': ('hbm', bwd),
             'subgnn_adam_step': ('hbm', 28 * n_par), 'subgnn_grad_sumsq': ('hbm', 4 * n_par), 'subgnn_fill_zero': ('hbm', 4 * n_par)}
     if eng.lstm is not None:
         ls = eng.lstm
         M, H = ls.n_seq * ls.T, ls.H
         flops_in = sum(2 * M * 8 * H * (D if k == 0 else 2 * H) for k in range(ls.nl))
-        work['subgnn_linear_fwd'] = ('tensor', flops_in / ls.nl)
-        work['subgnn_linear_bwd_weight'] = ('tensor', flops_in / ls.nl)
-        work['subgnn_linear_bwd_input'] = ('tensor', flops_in / ls.nl)
-        work['subgnn_lstm_recur_fwd'] = ('tensor', 2 * 2 * M * 4 * H * H)
-        work['subgnn_lstm_recur_bwd'] = ('tensor', 2 * 2 * M * 4 * H * H)
+        # 'last' aggregator: the top layer's reverse direction takes one step only (SubGNN.py:83)
+        top_rev = 0 if ls.sum_mode else 1
+        rows_dir = [[M, M] for _ in range(ls.nl)]
+        if top_rev:
+            rows_dir[-1][1] = ls.n_seq
+        flops_proj = sum(2 * (rows_dir[k][0] + rows_dir[k][1]) * 4 * H * (D if k == 0 else 2 * H) for k in range(ls.nl))
+        flops_rec = sum(2 * (rows_dir[k][0] + rows_dir[k][1]) * 4 * H * H for k in range(ls.nl))
+        work['subgnn_tc_linear_fwd'] = ('tensor', flops_proj)
+        work['subgnn_tc_linear_bwd_weight'] = ('tensor', flops_proj + flops_rec)         # d W_ih and d W_hh
+        work['subgnn_tc_linear_bwd_input'] = ('tensor', flops_proj)
+        work['subgnn_lstm_recur_fwd'] = ('fp32', flops_rec)
+        work['subgnn_lstm_recur_bwd'] = ('fp32', flops_rec)
     return work, {'rows': R, 'component_nodes': n_nodes}
 
 
@@ -172,6 +180,10 @@ def measured_peaks():
         p = json.loads(f.read_text())
         return {'hbm': p['hbm_gbs'], 'tensor': p['bf16_tflops'], 'tensor_sustained': p.get('bf16_tflops_sustained', p['bf16_tflops']), 'src': 'measured'}
     return {'hbm': 6650.0, 'tensor': 1590.0, 'tensor_sustained': 1400.0, 'src': 'fallback'}
+
+
+# fp32 FFMA issue peak of the part (not in MEASURED_PEAKS.json): 148 SMs x 128 lanes x 2 flop x 1.965 GHz
+FP32_FFMA_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
 
 # ----------------------------------------------------------------------------------------------------
@@ -378,26 +390,38 @@ def main():
     ctx = eng.context('train', B, True)
     work, stats = algorithmic_work(eng, ctx)
     peaks = measured_peaks()
-    top = max(per_entry, key=lambda k: per_entry[k][0])
     breakdown = {k: {'ms_per_step': round(v[0], 4), 'calls_per_step': v[1]} for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1][0])}
 
     def roof(name):
-        ms, calls = per_entry[name]
-        if name not in work:
+        if name not in work or name not in per_entry:
             return None
+        ms, calls = per_entry[name]
         bound, amount = work[name]
         per_launch_s = ms * 1e-3 / calls
+        amount_launch = amount / calls
         if bound == 'hbm':
-            ach = amount / per_launch_s / 1e9
+            ach = amount_launch / per_launch_s / 1e9
             return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'],
-                    'traffic': None, 'algorithmic_bytes_per_launch': amount, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
-        ach = amount / per_launch_s / 1e12
+                    'traffic': None, 'algorithmic_bytes_per_launch': amount_launch, 'launches_per_step': calls,
+                    'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
+        ach = amount_launch / per_launch_s / 1e12
+        if bound == 'tensor':
+            return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
+                    'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount_launch,
+                    'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
+                    'note': 'tcgen05 kind::tf32 with 3xTF32 error compensation (3 MMAs per algorithmic product) measured against the bf16 tensor peak'}
         return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
-                'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount,
-                'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'], 'note': 'fp32 FFMA kernel measured against the bf16 tensor peak'}
+                'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount_launch,
+                'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
+                'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': ach / FP32_FFMA_TFLOPS,
+                'note': 'sequential fp32 FFMA matvec chain (T dependent steps of n_seq x 4H x H), not a tensor-core shape: the relevant ceiling '
+                        'is the nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz), reported beside the contract\'s bf16 peak'}
 
-    roofline = roof(top) or roof('subgnn_model_sub_fwd')
-    roofline['others'] = [r for r in (roof(k) for k in ('subgnn_model_sub_fwd', 'subgnn_model_sub_bwd', 'subgnn_adam_step') if k in per_entry and k != top) if r]
+    ranked = sorted(per_entry, key=lambda k: -per_entry[k][0])
+    roofline = next((r for r in (roof(k) for k in ranked) if r), None)
+    roofline['others'] = [r for r in (roof(k) for k in ('subgnn_model_rows_fwd', 'subgnn_model_rows_bwd', 'subgnn_tc_linear_fwd',
+                                                         'subgnn_tc_linear_bwd_weight', 'subgnn_lstm_recur_fwd', 'subgnn_adam_step')
+                                      if k in per_entry and k != roofline['kernel']) if r]
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

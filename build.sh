@@ -9,7 +9,7 @@ OBJS=""
 for f in $SRC; do
   o=build/$(basename ${f%.cu}).o
   OBJS="$OBJS $o"
-  if [ ! -f $o ] || [ $f -nt $o ] || [ subgnn_b200/csrc/common.cuh -nt $o ] || [ subgnn_b200/csrc/gemm_tile.cuh -nt $o ] || [ include/subgnn_b200.h -nt $o ]; then
+  if [ ! -f $o ] || [ $f -nt $o ] || [ subgnn_b200/csrc/common.cuh -nt $o ] || [ subgnn_b200/csrc/gemm_tile.cuh -nt $o ] || [ subgnn_b200/csrc/lstm_reg.cuh -nt $o ] || [ include/subgnn_b200.h -nt $o ]; then
     rm -f $o; nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo --extended-lambda -Xcompiler -fPIC ${NVCC_EXTRA} -c $f -o $o &
   fi
 done

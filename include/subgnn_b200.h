@@ -203,8 +203,20 @@ typedef struct subgnn_model_desc {
 } subgnn_model_desc;
 
 /* batch bookkeeping + per-step weight transposes + q = w_p . x_anchor for every shared anchor list */
-int subgnn_model_prep(const subgnn_model_desc* d, void* stream);
-int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream);
+int subgnn_model_prep(const subgnn_model_desc* d, void* stream);          /* == prep_batch + prep_weights */
+int subgnn_model_prep_batch(const subgnn_model_desc* d, void* stream);
+int subgnn_model_prep_weights(const subgnn_model_desc* d, void* stream);
+int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream);         /* == q_fwd_part(POS | STRUC) */
+#define SUBGNN_Q_POS 1     /* position-channel anchors (node embeddings) */
+#define SUBGNN_Q_STRUC 2   /* structure-channel anchors (LSTM output emb_s) */
+int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream);
+/* The row pass in phases, so that the neighbourhood chains (independent of the walk-encoder LSTM) can run concurrently
+ * with it on another stream: SUBGNN_PHASE_N = pooling + N channel, SUBGNN_PHASE_PS = P / S property-aware outputs. */
+#define SUBGNN_PHASE_N 1
+#define SUBGNN_PHASE_PS 2
+int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream);
+int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training) */
+int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream);
 /* SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers subgraph_mpn.py:133-241,
  * masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training also the
  * per-sample MLP backward (dZ). */

@@ -53,6 +53,12 @@ SIGNATURES = {
     'subgnn_group_bcast': [P, P, I, I, I, P],
     'subgnn_dropout': [P, P, LL, F, U64, U32, P, P],
     'subgnn_model_prep': [P, P],
+    'subgnn_model_prep_batch': [P, P],
+    'subgnn_model_prep_weights': [P, P],
+    'subgnn_model_q_fwd_part': [P, I, P],
+    'subgnn_model_rows_fwd': [P, I, P],
+    'subgnn_model_mlp_fwd': [P, P],
+    'subgnn_model_rows_bwd': [P, I, P],
     'subgnn_model_q_fwd': [P, P],
     'subgnn_model_sub_fwd': [P, P],
     'subgnn_model_mlp_bwd': [P, P],

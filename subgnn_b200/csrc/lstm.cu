@@ -17,6 +17,7 @@
 // the reference.
 #include "common.cuh"
 #include "../../include/subgnn_b200.h"
+#include "lstm_reg.cuh"
 
 #define S_TILE 8
 
@@ -295,16 +296,27 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
     y[e] = x[e] * sg_dropout_scale(seed, salt, (uint64_t)e, p);
 }
 
-// per-step weight staging: WhhT[dir][k][j] = Whh[dir][j][k]; bsum[dir][j] = b_ih[dir][j] + b_hh[dir][j]
+// per-step weight staging: bsum[dir][j] = b_ih[dir][j] + b_hh[dir][j] and the transposed recurrent weights, either
+//   cl == 0: WhhT[dir][k][j] = Whh[dir][j][k]                                   (streaming kernels above), or
+//   cl >= 1: Wp[dir][rank][k][half][p][g2][o] = Whh[dir][(2 half + g2)*H + rank*U + 2p + o][k], U = H / cl   (lstm_reg.cu: every
+//            CTA's slice is one contiguous block for its bulk copy; a thread's two float4 per k are contiguous across the warp).
 __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                 float* __restrict__ WhhT, float* __restrict__ bsum, int H) {
+                                 float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
   const int H4 = 4 * H;
   const long long total = (long long)2 * H4 * H;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
     const int dir = (int)(e / ((long long)H4 * H));
     const int r = (int)(e % ((long long)H4 * H));
-    const int k = r / H4, j = r % H4;
-    WhhT[e] = Whh[((size_t)dir * H4 + j) * H + k];
+    if (cl == 0) {
+      const int k = r / H4, j = r % H4;
+      WhhT[e] = Whh[((size_t)dir * H4 + j) * H + k];
+    } else {
+      const int U = H / cl, U4 = 4 * U;
+      const int rank = r / (H * U4), rr = r % (H * U4);
+      const int k = rr / U4, c = rr % U4;
+      const int half = c / (2 * U), p = (c % (2 * U)) / 4, gate = 2 * half + (c % 4) / 2, o = c % 2;
+      WhhT[e] = Whh[((size_t)dir * H4 + gate * H + rank * U + 2 * p + o) * H + k];
+    }
     if (e < 2 * H4) bsum[e] = b_ih[e] + b_hh[e];
   }
 }
@@ -325,7 +337,8 @@ static int lstm_block(int H) { return ((4 * H + 31) / 32) * 32; }
 
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256, "hidden size must be in [1, 256]");
-  lstm_prep_kernel<<<sg_grid_for((long long)8 * H * H, 256, 4), 256, 0, (cudaStream_t)stream>>>(whh, b_ih, b_hh, whh_t, bsum, H);
+  lstm_prep_kernel<<<sg_grid_for((long long)8 * H * H, 256, 4), 256, 0, (cudaStream_t)stream>>>(whh, b_ih, b_hh, whh_t, bsum, H,
+                                                                                                  lstm_reg_supported(H) ? lstm_reg_cluster(H) : 0);
   return subgnn_check_launch("lstm_prep_kernel");
 }
 
@@ -334,6 +347,7 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   SG_REQUIRE(steps_fwd >= 0 && steps_fwd <= T && steps_rev >= 0 && steps_rev <= T, "bad step counts");
   if (n_seq == 0) return SUBGNN_OK;
+  if (lstm_reg_supported(H)) return lstm_reg_fwd(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev, (cudaStream_t)stream);
   size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
   const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh_t) & 15) == 0;   // two CTAs per SM stay resident; bulk copy: 16-byte granules
@@ -359,6 +373,8 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
                           int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
+  if (lstm_reg_supported(H))
+    return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, (cudaStream_t)stream);
   size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
   const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh) & 15) == 0;

@@ -1,0 +1,452 @@
+// Walk-encoder LSTM recurrence as a register-tiled per-step GEMM with packed fp32 FMAs (FFMA2) and thread-block clusters.
+//
+// Same contract and data layout as the streaming kernels in lstm.cu (reference: SubGNN.py:60-88 nn.LSTM inside class LSTM,
+// called from anchor_patch_samplers.py:413-433); chosen by the host wrappers there whenever lstm_reg_supported(H).
+//
+// Why this shape (round-1 profile, profiles/r01_ncu_lstm_v5.txt): a thread-per-gate-column matvec reads every h value once per
+// FMA through a broadcast LDS.128 and is bound by the 128 B/clk shared-memory return path (fma pipe 23 % active).  Here each
+// thread owns a 4-sequence x 8-column register tile, so one loaded operand feeds 4-8 FMAs, and the FMAs are issued as packed
+// fma.rn.f32x2 (FFMA2, sm_100): 16 issues per k for 32 FMAs.
+//
+// Forward.  A CTA owns `tile` sequences of one direction and the gate columns of U hidden units (U = H, or H/2 with a
+// cluster of two CTAs when H > 64 so that the recurrent weights of a CTA — H x 4U fp32, staged once by a 1-D TMA bulk copy —
+// fit in shared memory).  Thread (sgroup, p) owns sequences 4 sgroup .. +3 and the FOUR gates of units 2p, 2p+1: after the
+// k loop it holds i, f, g, o of its units in registers, so the cell update needs no exchange and the cell state lives in
+// registers for the whole recurrence.  The new h is written (k-major, double buffered) into the h tile of every CTA of the
+// cluster through distributed shared memory: ONE (cluster) barrier per time step.
+//
+// Backward.  Same tiling for d h_{t-1} = d gates . W_hh: thread (sgroup, gate, kgroup) reduces over the U columns of one gate
+// for 4 sequences x 8 hidden units; the four per-gate partials (and, in a cluster, the peer CTA's) land in double-buffered
+// reduction slots of the CTA that owns the units (DSMEM), where the element-wise BPTT step sums them.
+#include "common.cuh"
+#include "../../include/subgnn_b200.h"
+#include "lstm_reg.cuh"
+
+namespace {
+
+// sigmoid / tanh from ex2.approx + rcp.approx: relative error ~1e-7 on the sigmoid, absolute error ~2e-7 on tanh — inside the
+// fp32 tolerance of the parity tests; 5 instructions instead of ~25 for the libm versions (40 activations per thread and step).
+__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ unsigned cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void st_cluster_v4(const float* local_addr, unsigned rank, float4 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(rank));
+  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(remote), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+__device__ __forceinline__ void st_cluster_v2(const float* local_addr, unsigned rank, float2 v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"(smem_u32(local_addr)), "r"(rank));
+  asm volatile("st.shared::cluster.v2.f32 [%0], {%1, %2};" :: "r"(remote), "f"(v.x), "f"(v.y) : "memory");
+}
+template <int CL>
+__device__ __forceinline__ void step_sync() {
+  if (CL > 1) cluster_sync_all(); else __syncthreads();
+}
+
+// 1-D TMA bulk copies global -> shared completing on one mbarrier (SASS UBLKCP); issued by one thread.
+__device__ __forceinline__ void bulk_begin(uint64_t* bar, uint32_t total_bytes) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(bar)) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(total_bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(reinterpret_cast<const char*>(dst) + off)), "l"(reinterpret_cast<const char*>(src) + off), "r"(n),
+                    "r"(smem_u32(bar)) : "memory");
+  }
+}
+__device__ __forceinline__ void bulk_wait(uint64_t* bar) {
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\tLSTMR_WAIT:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], 0;\n\t"
+      "@P1 bra LSTMR_DONE;\n\tbra LSTMR_WAIT;\n\tLSTMR_DONE:\n\t}\n"
+      :: "r"(smem_u32(bar)) : "memory");
+}
+
+// acc[s][c] (4 sequences x 4 column pairs) += x[s] * w[c]: 16 FFMA2
+__device__ __forceinline__ void tile_fma(float2 (&acc)[4][4], const float4 x, const float4 wa, const float4 wb) {
+  const float2 w0 = make_float2(wa.x, wa.y), w1 = make_float2(wa.z, wa.w), w2 = make_float2(wb.x, wb.y), w3 = make_float2(wb.z, wb.w);
+  const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+  for (int s = 0; s < 4; ++s) {
+    const float2 xx = make_float2(xs[s], xs[s]);
+    acc[s][0] = __ffma2_rn(xx, w0, acc[s][0]);
+    acc[s][1] = __ffma2_rn(xx, w1, acc[s][1]);
+    acc[s][2] = __ffma2_rn(xx, w2, acc[s][2]);
+    acc[s][3] = __ffma2_rn(xx, w3, acc[s][3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Forward.  grid (n_tiles * CL, 2 directions), cluster (CL, 1, 1); block = KS * (tile/4) * (U/2) threads:
+// thread (ks, sgroup, p).  The k range is split over KS warps per register tile (the whole problem is only ~500 such tiles:
+// one warp per SM sub-partition cannot hide the FFMA2 / LDS latencies, profiles/r01_ncu_lstm_v6.txt), the partial tiles meet in
+// shared memory and each of the KS threads finishes 4/KS of the tile's sequences (activations, cell update, outputs).
+// Wp: permuted transposed weights written by lstm_prep_kernel: [dir][rank][k][half][p][4] with the 4 = (gate 2 half + {0,1}) x
+// (unit 2p + {0,1}): a thread's two float4 loads per k are contiguous across the warp (conflict free).
+template <int CL, int KS>
+__global__ void __launch_bounds__(512)
+lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float* __restrict__ OUT, float* __restrict__ CS,
+                     int n_seq, int T, int H, int steps_fwd, int steps_rev, int tile) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ uint64_t wbar;
+  constexpr int NF = 4 / KS;                // sequences finished per thread
+  const int U = H / CL, U4 = 4 * U, H4 = 4 * H;
+  float* wsm = sm;                          // [H][2][U/2][4]
+  float* hS = wsm + (size_t)H * U4;         // [2][tile][H]   h_{t-1} of ALL hidden units, double buffered
+  float* part = hS + (size_t)2 * tile * H;  // [KS][tile][4U] partial gate pre-activations
+  const int dir = blockIdx.y;
+  const unsigned rank = CL > 1 ? cluster_rank() : 0u;
+  const int seq0 = (blockIdx.x / CL) * tile;
+  const int ns = min(tile, n_seq - seq0);
+  const int n_steps = dir == 0 ? steps_fwd : steps_rev;
+  const int half_u = U / 2, n_sg = tile / 4;
+  const int p = threadIdx.x % half_u, sg = (threadIdx.x / half_u) % n_sg, ks = threadIdx.x / (half_u * n_sg);
+  const int s0 = sg * 4;
+  const int unit0 = (int)rank * U + 2 * p;              // first of the two hidden units of this thread
+  const int kb = ks * (H / KS), ke = kb + H / KS;
+  if (threadIdx.x == 0) {
+    bulk_begin(&wbar, (uint32_t)((size_t)H * U4 * sizeof(float)));
+    bulk_copy(wsm, Wp + ((size_t)dir * CL + rank) * H * U4, (uint32_t)((size_t)H * U4 * sizeof(float)), &wbar);
+  }
+  for (int e = threadIdx.x; e < 2 * tile * H; e += blockDim.x) hS[e] = 0.f;
+  float2 c[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) c[f] = make_float2(0.f, 0.f);
+  step_sync<CL>();                          // every CTA's h tile is zeroed before a peer writes into it; mbarrier init published
+  bulk_wait(&wbar);
+  int cur = 0;
+  for (int st = 0; st < n_steps; ++st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    // gate pre-activations of the sequences this thread finishes: issued now, consumed after the k loop
+    float2 gin[NF][4];
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int s = s0 + ks + f * KS;
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        gin[f][g] = s < ns ? *reinterpret_cast<const float2*>(G + (((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + g * H + unit0)
+                           : make_float2(0.f, 0.f);
+    }
+    float2 acc[4][4];
+#pragma unroll
+    for (int s = 0; s < 4; ++s)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) acc[s][g] = make_float2(0.f, 0.f);
+    const float* hk = hS + ((size_t)cur * tile + s0) * H;
+    const float* wk = wsm + p * 4;
+#pragma unroll 2
+    for (int k = kb; k < ke; k += 4) {
+      float4 x[4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s) x[s] = *reinterpret_cast<const float4*>(hk + s * H + k);
+      const float* xf = reinterpret_cast<const float*>(x);
+#pragma unroll
+      for (int kk = 0; kk < 4; ++kk) {
+        const float4 wa = *reinterpret_cast<const float4*>(wk + (size_t)(k + kk) * U4);
+        const float4 wb = *reinterpret_cast<const float4*>(wk + (size_t)(k + kk) * U4 + 2 * U);
+        tile_fma(acc, make_float4(xf[kk], xf[4 + kk], xf[8 + kk], xf[12 + kk]), wa, wb);
+      }
+    }
+    {
+      float* pw = part + ((size_t)ks * tile + s0) * U4 + p * 4;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        *reinterpret_cast<float4*>(pw + (size_t)s * U4) = make_float4(acc[s][0].x, acc[s][0].y, acc[s][1].x, acc[s][1].y);
+        *reinterpret_cast<float4*>(pw + (size_t)s * U4 + 2 * U) = make_float4(acc[s][2].x, acc[s][2].y, acc[s][3].x, acc[s][3].y);
+      }
+    }
+    __syncthreads();
+    float* hnxt = hS + (size_t)(cur ^ 1) * tile * H;
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int s = s0 + ks + f * KS;
+      float4 pa = make_float4(0.f, 0.f, 0.f, 0.f), pb = pa;
+#pragma unroll
+      for (int q = 0; q < KS; ++q) {
+        const float4 va = *reinterpret_cast<const float4*>(part + ((size_t)q * tile + s) * U4 + p * 4);
+        const float4 vb = *reinterpret_cast<const float4*>(part + ((size_t)q * tile + s) * U4 + 2 * U + p * 4);
+        pa.x += va.x; pa.y += va.y; pa.z += va.z; pa.w += va.w;
+        pb.x += vb.x; pb.y += vb.y; pb.z += vb.z; pb.w += vb.w;
+      }
+      // gates (PyTorch order i, f, g, o) of units unit0, unit0 + 1
+      const float2 ai = make_float2(sigmoid_fast(pa.x + gin[f][0].x), sigmoid_fast(pa.y + gin[f][0].y));
+      const float2 af = make_float2(sigmoid_fast(pa.z + gin[f][1].x), sigmoid_fast(pa.w + gin[f][1].y));
+      const float2 ag = make_float2(tanh_fast(pb.x + gin[f][2].x), tanh_fast(pb.y + gin[f][2].y));
+      const float2 ao = make_float2(sigmoid_fast(pb.z + gin[f][3].x), sigmoid_fast(pb.w + gin[f][3].y));
+      float2 hn = make_float2(0.f, 0.f);
+      if (s < ns) {
+        c[f].x = fmaf(af.x, c[f].x, ai.x * ag.x);
+        c[f].y = fmaf(af.y, c[f].y, ai.y * ag.y);
+        hn = make_float2(ao.x * tanh_fast(c[f].x), ao.y * tanh_fast(c[f].y));
+        const size_t row = (size_t)(seq0 + s) * T + t;
+        float* gr = G + (row * 2 + dir) * H4 + unit0;
+        *reinterpret_cast<float2*>(gr) = ai;
+        *reinterpret_cast<float2*>(gr + H) = af;
+        *reinterpret_cast<float2*>(gr + 2 * H) = ag;
+        *reinterpret_cast<float2*>(gr + 3 * H) = ao;
+        *reinterpret_cast<float2*>(CS + (row * 2 + dir) * H + unit0) = c[f];
+        *reinterpret_cast<float2*>(OUT + row * 2 * H + dir * H + unit0) = hn;
+      }
+      if (CL == 1) *reinterpret_cast<float2*>(hnxt + (size_t)s * H + unit0) = hn;      // rows s >= ns stay zero
+      else {
+#pragma unroll
+        for (unsigned r = 0; r < (unsigned)CL; ++r) st_cluster_v2(hnxt + (size_t)s * H + unit0, r, hn);
+      }
+    }
+    step_sync<CL>();
+    cur ^= 1;
+  }
+  // steps not taken (top-layer reverse direction with the 'last' aggregator): outputs are never read
+}
+
+// ------------------------------------------------------------------------------------------------
+// BPTT.  dOUT [n_seq*T][2H]; G holds gate activations on entry and d(pre-activation) on exit.  Whh [2][4H][H] native layout.
+// block = KS * (tile/4) * 4 * (H/8) threads: thread (ks, sgroup, gate, kgroup) reduces over a 1/KS slice of the U columns of one
+// gate for 4 sequences x 8 hidden units (k in kg*4..+3 and H/2 + kg*4..+3: both weight loads contiguous across the warp).
+template <int CL, int KS>
+__global__ void __launch_bounds__(512)
+lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
+                     const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd, int steps_rev, int zero_untaken,
+                     float* __restrict__ db_ih, float* __restrict__ db_hh, int tile) {
+  extern __shared__ __align__(16) float sm[];
+  __shared__ uint64_t wbar;
+  const int U = H / CL, U4 = 4 * U, H4 = 4 * H;
+  constexpr int SLOTS = 4 * KS * CL;
+  float* wsm = sm;                                  // [4 gates][U][H]  rows of W_hh for this CTA's units
+  float* dgS = wsm + (size_t)U4 * H;                // [tile][4U]       d(pre-activation) of this CTA's columns
+  float* dc_rec = dgS + (size_t)U4 * tile;          // [tile][U]
+  float* bias_sm = dc_rec + (size_t)tile * U;       // [4U]
+  float* red = bias_sm + U4;                        // [SLOTS][tile][U] partial d h_{t-1} of this CTA's units (read by the element-wise
+                                                    // phase, rewritten by the matvec phase: a barrier separates the two)
+  const int dir = blockIdx.y;
+  const unsigned rank = CL > 1 ? cluster_rank() : 0u;
+  const int seq0 = (blockIdx.x / CL) * tile;
+  const int ns = min(tile, n_seq - seq0);
+  const int n_steps = dir == 0 ? steps_fwd : steps_rev;
+  const int tid = threadIdx.x;
+  const int KG = H / 8, n_sg = tile / 4;
+  const int kg = tid % KG, gate = (tid / KG) % 4, sg = (tid / (4 * KG)) % n_sg, ks = tid / (4 * KG * n_sg);
+  const int s0 = sg * 4;
+  const int ka = kg * 4, kb2 = H / 2 + kg * 4;      // the two 4-wide groups of hidden units this thread produces
+  const int jb = ks * (U / KS), je = jb + U / KS;
+  if (tid == 0) {
+    bulk_begin(&wbar, (uint32_t)((size_t)U4 * H * sizeof(float)));
+    for (int g = 0; g < 4; ++g)
+      bulk_copy(wsm + (size_t)g * U * H, Whh + ((size_t)dir * H4 + g * H + rank * U) * H, (uint32_t)((size_t)U * H * sizeof(float)), &wbar);
+  }
+  for (int e = tid; e < U4 * tile; e += blockDim.x) dgS[e] = 0.f;
+  for (int e = tid; e < tile * U; e += blockDim.x) dc_rec[e] = 0.f;
+  for (int e = tid; e < U4; e += blockDim.x) bias_sm[e] = 0.f;
+  for (int e = tid; e < SLOTS * tile * U; e += blockDim.x) red[e] = 0.f;
+  step_sync<CL>();
+  bulk_wait(&wbar);
+  const int n_el = ns * U;
+  for (int st = n_steps - 1; st >= 0; --st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    const int t_prev = dir == 0 ? t - 1 : t + 1;
+    // ---- element-wise BPTT step over this CTA's (sequence, unit) pairs, two per iteration with all loads issued up front ----
+    for (int e0 = tid; e0 < n_el; e0 += 2 * blockDim.x) {
+      float ig[2], fg[2], gg[2], og[2], cc[2], cp[2], dho[2], dhr[2];
+      size_t gbase[2];
+      bool on[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = e0 + q * blockDim.x;
+        on[q] = e < n_el;
+        const int s = on[q] ? e / U : 0, u = on[q] ? e % U : 0;
+        const int ug = (int)rank * U + u;
+        const size_t row = (size_t)(seq0 + s) * T + t;
+        gbase[q] = (row * 2 + dir) * H4 + ug;
+        ig[q] = G[gbase[q]]; fg[q] = G[gbase[q] + H]; gg[q] = G[gbase[q] + 2 * H]; og[q] = G[gbase[q] + 3 * H];
+        cc[q] = CS[(row * 2 + dir) * H + ug];
+        cp[q] = st > 0 ? CS[((((size_t)(seq0 + s) * T + t_prev) * 2) + dir) * H + ug] : 0.f;
+        dho[q] = dOUT[row * 2 * H + dir * H + ug];
+        float r = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) r += red[(size_t)sl * tile * U + s * U + u];
+        dhr[q] = r;
+      }
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        if (!on[q]) continue;
+        const int e = e0 + q * blockDim.x;
+        const int s = e / U, u = e % U;
+        const float tc = tanhf(cc[q]);
+        const float dh = dho[q] + dhr[q];
+        const float dc = dc_rec[e] + dh * og[q] * (1.f - tc * tc);
+        const float dai = dc * gg[q] * ig[q] * (1.f - ig[q]);
+        const float daf = dc * cp[q] * fg[q] * (1.f - fg[q]);
+        const float dag = dc * ig[q] * (1.f - gg[q] * gg[q]);
+        const float dao = dh * tc * og[q] * (1.f - og[q]);
+        dc_rec[e] = dc * fg[q];
+        float* dr = dgS + (size_t)s * U4 + u;
+        dr[0] = dai; dr[U] = daf; dr[2 * U] = dag; dr[3 * U] = dao;
+        G[gbase[q]] = dai; G[gbase[q] + H] = daf; G[gbase[q] + 2 * H] = dag; G[gbase[q] + 3 * H] = dao;
+      }
+    }
+    step_sync<CL>();                        // dgS complete; every CTA of the cluster has finished reading its reduction slots
+    // ---- bias gradient: column sums over the tile's sequences (rows s >= ns of dgS stay zero) ----
+    for (int col = tid; col < U4; col += blockDim.x) {
+      float bs = 0.f;
+      for (int s = 0; s < ns; ++s) bs += dgS[(size_t)s * U4 + col];
+      bias_sm[col] += bs;
+    }
+    // ---- d h_{t-1} partials ----
+    {
+      float2 acc[4][4];
+#pragma unroll
+      for (int s = 0; s < 4; ++s)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) acc[s][q] = make_float2(0.f, 0.f);
+      const float* dg = dgS + (size_t)s0 * U4 + gate * U;
+      const float* wr = wsm + (size_t)gate * U * H;
+#pragma unroll 2
+      for (int jj = jb; jj < je; jj += 4) {
+        float4 x[4];
+#pragma unroll
+        for (int s = 0; s < 4; ++s) x[s] = *reinterpret_cast<const float4*>(dg + (size_t)s * U4 + jj);
+        const float* xf = reinterpret_cast<const float*>(x);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 wa = *reinterpret_cast<const float4*>(wr + (size_t)(jj + q) * H + ka);
+          const float4 wb = *reinterpret_cast<const float4*>(wr + (size_t)(jj + q) * H + kb2);
+          tile_fma(acc, make_float4(xf[q], xf[4 + q], xf[8 + q], xf[12 + q]), wa, wb);
+        }
+      }
+      const unsigned owner_a = (unsigned)(ka / U), owner_b = (unsigned)(kb2 / U);
+      float* rout = red + (size_t)(((int)rank * 4 + gate) * KS + ks) * tile * U;
+#pragma unroll
+      for (int s = 0; s < 4; ++s) {
+        if (s0 + s < ns) {
+          const float4 va = make_float4(acc[s][0].x, acc[s][0].y, acc[s][1].x, acc[s][1].y);
+          const float4 vb = make_float4(acc[s][2].x, acc[s][2].y, acc[s][3].x, acc[s][3].y);
+          float* da = rout + (size_t)(s0 + s) * U + (ka % U);
+          float* db = rout + (size_t)(s0 + s) * U + (kb2 % U);
+          if (CL == 1) { *reinterpret_cast<float4*>(da) = va; *reinterpret_cast<float4*>(db) = vb; }
+          else { st_cluster_v4(da, owner_a, va); st_cluster_v4(db, owner_b, vb); }
+        }
+      }
+    }
+    step_sync<CL>();
+  }
+  for (int lc = tid; lc < U4; lc += blockDim.x) {
+    const float v = bias_sm[lc];
+    if (v != 0.f) {
+      const int col = (lc / U) * H + (int)rank * U + (lc % U);
+      if (db_ih) atomicAdd(db_ih + (size_t)dir * H4 + col, v);
+      if (db_hh) atomicAdd(db_hh + (size_t)dir * H4 + col, v);
+    }
+  }
+  // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations) unless the caller
+  // never reads them (zero_untaken == 0)
+  for (int st = n_steps; zero_untaken && st < T; ++st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    for (int e = tid; e < ns * U4; e += blockDim.x) {
+      const int s = e / U4, lc = e % U4;
+      const int col = (lc / U) * H + (int)rank * U + (lc % U);
+      G[(((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + col] = 0.f;
+    }
+  }
+}
+
+// sequences per CTA (multiple of 4, at most 32): fewest waves, then fewest warps sharing an SM sub-partition
+int pick_tile(int n_seq, int cl, int threads_per_4seq, size_t smem_fixed, size_t smem_per_seq) {
+  const int sms = subgnn_sm_count();
+  int best = -1;
+  long long best_cost = -1;
+  for (int tile = 4; tile <= 32; tile += 4) {
+    const size_t smem = smem_fixed + smem_per_seq * tile;
+    if (smem > 220 * 1024) continue;
+    const int threads = threads_per_4seq * (tile / 4);
+    if (threads > 512) continue;
+    int occ = (int)((220 * 1024) / smem);
+    if (occ < 1) occ = 1;
+    if (occ > 4) occ = 4;
+    const long long ctas = 2LL * sg_div_up(n_seq, tile) * cl;
+    const long long waves = (ctas + (long long)sms * occ - 1) / ((long long)sms * occ);
+    long long resident = (ctas + sms - 1) / sms;
+    if (resident > occ) resident = occ;
+    // time ~ waves x (per-step latency floor + issue time of the warps that share a sub-partition)
+    const long long warps = resident * ((threads + 31) / 32);
+    const long long cost = waves * (4 + (warps + 3) / 4) * 100 + (32 - tile);
+    if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tile; }
+  }
+  return best;
+}
+
+template <int CL, int KS>
+int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, cudaStream_t st) {
+  const int U = H / CL;
+  const size_t fixed = (size_t)H * 4 * U * sizeof(float), per_seq = (size_t)(2 * H + KS * 4 * U) * sizeof(float);
+  const int tile = pick_tile(n_seq, CL, KS * (U / 2), fixed, per_seq);
+  if (tile < 0) { subgnn_set_error("lstm_fwd_tile: no feasible tile"); return SUBGNN_ERR_ARG; }
+  const size_t smem = fixed + per_seq * tile;
+  cudaFuncSetAttribute(lstm_fwd_tile_kernel<CL, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(sg_div_up(n_seq, tile) * CL, 2, 1);
+  cfg.blockDim = dim3(KS * (U / 2) * (tile / 4), 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile);
+  return subgnn_check_launch("lstm_fwd_tile_kernel");
+}
+
+template <int CL, int KS>
+int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
+               int zero_untaken, float* db_ih, float* db_hh, cudaStream_t st) {
+  const int U = H / CL;
+  const size_t fixed = (size_t)(4 * U * H + 4 * U) * sizeof(float), per_seq = (size_t)(4 * U + U + 4 * KS * CL * U) * sizeof(float);
+  const int tile = pick_tile(n_seq, CL, KS * 4 * (H / 8), fixed, per_seq);
+  if (tile < 0) { subgnn_set_error("lstm_bwd_tile: no feasible tile"); return SUBGNN_ERR_ARG; }
+  const size_t smem = fixed + per_seq * tile;
+  cudaFuncSetAttribute(lstm_bwd_tile_kernel<CL, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(sg_div_up(n_seq, tile) * CL, 2, 1);
+  cfg.blockDim = dim3(KS * (H / 8) * tile, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile);
+  return subgnn_check_launch("lstm_bwd_tile_kernel");
+}
+
+}  // namespace
+
+// H % 8: float4 / 8-wide register tiles and 16-byte bulk-copy granules; H > 64 runs on 2-CTA clusters (U = H/2, a multiple of 8)
+bool lstm_reg_supported(int H) { return H >= 8 && H <= 128 && (H % 8) == 0 && (H <= 64 || (H % 16) == 0); }
+int lstm_reg_cluster(int H) { return H <= 64 ? 1 : 2; }
+
+int lstm_reg_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, cudaStream_t st) {
+  if (lstm_reg_cluster(H) == 2) return launch_fwd<2, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
+  if (H % 16 == 0) return launch_fwd<1, 4>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
+  return launch_fwd<1, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
+}
+
+int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
+                 int zero_untaken, float* db_ih, float* db_hh, cudaStream_t st) {
+  if (lstm_reg_cluster(H) == 2) return launch_bwd<2, 1>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
+  if (H % 16 == 0) return launch_bwd<1, 4>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
+  return launch_bwd<1, 2>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
+}

@@ -162,13 +162,17 @@ __device__ __forceinline__ QEntry q_entry(const Desc& d, int l, int e) {
   return r;
 }
 
-__global__ void __launch_bounds__(256) q_fwd_kernel(Desc d) {
+// which: bit 0 = position-channel entries, bit 1 = structure-channel entries (these need the LSTM output emb_s)
+__global__ void __launch_bounds__(256) q_fwd_kernel(Desc d, int which) {
   const int lane = threadIdx.x & 31;
   const int per_layer = q_entries_per_layer(d);
   const int total = per_layer * d.L;
+  const int n_pos = d.use_p ? d.B * d.A_pi + d.A_pb : 0;
   const int warp_global = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int warps_total = (gridDim.x * blockDim.x) >> 5;
   for (int w = warp_global; w < total; w += warps_total) {
+    const bool is_pos = (w % per_layer) < n_pos;
+    if (!((which & 1) && is_pos) && !((which & 2) && !is_pos)) continue;
     const QEntry en = q_entry(d, w / per_layer, w % per_layer);
     float acc = 0.f;
     if (en.x)
@@ -249,7 +253,8 @@ __device__ void mlp_forward(const Desc& d, int b, const float* zs, float* work) 
     const int i0 = (int)((long long)d.hid * part / parts), i1 = (int)((long long)d.hid * (part + 1) / parts);
     float acc = 0.f;
     const float* wt = d.lin_wt[0] + j;
-    for (int i = i0; i < i1; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
+#pragma unroll 8
+    for (int i = i0; i < i1; ++i) acc = fmaf(zs[i], __ldg(wt + (size_t)i * d.h1), acc);
     psum[part * d.h1 + j] = acc;
   }
   __syncthreads();
@@ -270,7 +275,8 @@ __device__ void mlp_forward(const Desc& d, int b, const float* zs, float* work) 
   for (int j = tid; j < d.h2; j += blockDim.x) {
     float acc = d.lin_b[1][j];
     const float* wt = d.lin_wt[1] + j;
-    for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], wt[(size_t)i * d.h2], acc);
+#pragma unroll 8
+    for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], __ldg(wt + (size_t)i * d.h2), acc);
     acc = fmaxf(acc, 0.f);
     if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
     h2s[j] = acc;
@@ -334,7 +340,8 @@ __device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
   __syncthreads();
   for (int i = tid; i < d.h1; i += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < d.h2; ++j) acc = fmaf(g2[j], d.lin_w[1][(size_t)j * d.h1 + i], acc);
+#pragma unroll 8
+    for (int j = 0; j < d.h2; ++j) acc = fmaf(g2[j], __ldg(d.lin_w[1] + (size_t)j * d.h1 + i), acc);
     const float hv = d.H1[(size_t)b * d.h1 + i];
     float sc = d.training ? sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + i, d.lin_dropout) : 1.f;
     acc = hv > 0.f ? acc * sc : 0.f;
@@ -344,7 +351,8 @@ __device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
   __syncthreads();
   for (int i = tid; i < d.hid; i += blockDim.x) {
     float acc = 0.f;
-    for (int j = 0; j < d.h1; ++j) acc = fmaf(g1[j], d.lin_w[0][(size_t)j * d.hid + i], acc);
+#pragma unroll 8
+    for (int j = 0; j < d.h1; ++j) acc = fmaf(g1[j], __ldg(d.lin_w[0] + (size_t)j * d.hid + i), acc);
     dzs[i] = acc;
     d.dZ[(size_t)b * d.hid + i] = acc;
   }
@@ -378,8 +386,9 @@ __device__ __forceinline__ RowSmem row_smem(float* sm, int D) {
 }
 static size_t row_smem_bytes(int D) { return (size_t)(D + 2 * D + 4 * D + 2 * SIDE_WARPS * D + 16) * sizeof(float); }
 
+// phases: bit 0 = pooling + neighbourhood channel, bit 1 = position / structure property-aware outputs (needs q)
 template <int DPL>
-__global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
+__global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases) {
   extern __shared__ float sm[];
   const int D = d.D;
   const RowSmem S = row_smem(sm, D);
@@ -393,7 +402,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
     float* zrow = d.Z + (size_t)b * d.hid;
     __syncthreads();
     // ---- pooling (SubGNN.py:609-622): threads (k, part) split the component's nodes ----
-    {
+    if (phases & 1) {
       const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
       const int parts = D <= ROW_THREADS ? ROW_THREADS / D : 1;
       float* ps = S.part;                                   // reuse: [parts][D] <= 8 * D floats when parts <= 8 ... guard below
@@ -420,7 +429,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
       __syncthreads();
     }
     // ---- neighbourhood channel ----
-    if (d.use_n) {
+    if (d.use_n && (phases & 1)) {
       const int A = side ? d.A_nb : d.A_ni;
       for (int k = st; k < D; k += SIDE_THREADS) {
         const float v = d.trainable_cc ? d.cc_tab[side][((size_t)sub * d.C_pad + (g - d.sub_ccptr[sub])) * D + k] : S.x0[k];
@@ -507,7 +516,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
       }
     }
     // ---- position / structure channels: property-aware outputs relu(s q + b_p) ----
-    {
+    if (phases & 2) {
       const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
       const int per_layer = wp_ + ws_;
       for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
@@ -537,11 +546,14 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d) {
 }
 
 // per-sample MLP + loss (+ MLP backward when training): grid = B
+// 1024 threads per sample: the hid-long reductions of lin (and the hid-wide d Z) are split over 1024 / h1 thread groups so that
+// every thread's dependent load -> FMA chain is short (the 256-thread version was L2-latency bound: 87 us for 32 samples).
+#define MLP_THREADS 1024
 static size_t mlp_smem(const Desc& d) {
-  const int parts = d.h1 <= ROW_THREADS ? ROW_THREADS / d.h1 : 1;
+  const int parts = d.h1 <= MLP_THREADS ? MLP_THREADS / d.h1 : 1;
   return (size_t)(d.hid + 2 * (d.h1 + d.h2) + d.n_classes + 8 + parts * d.h1 + 8) * sizeof(float);
 }
-__global__ void __launch_bounds__(ROW_THREADS) mlp_kernel(Desc d) {
+__global__ void __launch_bounds__(MLP_THREADS) mlp_kernel(Desc d) {
   extern __shared__ float sm[];
   float* zs = sm;
   float* work = zs + d.hid;
@@ -551,13 +563,13 @@ __global__ void __launch_bounds__(ROW_THREADS) mlp_kernel(Desc d) {
   mlp_forward(d, b, zs, work);
   if (d.training && d.dZ) mlp_backward(d, b, zs, work);
 }
-__global__ void __launch_bounds__(ROW_THREADS) mlp_bwd_kernel(Desc d) {
+__global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
   extern __shared__ float sm[];
   mlp_backward(d, blockIdx.x, sm, sm + d.hid);
 }
 
 template <int DPL>
-__global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d) {
+__global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases) {
   extern __shared__ float sm[];
   const int D = d.D;
   float* dx0 = sm;                  // [D]
@@ -577,7 +589,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d) {
     for (int k = tid; k < d.L * 4; k += ROW_THREADS) acc_bp[k] = 0.f;
     for (int k = st; k < D; k += SIDE_THREADS) din[side * 2 * D + k] = 0.f;          // dh carried between layers
     __syncthreads();
-    if (d.use_n) {
+    if (d.use_n && (phases & 1)) {
       const int A = side ? d.A_nb : d.A_ni;
       for (int l = d.L - 1; l >= 0; --l) {
         const int zc = col_n(d, l, side);
@@ -633,7 +645,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d) {
       __syncthreads();
     }
     // ---- pooling backward ----
-    if (d.dE) {
+    if (d.dE && (phases & 1)) {
       const int nb = d.cc_nodeptr[g], ne = d.cc_nodeptr[g + 1];
       if (!d.pool_max) {
         for (int e = tid; e < (ne - nb) * D; e += ROW_THREADS) {
@@ -651,7 +663,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d) {
       }
     }
     // ---- property-aware outputs backward: d q (global atomics) and d b_p (CTA reduction) ----
-    {
+    if (phases & 2) {
       const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
       const int per_layer = wp_ + ws_;
       for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
@@ -752,37 +764,64 @@ extern "C" {
 
 int subgnn_model_desc_size(void) { return (int)sizeof(subgnn_model_desc); }
 
-int subgnn_model_prep(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_prep_batch(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   prep_batch_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*d);
-  rc = subgnn_check_launch("prep_batch_kernel");
+  return subgnn_check_launch("prep_batch_kernel");
+}
+
+int subgnn_model_prep_weights(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
   if (rc) return rc;
-  dim3 grid(8, (d->use_n ? 2 * d->L : 0) + 3);
+  dim3 grid(32, (d->use_n ? 2 * d->L : 0) + 3);
   transpose_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
   return subgnn_check_launch("transpose_weights_kernel");
 }
 
-int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_prep(const subgnn_model_desc* d, void* stream) {
+  int rc = subgnn_model_prep_batch(d, stream);
+  if (rc) return rc;
+  return subgnn_model_prep_weights(d, stream);
+}
+
+int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   const long long total = (long long)d->L * ((d->use_p ? d->B * d->A_pi + d->A_pb : 0) + (d->use_s ? 2 * d->A_s : 0));
   if (total == 0) return SUBGNN_OK;
-  q_fwd_kernel<<<sg_grid_for(total, 8, 8), 256, 0, (cudaStream_t)stream>>>(*d);
+  if (!d->use_p) which &= ~SUBGNN_Q_POS;
+  if (!d->use_s) which &= ~SUBGNN_Q_STRUC;
+  if (!which) return SUBGNN_OK;
+  q_fwd_kernel<<<sg_grid_for(total, 8, 8), 256, 0, (cudaStream_t)stream>>>(*d, which);
   return subgnn_check_launch("q_fwd_kernel");
 }
 
-int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream) { return subgnn_model_q_fwd_part(d, SUBGNN_Q_POS | SUBGNN_Q_STRUC, stream); }
+
+int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
+  if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
+  if (!phases) return SUBGNN_OK;
   const size_t smem = row_smem_bytes(d->D);
-  DISPATCH_DPL(d->D, row_fwd_kernel, <<<row_grid(d), ROW_THREADS, smem, (cudaStream_t)stream>>>(*d));
-  rc = subgnn_check_launch("row_fwd_kernel");
+  DISPATCH_DPL(d->D, row_fwd_kernel, <<<row_grid(d), ROW_THREADS, smem, (cudaStream_t)stream>>>(*d, phases));
+  return subgnn_check_launch("row_fwd_kernel");
+}
+
+int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
   if (rc) return rc;
   const size_t ms = mlp_smem(*d);
   if (ms > 48 * 1024) cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms);
-  mlp_kernel<<<d->B, ROW_THREADS, ms, (cudaStream_t)stream>>>(*d);
+  mlp_kernel<<<d->B, MLP_THREADS, ms, (cudaStream_t)stream>>>(*d);
   return subgnn_check_launch("mlp_kernel");
+}
+
+int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {
+  int rc = subgnn_model_rows_fwd(d, SUBGNN_PHASE_N | SUBGNN_PHASE_PS, stream);
+  if (rc) return rc;
+  return subgnn_model_mlp_fwd(d, stream);
 }
 
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
@@ -790,23 +829,33 @@ int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
   if (rc) return rc;
   const size_t smem = (size_t)(d->hid + d->h1 + d->h2 + d->n_classes + 8) * sizeof(float);
   if (smem > 48 * 1024) cudaFuncSetAttribute(mlp_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  mlp_bwd_kernel<<<d->B, ROW_THREADS, smem, (cudaStream_t)stream>>>(*d);
+  mlp_bwd_kernel<<<d->B, MLP_THREADS, smem, (cudaStream_t)stream>>>(*d);
   return subgnn_check_launch("mlp_bwd_kernel");
 }
 
-int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  DISPATCH_DPL(d->D, row_bwd_kernel, <<<row_grid(d), ROW_THREADS, bwd_smem(*d), (cudaStream_t)stream>>>(*d));
+  if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
+  if (!phases) return SUBGNN_OK;
+  DISPATCH_DPL(d->D, row_bwd_kernel, <<<row_grid(d), ROW_THREADS, bwd_smem(*d), (cudaStream_t)stream>>>(*d, phases));
   return subgnn_check_launch("row_bwd_kernel");
 }
+
+int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream) { return subgnn_model_rows_bwd(d, SUBGNN_PHASE_N | SUBGNN_PHASE_PS, stream); }
 
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   const int groups = (d->use_p ? 2 : 0) + (d->use_s ? 2 : 0);
   if (groups == 0) return SUBGNN_OK;
-  dim3 grid(8, d->L * groups);
+  // grid.x sized for the largest group (the B * A_pi position-internal entries): ~2-3 entries per warp keeps the dependent
+  // id -> row -> atomics chains short; CTAs of the small groups retire immediately
+  int max_cnt = d->use_p ? (d->B * d->A_pi > d->A_pb ? d->B * d->A_pi : d->A_pb) : d->A_s;
+  if (d->use_s && d->A_s > max_cnt) max_cnt = d->A_s;
+  int gx = sg_div_up(max_cnt, 24);
+  gx = gx < 8 ? 8 : (gx > 96 ? 96 : gx);
+  dim3 grid(gx, d->L * groups);
   q_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
   return subgnn_check_launch("q_bwd_kernel");
 }

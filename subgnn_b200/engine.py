@@ -472,6 +472,8 @@ class Engine:
         self.eval_cc = {}
         self.lr = float(hp['learning_rate'])
         self.grad_clip = float(hp.get('grad_clip', 0.0) or 0.0)
+        self.concurrent = bool(hp.get('b200_concurrent_streams', True))
+        self._side = None
 
     def init_parameters(self, seed=0):
         """Random initialisation with torch's default laws for the reference's modules: nn.Linear
@@ -541,23 +543,54 @@ class Engine:
         return self.ctx[key]
 
     # ---- launches --------------------------------------------------------------------------------
+    # The walk-encoder LSTM depends only on the parameters (the structure anchor patches are shared by every subgraph,
+    # anchor_patch_samplers.py:381-386), the neighbourhood chains only on the batch: they are launched on two streams
+    # (fork / join with events, captured into the step graph as parallel branches).
+    def _side_stream(self):
+        if getattr(self, '_side', None) is None:
+            self._side = torch.cuda.Stream(device=self.device)
+        return self._side
+
     def _forward_launches(self, c, st):
+        main = torch.cuda.current_stream()
         call('subgnn_fill_zero', ptr(c.Z), c.Z.numel(), st)
-        if self.lstm is not None:
+        fork = self.lstm is not None and self.concurrent
+        if fork:
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
+        elif self.lstm is not None:
             self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
-        call('subgnn_model_prep', c.dptr, st)
-        call('subgnn_model_q_fwd', c.dptr, st)
-        call('subgnn_model_sub_fwd', c.dptr, st)
+        call('subgnn_model_prep_batch', c.dptr, st)
+        call('subgnn_model_prep_weights', c.dptr, st)
+        call('subgnn_model_q_fwd_part', c.dptr, 1, st)               # position anchors
+        call('subgnn_model_rows_fwd', c.dptr, 1, st)                 # pooling + neighbourhood channel
+        if fork:
+            main.wait_stream(side)
+        call('subgnn_model_q_fwd_part', c.dptr, 2, st)               # structure anchors (LSTM output)
+        call('subgnn_model_rows_fwd', c.dptr, 2, st)                 # P / S property-aware outputs
+        call('subgnn_model_mlp_fwd', c.dptr, st)
         call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
 
     def _backward_launches(self, c, st, external_dlogits=False):
+        main = torch.cuda.current_stream()
         if external_dlogits:
             call('subgnn_model_mlp_bwd', c.dptr, st)
-        call('subgnn_model_sub_bwd', c.dptr, st)
-        call('subgnn_model_q_bwd', c.dptr, st)
-        if self.lstm is not None:
+        call('subgnn_model_rows_bwd', c.dptr, 2, st)                 # d q, d b_p
+        call('subgnn_model_q_bwd', c.dptr, st)                       # d emb_s, d w_p, position-anchor rows of dE
+        fork = self.lstm is not None and self.concurrent
+        if fork:
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
+        elif self.lstm is not None:
             self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), st)
+        call('subgnn_model_rows_bwd', c.dptr, 1, st)                 # neighbourhood chains + pooling
         call('subgnn_model_wgrad', c.dptr, st)
+        if fork:
+            main.wait_stream(side)
 
     def zero_grads(self, c, st):
         call('subgnn_fill_zero', ptr(self.arena.grads), self.arena.size, st)
