@@ -28,27 +28,7 @@ from .graph import DeviceGraph
 PROJECT_ROOT = Path('.')      # config.py:5 equivalent; set subgnn_b200.SubGNN.PROJECT_ROOT like config.PROJECT_ROOT
 
 
-def read_subgraphs(sub_f):
-    """subgraph_utils.py:24-92 — 'n1-n2-..\\tlabel[-label]\\tsplit' lines -> train/val/test node lists and labels."""
-    labels, out = {}, {'train': ([], []), 'val': ([], []), 'test': ([], [])}
-    multilabel = False
-    with open(sub_f) as fin:
-        for line in fin:
-            parts = line.rstrip('\n').split('\t')
-            nodes = [int(n) for n in parts[0].split('-') if n != '']
-            if not nodes:
-                continue
-            labs = parts[1].split('-')
-            multilabel |= len(labs) > 1
-            for lab in labs:
-                labels.setdefault(lab, len(labels))
-            split = parts[2].strip()
-            if split in out:
-                out[split][0].append(nodes)
-                out[split][1].append([labels[l] for l in labs])
-    if len(out['val'][0]) < len(out['test'][0]):                       # subgraph_utils.py:89-90
-        out['val'], out['test'] = out['test'], out['val']
-    return out, multilabel, len(labels)
+from .formats import SimilarityCache, load_embeddings, load_hop_table, read_edge_list, read_subgraphs  # noqa: E402,F401
 
 
 class _LSTMFunction(torch.autograd.Function):
@@ -160,9 +140,13 @@ class SubGNN(nn.Module):
             self.hparams['structure_similarity_fn'] = 'dtw'                                    # SubGNN.py:186-187
         self.engine = None
         self.metric_scores = []
+        self.test_results = None
         self._param_names = []
         if graph_path is not None:
             self.read_data()
+            # parameters must exist once the constructor returns (train.py:307-316 restores a checkpoint before fit), so the
+            # one-off preparation runs here; Trainer.fit's prepare_data() call is then a no-op
+            self.prepare_data()
 
     # ---- construction helpers ----------------------------------------------------------------------
     @classmethod
@@ -202,38 +186,73 @@ class SubGNN(nn.Module):
     # ---- data (SubGNN.py:519-570) --------------------------------------------------------------------
     def read_data(self):
         root = PROJECT_ROOT
-        edges = np.loadtxt(root / self.graph_path, dtype=np.int64, usecols=(0, 1)).reshape(-1, 2)
-        n_nodes = int(edges.max()) + 1
-        emb = torch.load(root / self.embedding_path, map_location='cpu')
-        n_nodes = max(n_nodes, emb.shape[0])
+        edges = read_edge_list(root / self.graph_path)
+        emb = load_embeddings(root / self.embedding_path)
+        n_nodes = max(int(edges.max()) + 1 if edges.size else 0, emb.shape[0])
         self.graph = DeviceGraph.from_edges(n_nodes, edges, device=self.device_, one_indexed=False)    # ids become 1-indexed (:555-559)
+        first = np.full(n_nodes, n_nodes, dtype=np.int64)                                      # nx.read_edgelist node insertion order
+        np.minimum.at(first, edges.reshape(-1), np.arange(edges.size))
+        self.graph.insertion_rank = np.argsort(np.argsort(first, kind='stable'), kind='stable')
         splits, self.multilabel, n_labels = read_subgraphs(root / self.subgraph_path)
-        if self.multilabel:
-            raise NotImplementedError('multi-label files: use from_prepared with labels_multi')
         self.sub_G = {k: [[n + 1 for n in s] for s in v[0]] for k, v in splits.items()}
-        self.sub_G_label = {k: np.array([l[0] for l in v[1]], dtype=np.int64) for k, v in splits.items()}
         if self.hparams.get('subset_data', False):                                             # :542-546
             B = self.hparams['batch_size']
             self.sub_G = {k: v[:B] for k, v in self.sub_G.items()}
-            self.sub_G_label = {k: v[:B] for k, v in self.sub_G_label.items()}
-        self.num_classes = int(max(v.max() for v in self.sub_G_label.values() if len(v))) + 1
+            splits = {k: (v[0][:B], v[1][:B]) for k, v in splits.items()}
+        if self.multilabel:                                                                    # :533-536 MultiLabelBinarizer().fit(all)
+            classes = sorted({l for v in splits.values() for labs in v[1] for l in labs})
+            col = {c: i for i, c in enumerate(classes)}
+            self.multilabel_classes = classes
+            self.sub_G_label = {}
+            for k, v in splits.items():
+                ind = np.zeros((len(v[1]), len(classes)), dtype=np.int64)
+                for i, labs in enumerate(v[1]):
+                    ind[i, [col[l] for l in labs]] = 1
+                self.sub_G_label[k] = ind
+            self.num_classes = max(classes) + 1                                                # :548-549
+            if self.num_classes != len(classes):
+                raise NotImplementedError('multi-label task whose label ids are not all present in train/val/test')
+        else:
+            self.sub_G_label = {k: np.array([l[0] for l in v[1]], dtype=np.int64) for k, v in splits.items()}
+            self.num_classes = int(max(v.max() for v in self.sub_G_label.values() if len(v))) + 1   # :551
         self.hparams['node_embed_size'] = emb.shape[1]
-        self.embeddings = np.concatenate([np.zeros((1, emb.shape[1]), dtype=np.float32), emb.numpy().astype(np.float32)])   # :564-565
+        self.embeddings = np.concatenate([np.zeros((1, emb.shape[1]), dtype=np.float32), emb,
+                                          np.zeros((n_nodes - emb.shape[0], emb.shape[1]), dtype=np.float32)])   # :564-565
         sp = root / self.shortest_paths_path if self.shortest_paths_path else None
         if sp is not None and sp.exists() and (self.hparams['use_position'] or self.hparams['use_neighborhood']):
-            self.graph.set_hop_table(np.load(sp, allow_pickle=True))
+            self.graph.set_hop_table(load_hop_table(sp, n_nodes))
+
+    def _cache(self):
+        if not self.similarities_path:
+            return None
+        return SimilarityCache(PROJECT_ROOT / self.similarities_path, self.hparams, write=bool(self.hparams.get('b200_write_caches', True)))
 
     def prepare_data(self, seed=None):
-        """SubGNN.py:1024-1063 on the GPU (components, border sets, walks, DTW / SP similarities, anchors)."""
+        """SubGNN.py:1024-1063 on the GPU (components, border sets, walks, DTW / SP similarities, anchors); every cached
+        product under <task>/similarities/ is read / written with the reference's file names (formats.SimilarityCache)."""
         from . import prepare as prep
+        if self.engine is not None:                      # Lightning calls prepare_data once; from_prepared models are ready
+            return
         seed = self.hparams.get('seed', 0) if seed is None else seed
         splits = [s for s in ('train', 'val') if len(self.sub_G[s])]
+        self.sim_cache = self._cache()
         prepared = prep.prepare(self.hparams, self.graph, self.sub_G, self.sub_G_label, self.embeddings, seed=seed, splits=splits,
-                                num_classes=self.num_classes)
+                                num_classes=self.num_classes, cache=self.sim_cache, multilabel=self.multilabel)
         eng = Engine(self.hparams, prepared, device=self.device_, graph=self.graph, seed=seed)
         eng.init_parameters(seed)
         self.prepared = prepared
         self._attach(eng)
+
+    def prepare_test_data(self, seed=None):
+        """SubGNN.py:994-1022: same products for the test split; P-border and structure anchors are shared with training."""
+        from . import prepare as prep
+        if 'test' in self.engine.prepared['cc_ids']:
+            return
+        seed = self.hparams.get('seed', 0) if seed is None else seed
+        q = prep.prepare(self.hparams, self.graph, self.sub_G, self.sub_G_label, self.embeddings, seed=seed, splits=['test'],
+                         num_classes=self.num_classes, cache=getattr(self, 'sim_cache', None) or self._cache(), multilabel=self.multilabel,
+                         shared=self.engine.prepared)
+        self.engine.add_split('test', q)
 
     # ---- forward / steps -----------------------------------------------------------------------------
     def forward(self, dataset_type, *unused, subgraph_idx=None, **kw):
@@ -255,9 +274,10 @@ class SubGNN(nn.Module):
     def training_step(self, train_batch, batch_idx=0):
         """SubGNN.py:317-348 (autograd path: usable with any torch optimizer / trainer loop)."""
         logits = self.forward('train', subgraph_idx=train_batch['subgraph_idx'])
-        labels = train_batch['label'].to(logits.device).squeeze(-1)
+        labels = train_batch['label'].to(logits.device)
+        labels = labels.reshape(logits.shape[0], -1) if self.multilabel else labels.reshape(-1)
         loss = self._loss(logits, labels)
-        acc = (logits.argmax(dim=1) == labels).float().mean() if not self.multilabel else torch.tensor(0.0)
+        acc = calc_accuracy(logits.detach(), labels, self.multilabel)
         return {'loss': loss, 'log': {'train_loss': loss, 'train_acc': acc}}
 
     def training_step_fused(self, train_batch, use_graph=True):
@@ -268,14 +288,17 @@ class SubGNN(nn.Module):
         return {'loss': loss}
 
     def val_test_step(self, batch, batch_idx=0, is_test=False):
-        split = 'test' if is_test else 'val'
+        """SubGNN.py:350-391."""
+        k = 'test' if is_test else 'val'
         with torch.no_grad():
             idx = batch['subgraph_idx'].reshape(-1).cpu().numpy()
-            logits, loss = self.engine.forward(split, idx, training=False)
-        labels = batch['label'].to(logits.device).squeeze(-1)
-        acc = (logits.argmax(dim=1) == labels).float().mean()
-        k = 'test' if is_test else 'val'
-        return {k + '_loss': loss.clone().squeeze(), k + '_acc': acc, k + '_logits': logits.clone(), k + '_labels': labels}
+            logits, loss = self.engine.forward(k, idx, training=False)
+        labels = batch['label'].to(logits.device)
+        labels = labels.reshape(len(idx), -1) if self.multilabel else labels.reshape(-1)
+        logits = logits.clone()
+        acc = calc_accuracy(logits, labels, self.multilabel)
+        macro_f1 = calc_f1(logits, labels, 'macro', self.multilabel)
+        return {k + '_loss': loss.clone().squeeze(), k + '_acc': acc, k + '_macro_f1': macro_f1, k + '_logits': logits, k + '_labels': labels}
 
     def validation_step(self, val_batch, batch_idx=0):
         return self.val_test_step(val_batch, batch_idx, is_test=False)
@@ -283,16 +306,48 @@ class SubGNN(nn.Module):
     def test_step(self, test_batch, batch_idx=0):
         return self.val_test_step(test_batch, batch_idx, is_test=True)
 
+    # ---- epoch end (SubGNN.py:408-504): host-side sklearn metrics over the gathered logits -------------------
+    def _epoch_end(self, outputs, k):
+        logits = torch.cat([x[k + '_logits'] for x in outputs], dim=0)
+        labels = torch.cat([x[k + '_labels'] for x in outputs], dim=0)
+        logs = epoch_metrics(logits, labels, self.multilabel, k)
+        avg_loss = torch.stack([x[k + '_loss'] for x in outputs]).mean().cpu()
+        avg_acc = torch.stack([x[k + '_acc'] for x in outputs]).mean()
+        avg_macro_f1 = torch.stack([x[k + '_macro_f1'] for x in outputs]).mean()
+        head = {k + '_loss': avg_loss, k + '_micro_f1': logs.pop('micro_f1'), k + '_macro_f1': logs.pop('macro_f1'), k + '_acc': logs.pop('acc'),
+                'avg_%s_acc' % k: avg_acc, ('avg_macro_f1' if k == 'val' else 'test_avg_macro_f1'): avg_macro_f1, k + '_auroc': logs.pop('auroc')}
+        head.update(logs)
+        return avg_loss, head
+
+    def validation_epoch_end(self, outputs):
+        avg_loss, logs = self._epoch_end(outputs, 'val')
+        if self.hparams.get('resample_anchor_patches', False):                                  # SubGNN.py:449-457
+            self.resample_anchor_patches()
+        self.metric_scores.append(logs)                                                        # keep track for optuna (:459)
+        return {'avg_val_loss': avg_loss, 'log': logs}
+
+    def test_epoch_end(self, outputs):
+        avg_loss, logs = self._epoch_end(outputs, 'test')
+        self.test_results = logs
+        return {'avg_test_loss': avg_loss, 'log': logs}
+
+    def resample_anchor_patches(self):
+        """SubGNN.py:449-457: draw fresh N / P / S anchors for train + val (similarities come from the cache / hop table)."""
+        from . import prepare as prep
+        self._resample_round = getattr(self, '_resample_round', 0) + 1
+        old = self.engine.prepared
+        splits = [s for s in ('train', 'val') if s in old['cc_ids']]
+        sub_G, labels = {s: old['sub_G'][s] for s in splits}, {s: old['labels'][s] for s in splits}
+        from .formats import MemoryCache
+        q = prep.prepare(self.hparams, self.engine.graph, sub_G, labels, old['embeddings'], seed=self.engine.seed + 7717 * self._resample_round,
+                         splits=splits, num_classes=self.num_classes, multilabel=self.multilabel, cache=MemoryCache(self.hparams, old))
+        self.engine.rebind(q)
+
     # ---- loaders (SubGNN.py:1116-1151): batches carry indices and labels only ---------------------------
     def _loader(self, split, shuffle):
         labels = torch.as_tensor(np.asarray(self.engine.prepared['labels'][split]))
-        n, B = len(labels), self.hparams['batch_size']
-        order = torch.randperm(n) if shuffle else torch.arange(n)
-        drop_last = shuffle and B <= n
-        for i in range(0, n - (B - 1 if drop_last else 0), B):
-            idx = order[i:i + B]
-            if len(idx):
-                yield {'subgraph_idx': idx.view(-1, 1), 'label': labels[idx]}
+        B = self.hparams['batch_size']
+        return IndexLoader(labels, B, shuffle, drop_last=shuffle and B <= len(labels))           # drop_last: SubGNN.py:1126
 
     def train_dataloader(self):
         return self._loader('train', True)
@@ -300,8 +355,67 @@ class SubGNN(nn.Module):
     def val_dataloader(self):
         return self._loader('val', False)
 
+    def test_dataloader(self):
+        self.prepare_test_data()                                                               # SubGNN.py:1146
+        return self._loader('test', False)
+
     def configure_optimizers(self):
         return torch.optim.Adam(self.parameters(), lr=self.hparams['learning_rate'])               # SubGNN.py:1156-1161
 
     def backward(self, trainer, loss, optimizer, optimizer_idx):
         loss.backward(retain_graph=True)                                                        # SubGNN.py:1163-1164
+
+
+class IndexLoader:
+    """Re-iterable stand-in for DataLoader(SubgraphDataset, collate_fn=_pad_collate) (SubGNN.py:1068-1151): a batch is
+    {'subgraph_idx': (B, 1) int64, 'label': (B,) or (B, K)} — component ids, border sets and similarity slabs stay on the device."""
+
+    def __init__(self, labels, batch_size, shuffle, drop_last):
+        self.labels, self.batch_size, self.shuffle, self.drop_last = labels, batch_size, shuffle, drop_last
+
+    def __len__(self):
+        n, B = len(self.labels), self.batch_size
+        return n // B if self.drop_last else (n + B - 1) // B
+
+    def __iter__(self):
+        n, B = len(self.labels), self.batch_size
+        order = torch.randperm(n) if self.shuffle else torch.arange(n)
+        for b in range(len(self)):
+            idx = order[b * B:(b + 1) * B]
+            yield {'subgraph_idx': idx.view(-1, 1), 'label': self.labels[idx]}
+
+
+# ---- metrics (subgraph_utils.py:93-124, SubGNN.py:408-504): sklearn on the host, as in the reference ----------------------
+def _pred(logits, multilabel):
+    return (torch.sigmoid(logits) > 0.5) if multilabel else torch.argmax(logits, dim=-1)
+
+
+def calc_f1(logits, labels, avg_type='macro', multilabel=False):
+    from sklearn.metrics import f1_score
+    return torch.tensor([f1_score(labels.cpu().numpy(), _pred(logits, multilabel).cpu().numpy(), average=avg_type)])
+
+
+def calc_accuracy(logits, labels, multilabel=False):
+    from sklearn.metrics import accuracy_score
+    return torch.tensor([accuracy_score(labels.cpu().numpy(), _pred(logits, multilabel).cpu().numpy())])
+
+
+def epoch_metrics(logits, labels, multilabel, prefix):
+    """micro / macro F1, accuracy, AUROC (+ per-class AUROC keyed '<prefix>_auroc_class_<c>') exactly as
+    validation_epoch_end / test_epoch_end compute them."""
+    from sklearn.metrics import roc_auc_score
+    logits, labels = logits.detach().float().cpu(), labels.detach().cpu()
+    out = {'macro_f1': calc_f1(logits, labels, 'macro', multilabel).squeeze(), 'micro_f1': calc_f1(logits, labels, 'micro', multilabel).squeeze(),
+           'acc': calc_accuracy(logits, labels, multilabel).squeeze()}
+    if multilabel:
+        out['auroc'] = roc_auc_score(labels, torch.sigmoid(logits), multi_class='ovr')
+    elif len(torch.unique(labels)) == 2:
+        out['auroc'] = roc_auc_score(labels, torch.softmax(logits, dim=1)[:, 1])
+    else:
+        out['auroc'] = roc_auc_score(labels, torch.softmax(logits, dim=1), multi_class='ovr')
+    for c in range(logits.shape[1]):
+        if multilabel:
+            out['%s_auroc_class_%d' % (prefix, c)] = roc_auc_score(labels[:, c], torch.sigmoid(logits)[:, c])
+        else:
+            out['%s_auroc_class_%d' % (prefix, c)] = roc_auc_score(torch.nn.functional.one_hot(labels, num_classes=logits.shape[1])[:, c], logits[:, c])
+    return out

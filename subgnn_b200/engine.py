@@ -154,7 +154,7 @@ class SplitTables:
         self.multilabel = bool(prepared.get('multilabel', False))
         self.labels = tf(lab) if self.multilabel else t32(lab.reshape(-1))
         dense = prepared.get('NP_sim')
-        dense_rows = np.asarray(dense[split])[valid] if dense is not None else None     # (n_cc, N)
+        dense_rows = np.asarray(dense[split])[valid] if (dense is not None and split in dense) else None     # (n_cc, N)
         hop = graph.hop if (graph is not None and dense_rows is None) else None
 
         def resolve(ids_rows, anchor_row=None):
@@ -461,13 +461,7 @@ class Engine:
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=self.device)
         self.lstm = None
         if hp['use_structure']:
-            W, T = hp['n_triangular_walks'], hp['random_walk_len']
-            walks = []
-            for key in (2, 3):                                           # internal walks, then border walks (side-major)
-                for l in range(L):
-                    walks.append(np.asarray(prepared['anchors_structure'][l][key]).reshape(-1, T))
-            walks = torch.from_numpy(np.concatenate(walks).astype(np.int32)).to(self.device)
-            self.lstm = LstmRunner(self.arena, hp, walks, 2 * L * self.A['s'], self.device)
+            self.lstm = LstmRunner(self.arena, hp, self._structure_walks(prepared), 2 * L * self.A['s'], self.device)
         self.ctx = {}
         self.eval_cc = {}
         self.lr = float(hp['learning_rate'])
@@ -535,6 +529,37 @@ class Engine:
         pooled = e.sum(dim=2) if self.hp['cc_aggregator'] == 'sum' else e.max(dim=2)[0]
         for nm in ('N_I', 'N_B', 'S_I', 'S_B', 'P_I', 'P_B'):
             self.arena.view('train_%s_cc_embed' % nm).copy_(pooled)
+
+    def add_split(self, split, q):
+        """merge the products of a later-prepared split (prepare_test_data, SubGNN.py:994-1022) into the engine."""
+        p = self.prepared
+        for key in ('cc_ids', 'labels', 'sub_G', 'N_border', 'I_S_sim', 'B_S_sim', 'anchors_neigh_int', 'anchors_neigh_border', 'anchors_pos_int'):
+            if isinstance(q.get(key), dict) and split in q[key]:
+                if not isinstance(p.get(key), dict):
+                    p[key] = {}
+                p[key][split] = q[key][split]
+        if isinstance(q.get('NP_sim'), dict) and split in q['NP_sim'] and isinstance(p.get('NP_sim'), dict):
+            p['NP_sim'][split] = q['NP_sim'][split]
+        elif isinstance(p.get('NP_sim'), dict) and self.graph is not None and self.graph.hop is not None:
+            pass                                              # SplitTables falls back to the hop table for this split
+        self.tables.pop(split, None)
+
+    def rebind(self, prepared):
+        """swap in freshly sampled anchors (resample_anchor_patches, SubGNN.py:449-457); parameters and Adam state stay."""
+        hp = self.hp
+        self.prepared = prepared
+        self.tables = {'train': SplitTables(prepared, 'train', hp, self.device, self.graph)}
+        self.ctx, self.eval_cc = {}, {}
+        if hp['use_structure']:
+            self.lstm = LstmRunner(self.arena, hp, self._structure_walks(prepared), 2 * hp['n_layers'] * self.A['s'], self.device)
+
+    def _structure_walks(self, prepared):
+        T = self.hp['random_walk_len']
+        walks = []
+        for key in (2, 3):                                           # internal walks, then border walks (side-major)
+            for l in range(self.hp['n_layers']):
+                walks.append(np.asarray(prepared['anchors_structure'][l][key]).reshape(-1, T))
+        return torch.from_numpy(np.concatenate(walks).astype(np.int32)).to(self.device)
 
     def context(self, split, B, training):
         key = (split, B, training)
