@@ -267,6 +267,8 @@ def main():
     dev = 'cuda:%d' % local_rank
     if world > 1:
         import torch.distributed as dist
+        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
+            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device(dev))
     from subgnn_b200 import _abi
     from subgnn_b200.engine import Engine

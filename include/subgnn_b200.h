@@ -131,6 +131,13 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
 int subgnn_add_inplace(float* dst, const float* src, int n, void* stream);
 int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
 int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);
+/* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out))): the head is
+   linear, so the walks are summed first.  fwd: AGGG[g][:] = sum_w agg(OUT[g*group+w]), bias_scaled = group * bias;
+   bwd: dOUT rows <- dAGGG[g] (t = T-1 only for 'last'), db += group * sum_g dEMB[g] */
+int subgnn_lstm_agg_group_fwd(const float* OUT, float* AGGG, int n_groups, int group, int T, int H2, int sum_mode, const float* bias,
+                              float* bias_scaled, int D, void* stream);
+int subgnn_lstm_agg_group_bwd(const float* dAGGG, float* dOUT, int n_groups, int group, int T, int H2, int sum_mode, const float* dEMB,
+                              float* db, int D, void* stream);
 int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream);
 int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream);
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,

@@ -42,7 +42,7 @@ class _LSTMFunction(torch.autograd.Function):
         runner.forward(None, module.training, module._seed, ptr(module._step), st, dense_x=xc.view(-1, x.shape[2]))
         ctx.module, ctx.runner, ctx.arena, ctx.training = module, runner, arena, module.training
         ctx.x_shape = x.shape
-        return runner.Y.clone()
+        return runner.EMB.clone()
 
     @staticmethod
     def backward(ctx, dy):

@@ -287,12 +287,72 @@ __global__ void group_bcast_kernel(const float* __restrict__ dEMB, float* __rest
   }
 }
 
+// Walk-group head, forward.  The head is linear and the patch embedding is the SUM of its walks' outputs
+// (anchor_patch_samplers.py:429-433), so the walks are summed first and the Linear runs on one row per patch:
+//   AGGG[g][c] = sum_{w<group} agg(OUT[g*group + w])[c],   bias_scaled[d] = group * bias[d]
+// (agg = row T-1 for 'last', SubGNN.py:83, or the sum over t for 'sum', :85).  group = 1 is the plain per-sequence head.
+__global__ void lstm_agg_group_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGGG, int n_groups, int group, int T, int H2,
+                                          int sum_mode, const float* __restrict__ bias, float* __restrict__ bias_scaled, int D) {
+  const long long total = (long long)n_groups * H2;
+  const long long tid0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (bias_scaled && tid0 < D) bias_scaled[tid0] = (float)group * bias[tid0];
+  for (long long e = tid0; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int g = (int)(e / H2), c = (int)(e % H2);
+    float v = 0.f;
+    for (int w = 0; w < group; ++w) {
+      const size_t seq = (size_t)g * group + w;
+      if (sum_mode) {
+        for (int t = 0; t < T; ++t) v += OUT[(seq * T + t) * H2 + c];
+      } else {
+        v += OUT[(seq * T + T - 1) * H2 + c];
+      }
+    }
+    AGGG[e] = v;
+  }
+}
+
+// Walk-group head, backward: dOUT[(g, w)][t][:] = dAGGG[g][:] for every t ('sum') or only t = T-1 ('last', zero elsewhere);
+// block 0 also accumulates the head's bias gradient  db[d] += group * sum_g dEMB[g][d].
+__global__ void lstm_agg_group_bwd_kernel(const float* __restrict__ dAGGG, float* __restrict__ dOUT, int n_groups, int group, int T, int H2,
+                                          int sum_mode, const float* __restrict__ dEMB, float* __restrict__ db, int D) {
+  const long long total = (long long)n_groups * group * T * H2;
+  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(e % H2);
+    const long long st = e / H2;
+    const int t = (int)(st % T);
+    const long long seq = st / T;
+    dOUT[e] = (sum_mode || t == T - 1) ? dAGGG[(size_t)(seq / group) * H2 + c] : 0.f;
+  }
+  if (db && blockIdx.x == 0) {
+    for (int d = threadIdx.x; d < D; d += blockDim.x) {
+      float v = 0.f;
+      for (int g = 0; g < n_groups; ++g) v += dEMB[(size_t)g * D + d];
+      atomicAdd(db + d, (float)group * v);
+    }
+  }
+}
+
 // inter-layer dropout (nn.LSTM dropout=p, training only): y = x * keep/(1-p); the same kernel applies the mask
 // to gradients.  Counter-based mask: element index within the buffer, salt = layer / step counter.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
                                unsigned salt, const int* __restrict__ step_dev) {
   if (step_dev) salt += 64u * (unsigned)*step_dev + 0x80000000u;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
+  // one Philox4x32 draw serves the four elements 4q .. 4q+3 (sg_dropout_scale uses word (idx & 3) of draw idx >> 2)
+  const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
+  const long long nq = n >> 2;
+  const bool vec = ((reinterpret_cast<uintptr_t>(x) | reinterpret_cast<uintptr_t>(y)) & 15) == 0;
+  for (long long q = blockIdx.x * (long long)blockDim.x + threadIdx.x; q < nq && vec; q += (long long)gridDim.x * blockDim.x) {
+    float4 v = reinterpret_cast<const float4*>(x)[q];
+    if (p > 0.f) {
+      const Philox4 r = sg_draw(seed, (uint64_t)q, salt, SG_TAG_DROP);
+      v.x *= sg_unit(r.x) >= p ? keep : 0.f;
+      v.y *= sg_unit(r.y) >= p ? keep : 0.f;
+      v.z *= sg_unit(r.z) >= p ? keep : 0.f;
+      v.w *= sg_unit(r.w) >= p ? keep : 0.f;
+    }
+    reinterpret_cast<float4*>(y)[q] = v;
+  }
+  for (long long e = (vec ? nq * 4 : 0) + blockIdx.x * (long long)blockDim.x + threadIdx.x; e < n; e += (long long)gridDim.x * blockDim.x)
     y[e] = x[e] * sg_dropout_scale(seed, salt, (uint64_t)e, p);
 }
 
@@ -421,10 +481,26 @@ int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, in
   return subgnn_check_launch("group_bcast_kernel");
 }
 
+int subgnn_lstm_agg_group_fwd(const float* OUT, float* AGGG, int n_groups, int group, int T, int H2, int sum_mode, const float* bias,
+                              float* bias_scaled, int D, void* stream) {
+  if (n_groups == 0) return SUBGNN_OK;
+  lstm_agg_group_fwd_kernel<<<sg_grid_for((long long)n_groups * H2, 128, 8), 128, 0, (cudaStream_t)stream>>>(OUT, AGGG, n_groups, group, T, H2,
+                                                                                                            sum_mode, bias, bias_scaled, D);
+  return subgnn_check_launch("lstm_agg_group_fwd_kernel");
+}
+
+int subgnn_lstm_agg_group_bwd(const float* dAGGG, float* dOUT, int n_groups, int group, int T, int H2, int sum_mode, const float* dEMB,
+                              float* db, int D, void* stream) {
+  if (n_groups == 0) return SUBGNN_OK;
+  lstm_agg_group_bwd_kernel<<<sg_grid_for((long long)n_groups * group * T * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(
+      dAGGG, dOUT, n_groups, group, T, H2, sum_mode, dEMB, db, D);
+  return subgnn_check_launch("lstm_agg_group_bwd_kernel");
+}
+
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
                    void* stream) {
   if (n == 0) return SUBGNN_OK;
-  dropout_kernel<<<sg_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, salt, step_dev);
+  dropout_kernel<<<sg_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, salt, step_dev);
   return subgnn_check_launch("dropout_kernel");
 }
 

@@ -219,9 +219,11 @@ class LstmRunner:
         self.X = [None] + [z(M + 1, 2 * H) for _ in range(1, self.nl)] if self.p_drop > 0 else [None] * self.nl
         self.whh_t = [z(2 * H * 4 * H) for _ in range(self.nl)]
         self.bsum = [z(8 * H) for _ in range(self.nl)]
-        self.AGG, self.dAGG = z(self.n_seq, 2 * H), z(self.n_seq, 2 * H)
-        self.Y, self.dY = z(self.n_seq, self.D), z(self.n_seq, self.D)
+        # head: the walks of a patch are summed BEFORE the (linear) head, so it runs on one row per patch (n_groups rows)
+        self.AGG, self.dAGG = z(n_groups, 2 * H), z(n_groups, 2 * H)
+        self.bias_scaled = z(self.D)
         self.EMB, self.dEMB = z(n_groups, self.D), z(n_groups, self.D)
+        self._aux = None
         t = torch.arange(M, device=self.dev, dtype=torch.int64)
         tt = t % self.T
         zero_row = torch.full_like(t, M)
@@ -239,8 +241,18 @@ class LstmRunner:
         top = k == self.nl - 1
         return (self.T, 1) if (top and not self.sum_mode) else (self.T, self.T)
 
+    # Independent launches (the reverse-direction projection of the top layer's last rows, every weight-gradient GEMM of the
+    # backward pass) go to two auxiliary streams, forked from / joined into the stream the runner is called on with events;
+    # under graph capture they become parallel branches of the step graph.
+    def _aux_streams(self):
+        if self._aux is None:
+            self._aux = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
+        return self._aux
+
     def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None):
         a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
+        cur = torch.cuda.current_stream()
+        aux = self._aux_streams()
         self.dense_x = dense_x
         if dense_x is not None:
             E_ptr = ptr(dense_x)
@@ -248,6 +260,8 @@ class LstmRunner:
             o = a.lstm_off[k]
             call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
                  ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
+        for k in range(self.nl):
+            o = a.lstm_off[k]
             x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st)
             sf, sr = self.steps(k)
             w_ih, G = a.base_addr(o['weight_ih']), ptr(self.G[k])
@@ -255,16 +269,19 @@ class LstmRunner:
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 8 * H, din, 0, st)
             else:
                 # 'last' aggregator, top layer: the reverse direction is only ever read at t = T-1 (SubGNN.py:83), so its
-                # input projection is computed for those n_seq rows only
+                # input projection is computed for those n_seq rows only (disjoint gate columns: runs beside the main GEMM)
+                aux[0].wait_stream(cur)
+                with torch.cuda.stream(aux[0]):
+                    xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
+                    call(self.fwd_fn, xl, ldxl, idsl, w_ih + 4 * (4 * H * din), din, self.bsum[k].data_ptr() + 4 * 4 * H,
+                         G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, aux[0].cuda_stream)
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
-                xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
-                call(self.fwd_fn, xl, ldxl, idsl, w_ih + 4 * (4 * H * din), din, self.bsum[k].data_ptr() + 4 * 4 * H,
-                     G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, st)
+                cur.wait_stream(aux[0])
             call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
-        call('subgnn_lstm_agg_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_seq, T, 2 * H, self.sum_mode, st)
-        call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, a.addr('lstm.linear.bias'),
-             ptr(self.Y), D, self.n_seq, D, 2 * H, 0, st)
-        call('subgnn_group_sum', ptr(self.Y), ptr(self.EMB), self.n_groups, self.W, D, st)
+        call('subgnn_lstm_agg_group_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_groups, self.W, T, 2 * H, self.sum_mode,
+             a.addr('lstm.linear.bias'), ptr(self.bias_scaled), D, st)
+        call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, ptr(self.bias_scaled),
+             ptr(self.EMB), D, self.n_groups, D, 2 * H, 0, st)
 
     def _wgrad(self, dy, ldy, x, ldx, ids, dw, lddw, db, M, N, K, st):
         if self.use_tc and M >= 256:
@@ -292,18 +309,24 @@ class LstmRunner:
         return x_ptr + 4 * ((T - 1) * ldx), T * ldx, None
 
     def backward(self, E_ptr, dE_ptr, training, seed, step_dev, st, dense_dx=None):
-        """consumes self.dEMB; accumulates into the gradient arena (and dE, or writes dense_dx for dense inputs)."""
+        """consumes self.dEMB; accumulates into the gradient arena (and dE, or writes dense_dx for dense inputs).
+        Critical chain on the calling stream: head input gradient -> [recurrence BPTT -> input gradient -> dropout mask] per
+        layer; every weight-gradient GEMM only consumes what the chain has already produced and runs on the auxiliary streams."""
         a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
+        cur = torch.cuda.current_stream()
+        aux = self._aux_streams()
         dense = self.dense_x is not None
         if dense:
             E_ptr = ptr(self.dense_x)
         g = 'grads'
-        call('subgnn_group_bcast', ptr(self.dEMB), ptr(self.dY), self.n_groups, self.W, D, st)
-        call('subgnn_linear_bwd_weight', ptr(self.dY), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
-             a.addr('lstm.linear.bias', g), self.n_seq, D, 2 * H, None, st)
-        call('subgnn_linear_bwd_input', ptr(self.dY), D, a.addr('lstm.linear.weight'), 2 * H, ptr(self.dAGG), 2 * H, None, self.n_seq, D,
+        aux[1].wait_stream(cur)
+        with torch.cuda.stream(aux[1]):
+            call('subgnn_linear_bwd_weight', ptr(self.dEMB), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
+                 None, self.n_groups, D, 2 * H, None, aux[1].cuda_stream)
+        call('subgnn_linear_bwd_input', ptr(self.dEMB), D, a.addr('lstm.linear.weight'), 2 * H, ptr(self.dAGG), 2 * H, None, self.n_groups, D,
              2 * H, 0, st)
-        call('subgnn_lstm_agg_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_seq, T, 2 * H, self.sum_mode, st)
+        call('subgnn_lstm_agg_group_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_groups, self.W, T, 2 * H, self.sum_mode,
+             ptr(self.dEMB), a.addr('lstm.linear.bias', g), D, st)
         for k in range(self.nl - 1, -1, -1):
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
@@ -316,13 +339,21 @@ class LstmRunner:
             w_ih, gw_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g)
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
-            self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, None, M, n_out, din, st)
-            if not full:
-                xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
-                self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, None, self.n_seq, 4 * H, din, st)
-            for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
-                self._wgrad(dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H, ptr(self.hprev[d_]),
-                            a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, st)
+            # ---- weight gradients: off the critical chain ----
+            aux[0].wait_stream(cur)
+            aux[1].wait_stream(cur)
+            with torch.cuda.stream(aux[0]):
+                s0 = aux[0].cuda_stream
+                self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, None, M, n_out, din, s0)
+                if not full:
+                    xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
+                    self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, None, self.n_seq, 4 * H, din, s0)
+            with torch.cuda.stream(aux[1]):
+                s1 = aux[1].cuda_stream
+                for d_ in range(2 if full else 1):                 # reverse direction took one step from h = 0: no W_hh gradient
+                    self._wgrad(dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H, ptr(self.hprev[d_]),
+                                a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, s1)
+            # ---- input gradient: the chain ----
             if k > 0:
                 dx_ptr, lddx, scat = ptr(self.dOUT[k - 1]), 2 * H, None
             elif dense:
@@ -344,6 +375,8 @@ class LstmRunner:
                          None, self.n_seq, 4 * H, din, 1, st)
             if k > 0 and self.p_drop > 0 and training:
                 call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+        cur.wait_stream(aux[0])
+        cur.wait_stream(aux[1])
 
 
 # ------------------------------------------------------------------------------------------------------
