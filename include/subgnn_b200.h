@@ -131,13 +131,13 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
 int subgnn_add_inplace(float* dst, const float* src, int n, void* stream);
 int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
 int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);
-/* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out))): the head is
-   linear, so the walks are summed first.  fwd: AGGG[g][:] = sum_w agg(OUT[g*group+w]), bias_scaled = group * bias;
-   bwd: dOUT rows <- dAGGG[g] (t = T-1 only for 'last'), db += group * sum_g dEMB[g] */
-int subgnn_lstm_agg_group_fwd(const float* OUT, float* AGGG, int n_groups, int group, int T, int H2, int sum_mode, const float* bias,
-                              float* bias_scaled, int D, void* stream);
-int subgnn_lstm_agg_group_bwd(const float* dAGGG, float* dOUT, int n_groups, int group, int T, int H2, int sum_mode, const float* dEMB,
-                              float* db, int D, void* stream);
+/* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out)), SubGNN.py:83-88).
+   The head is linear, so the walks are summed first: fwd  AGG[g] = sum_w agg(OUT[g*group+w]),  EMB[g] = W AGG[g] + group * bias;
+   bwd  dOUT rows <- W^T dEMB[g] (t = T-1 only for 'last'),  db += group * sum_g dEMB[g]   (dW = dEMB^T AGG: subgnn_linear_bwd_weight) */
+int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,
+                         int D, int sum_mode, void* stream);
+int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,
+                         int sum_mode, void* stream);
 int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream);
 int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream);
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
@@ -222,7 +222,7 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
 #define SUBGNN_PHASE_N 1
 #define SUBGNN_PHASE_PS 2
 int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream);
-int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training) */
+int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training); H1 must be zero on entry (split-K target) */
 int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream);
 /* SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers subgraph_mpn.py:133-241,
  * masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training also the

@@ -49,8 +49,8 @@ SIGNATURES = {
     'subgnn_add_inplace': [P, P, I, P],
     'subgnn_lstm_agg_fwd': [P, P, I, I, I, I, P],
     'subgnn_lstm_agg_bwd': [P, P, I, I, I, I, P],
-    'subgnn_lstm_agg_group_fwd': [P, P, I, I, I, I, I, P, P, I, P],
-    'subgnn_lstm_agg_group_bwd': [P, P, I, I, I, I, I, P, P, I, P],
+    'subgnn_lstm_head_fwd': [P, P, P, P, P, I, I, I, I, I, I, P],
+    'subgnn_lstm_head_bwd': [P, P, P, P, I, I, I, I, I, I, P],
     'subgnn_group_sum': [P, P, I, I, I, P],
     'subgnn_group_bcast': [P, P, I, I, I, P],
     'subgnn_dropout': [P, P, LL, F, U64, U32, P, P],

@@ -70,6 +70,25 @@ __device__ __forceinline__ float sg_dropout_scale(uint64_t seed, uint32_t salt, 
   return sg_unit(w) >= p ? 1.f / (1.f - p) : 0.f;
 }
 
+// cooperative global -> shared staging with U independent loads in flight per thread (a plain load->store loop serialises on
+// the L2 latency: the store of iteration i needs its load before the load of iteration i+1 issues)
+template <int U, class Src>
+__device__ __forceinline__ void sg_stage(float* dst, int n, Src src) {
+  for (int e0 = threadIdx.x; e0 < n; e0 += U * (int)blockDim.x) {
+    float r[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * (int)blockDim.x;
+      r[u] = e < n ? src(e) : 0.f;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int e = e0 + u * (int)blockDim.x;
+      if (e < n) dst[e] = r[u];
+    }
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

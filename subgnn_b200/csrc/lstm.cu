@@ -287,48 +287,91 @@ __global__ void group_bcast_kernel(const float* __restrict__ dEMB, float* __rest
   }
 }
 
-// Walk-group head, forward.  The head is linear and the patch embedding is the SUM of its walks' outputs
-// (anchor_patch_samplers.py:429-433), so the walks are summed first and the Linear runs on one row per patch:
-//   AGGG[g][c] = sum_{w<group} agg(OUT[g*group + w])[c],   bias_scaled[d] = group * bias[d]
-// (agg = row T-1 for 'last', SubGNN.py:83, or the sum over t for 'sum', :85).  group = 1 is the plain per-sequence head.
-__global__ void lstm_agg_group_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGGG, int n_groups, int group, int T, int H2,
-                                          int sum_mode, const float* __restrict__ bias, float* __restrict__ bias_scaled, int D) {
-  const long long total = (long long)n_groups * H2;
-  const long long tid0 = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (bias_scaled && tid0 < D) bias_scaled[tid0] = (float)group * bias[tid0];
-  for (long long e = tid0; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(e / H2), c = (int)(e % H2);
+// Walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out))).  The head
+// is linear, so the walks are summed first and the Linear runs once per patch.  One CTA per patch g:
+//   AGG[g][c] = sum_{w<group} agg(OUT[g*group + w])[c]          (agg = row T-1 for 'last', SubGNN.py:83; sum over t for 'sum', :85)
+//   EMB[g][d] = sum_c AGG[g][c] W[d][c] + group * bias[d]        (warp per output, lanes along c: coalesced weight rows)
+// group = 1 is the plain per-sequence head of LSTM.forward (SubGNN.py:76-88).
+__global__ void __launch_bounds__(512) lstm_head_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGG, float* __restrict__ EMB,
+                                                            const float* __restrict__ W, const float* __restrict__ bias, int n_groups,
+                                                            int group, int T, int H2, int D, int sum_mode) {
+  extern __shared__ float sm_head[];
+  const int g = blockIdx.x;
+  const int rows = sum_mode ? group * T : group;          // rows of OUT that are summed: every (w, t) or (w, T-1)
+  for (int c = threadIdx.x; c < H2; c += blockDim.x) {
     float v = 0.f;
-    for (int w = 0; w < group; ++w) {
-      const size_t seq = (size_t)g * group + w;
-      if (sum_mode) {
-        for (int t = 0; t < T; ++t) v += OUT[(seq * T + t) * H2 + c];
-      } else {
-        v += OUT[(seq * T + T - 1) * H2 + c];
+    for (int r0 = 0; r0 < rows; r0 += 8) {
+      float x[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        const int r = r0 + u;
+        const size_t row = sum_mode ? (size_t)g * rows + r : ((size_t)g * group + r) * T + T - 1;
+        x[u] = r < rows ? OUT[row * H2 + c] : 0.f;
       }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v += x[u];
     }
-    AGGG[e] = v;
+    sm_head[c] = v;
+    AGG[(size_t)g * H2 + c] = v;
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int d0 = warp * 4; d0 < D; d0 += nw * 4) {         // 4 outputs per warp pass: their weight rows load together
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = lane; c < H2; c += 32) {
+      const float a = sm_head[c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u)
+        if (d0 + u < D) acc[u] = fmaf(a, __ldg(W + (size_t)(d0 + u) * H2 + c), acc[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const float t = warp_sum(acc[u]);
+      if (lane == 0 && d0 + u < D) EMB[(size_t)g * D + d0 + u] = t + (float)group * bias[d0 + u];
+    }
   }
 }
 
-// Walk-group head, backward: dOUT[(g, w)][t][:] = dAGGG[g][:] for every t ('sum') or only t = T-1 ('last', zero elsewhere);
-// block 0 also accumulates the head's bias gradient  db[d] += group * sum_g dEMB[g][d].
-__global__ void lstm_agg_group_bwd_kernel(const float* __restrict__ dAGGG, float* __restrict__ dOUT, int n_groups, int group, int T, int H2,
-                                          int sum_mode, const float* __restrict__ dEMB, float* __restrict__ db, int D) {
-  const long long total = (long long)n_groups * group * T * H2;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % H2);
-    const long long st = e / H2;
-    const int t = (int)(st % T);
-    const long long seq = st / T;
-    dOUT[e] = (sum_mode || t == T - 1) ? dAGGG[(size_t)(seq / group) * H2 + c] : 0.f;
+// backward of the head for patch g: dAGG[c] = sum_d dEMB[g][d] W[d][c]; dOUT[(g, w)][t][:] = dAGG for every t ('sum') or only
+// t = T-1 ('last', zero elsewhere); db[d] += group * dEMB[g][d].  (dW = dEMB^T AGG is a separate GEMM off the critical chain.)
+__global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restrict__ dEMB, const float* __restrict__ W, float* __restrict__ dOUT,
+                                                            float* __restrict__ db, int n_groups, int group, int T, int H2, int D,
+                                                            int sum_mode) {
+  extern __shared__ float sm_head[];
+  float* dy = sm_head;          // [D]
+  float* dagg = sm_head + D;    // [H2]
+  const int g = blockIdx.x;
+  for (int d = threadIdx.x; d < D; d += blockDim.x) {
+    const float v = dEMB[(size_t)g * D + d];
+    dy[d] = v;
+    if (db && v != 0.f) atomicAdd(db + d, (float)group * v);
   }
-  if (db && blockIdx.x == 0) {
-    for (int d = threadIdx.x; d < D; d += blockDim.x) {
-      float v = 0.f;
-      for (int g = 0; g < n_groups; ++g) v += dEMB[(size_t)g * D + d];
-      atomicAdd(db + d, (float)group * v);
+  for (int c = threadIdx.x; c < H2; c += blockDim.x) dagg[c] = 0.f;
+  __syncthreads();
+  // thread (c, part): the D reduction is split over blockDim / H2 parts so that every thread has few, independent loads
+  {
+    const int parts = max(1, (int)blockDim.x / H2);
+    const int c = threadIdx.x % H2, part = threadIdx.x / H2;
+    if (part < parts) {
+      const int d_lo = (int)((long long)D * part / parts), d_hi = (int)((long long)D * (part + 1) / parts);
+      float acc = 0.f;
+#pragma unroll 16
+      for (int d = d_lo; d < d_hi; ++d) acc = fmaf(dy[d], __ldg(W + (size_t)d * H2 + c), acc);
+      if (parts == 1) dagg[c] = acc; else atomicAdd(dagg + c, acc);
     }
+    if (parts == 1)
+      for (int c2 = threadIdx.x + blockDim.x; c2 < H2; c2 += blockDim.x) {
+        float acc = 0.f;
+        for (int d = 0; d < D; ++d) acc = fmaf(dy[d], __ldg(W + (size_t)d * H2 + c2), acc);
+        dagg[c2] = acc;
+      }
+  }
+  __syncthreads();
+  const int rows = group * T;
+  float* base = dOUT + (size_t)g * rows * H2;
+  for (int e = threadIdx.x; e < rows * H2; e += blockDim.x) {
+    const int c = e % H2, t = (e / H2) % T;
+    base[e] = (sum_mode || t == T - 1) ? dagg[c] : 0.f;
   }
 }
 
@@ -481,20 +524,20 @@ int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, in
   return subgnn_check_launch("group_bcast_kernel");
 }
 
-int subgnn_lstm_agg_group_fwd(const float* OUT, float* AGGG, int n_groups, int group, int T, int H2, int sum_mode, const float* bias,
-                              float* bias_scaled, int D, void* stream) {
+int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,
+                         int D, int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  lstm_agg_group_fwd_kernel<<<sg_grid_for((long long)n_groups * H2, 128, 8), 128, 0, (cudaStream_t)stream>>>(OUT, AGGG, n_groups, group, T, H2,
-                                                                                                            sum_mode, bias, bias_scaled, D);
-  return subgnn_check_launch("lstm_agg_group_fwd_kernel");
+  lstm_head_fwd_kernel<<<n_groups, 512, (size_t)H2 * sizeof(float), (cudaStream_t)stream>>>(OUT, AGG, EMB, W, bias, n_groups, group, T, H2, D,
+                                                                                          sum_mode);
+  return subgnn_check_launch("lstm_head_fwd_kernel");
 }
 
-int subgnn_lstm_agg_group_bwd(const float* dAGGG, float* dOUT, int n_groups, int group, int T, int H2, int sum_mode, const float* dEMB,
-                              float* db, int D, void* stream) {
+int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,
+                         int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  lstm_agg_group_bwd_kernel<<<sg_grid_for((long long)n_groups * group * T * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(
-      dAGGG, dOUT, n_groups, group, T, H2, sum_mode, dEMB, db, D);
-  return subgnn_check_launch("lstm_agg_group_bwd_kernel");
+  lstm_head_bwd_kernel<<<n_groups, 512, (size_t)(H2 + D) * sizeof(float), (cudaStream_t)stream>>>(dEMB, W, dOUT, db, n_groups, group, T, H2, D,
+                                                                                                sum_mode);
+  return subgnn_check_launch("lstm_head_bwd_kernel");
 }
 
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,

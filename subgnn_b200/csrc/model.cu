@@ -238,87 +238,7 @@ __global__ void __launch_bounds__(256) q_bwd_kernel(Desc d) {
 __device__ __forceinline__ unsigned mlp_salt(const Desc& d) { return (d.step_dev ? (unsigned)*d.step_dev : d.step) * 4u; }
 
 // ------------------------------------------------------------------------------------------------
-// per-sample MLP (forward + optional backward).  zs: subgraph embedding in shared memory (hid floats);
-// work: shared scratch of at least h1 + h2 + K + h1 + h2 floats.
-__device__ void mlp_forward(const Desc& d, int b, const float* zs, float* work) {
-  float* h1s = work;
-  float* h2s = h1s + d.h1;
-  float* lg = h2s + d.h2;
-  const int tid = threadIdx.x;
-  // lin: hid is large (up to ~2k) and h1 small: split the reduction over blockDim / h1 thread groups
-  float* psum = lg + d.n_classes + 4;                       // [parts][h1] scratch (fits: see mlp_smem)
-  const int parts = d.h1 <= (int)blockDim.x ? (int)blockDim.x / d.h1 : 1;
-  if (tid < parts * d.h1) {
-    const int j = tid % d.h1, part = tid / d.h1;
-    const int i0 = (int)((long long)d.hid * part / parts), i1 = (int)((long long)d.hid * (part + 1) / parts);
-    float acc = 0.f;
-    const float* wt = d.lin_wt[0] + j;
-#pragma unroll 8
-    for (int i = i0; i < i1; ++i) acc = fmaf(zs[i], __ldg(wt + (size_t)i * d.h1), acc);
-    psum[part * d.h1 + j] = acc;
-  }
-  __syncthreads();
-  for (int j = tid; j < d.h1; j += blockDim.x) {
-    float acc = d.lin_b[0][j];
-    if (d.h1 <= (int)blockDim.x) {
-      for (int p_ = 0; p_ < parts; ++p_) acc += psum[p_ * d.h1 + j];
-    } else {
-      const float* wt = d.lin_wt[0] + j;
-      for (int i = 0; i < d.hid; ++i) acc = fmaf(zs[i], wt[(size_t)i * d.h1], acc);
-    }
-    acc = fmaxf(acc, 0.f);
-    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
-    h1s[j] = acc;
-    d.H1[(size_t)b * d.h1 + j] = acc;
-  }
-  __syncthreads();
-  for (int j = tid; j < d.h2; j += blockDim.x) {
-    float acc = d.lin_b[1][j];
-    const float* wt = d.lin_wt[1] + j;
-#pragma unroll 8
-    for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], __ldg(wt + (size_t)i * d.h2), acc);
-    acc = fmaxf(acc, 0.f);
-    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
-    h2s[j] = acc;
-    d.H2[(size_t)b * d.h2 + j] = acc;
-  }
-  __syncthreads();
-  for (int c = tid; c < d.n_classes; c += blockDim.x) {
-    float acc = d.lin_b[2][c];
-    const float* wt = d.lin_wt[2] + c;
-    for (int i = 0; i < d.h2; ++i) acc = fmaf(h2s[i], wt[(size_t)i * d.n_classes], acc);
-    lg[c] = acc;
-    d.logits[(size_t)b * d.n_classes + c] = acc;
-  }
-  __syncthreads();
-  // loss term and d logits (thread 0: K is tiny)
-  if (tid == 0) {
-    const int K = d.n_classes;
-    const int sub = d.batch_idx[b];
-    float loss = 0.f;
-    if (!d.multilabel) {
-      float mx = lg[0];
-      for (int c = 1; c < K; ++c) mx = fmaxf(mx, lg[c]);
-      float se = 0.f;
-      for (int c = 0; c < K; ++c) se += expf(lg[c] - mx);
-      const float lse = mx + logf(se);
-      const int y = d.labels ? d.labels[sub] : 0;
-      loss = (lse - lg[y]) / (float)d.B;
-      if (d.dlogits)
-        for (int c = 0; c < K; ++c) d.dlogits[(size_t)b * K + c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)d.B;
-    } else {
-      const float inv = 1.f / ((float)d.B * (float)K);
-      for (int c = 0; c < K; ++c) {
-        const float x = lg[c], y = d.labels_multi[(size_t)sub * K + c];
-        loss += (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)))) * inv;
-        if (d.dlogits) d.dlogits[(size_t)b * K + c] = (1.f / (1.f + expf(-x)) - y) * inv;
-      }
-    }
-    d.loss_b[b] = loss;
-  }
-  __syncthreads();
-}
-
+// per-sample MLP backward from external d logits (autograd path); work: shared scratch of at least K + h2 + h1 floats.
 // d logits (global) -> dH2, dH1 (pre-activation grads), dZ; dzs (shared, hid floats) receives dZ[b]
 __device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
   float* dl = work;                 // K
@@ -549,23 +469,155 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
 // 1024 threads per sample: the hid-long reductions of lin (and the hid-wide d Z) are split over 1024 / h1 thread groups so that
 // every thread's dependent load -> FMA chain is short (the 256-thread version was L2-latency bound: 87 us for 32 samples).
 #define MLP_THREADS 1024
-static size_t mlp_smem(const Desc& d) {
-  const int parts = d.h1 <= MLP_THREADS ? MLP_THREADS / d.h1 : 1;
-  return (size_t)(d.hid + 2 * (d.h1 + d.h2) + d.n_classes + 8 + parts * d.h1 + 8) * sizeof(float);
-}
-__global__ void __launch_bounds__(MLP_THREADS) mlp_kernel(Desc d) {
-  extern __shared__ float sm[];
-  float* zs = sm;
-  float* work = zs + d.hid;
-  const int b = blockIdx.x;
-  for (int i = threadIdx.x; i < d.hid; i += blockDim.x) zs[i] = d.Z[(size_t)b * d.hid + i];
-  __syncthreads();
-  mlp_forward(d, b, zs, work);
-  if (d.training && d.dZ) mlp_backward(d, b, zs, work);
-}
 __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
   extern __shared__ float sm[];
   mlp_backward(d, blockIdx.x, sm, sm + d.hid);
+}
+
+// ------------------------------------------------------------------------------------------------
+// Readout MLP as three batch-level kernels (SubGNN.py:306-310 lin -> lin2 -> lin3, subgraph_utils / loss :338-343).  The
+// per-sample kernel above reads all of W1 (hid x h1, ~0.45 MB) once PER SAMPLE in ~14 dependent L2 round trips; here W1 is
+// read once per step, K-sliced over CTAs, and every phase issues its loads together:
+//   mlp_lin1_kernel  CTA per 64-row slice of hid: H1pre[b][j] += sum_{k in slice} Z[b][k] W1t[k][j]   (H1 zeroed per step)
+//   mlp_rest_kernel  CTA per sample: bias / relu / dropout, lin2, lin3, loss, d logits, dH2, dH1       (W2 staged in smem)
+//   mlp_dz_kernel    CTA per 64-column slice of hid: dZ[b][i] = sum_j dH1[b][j] W1[j][i]
+#define MLP_SLICE 64
+__global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
+  extern __shared__ float sm[];
+  float* zs = sm;                               // [B][MLP_SLICE]
+  float* ws = sm + (size_t)d.B * MLP_SLICE;     // [MLP_SLICE][h1]
+  const int k0 = blockIdx.x * MLP_SLICE, kn = min(MLP_SLICE, d.hid - k0);
+  sg_stage<8>(zs, d.B * MLP_SLICE, [&](int e) {
+    const int b = e / MLP_SLICE, kk = e % MLP_SLICE;
+    return kk < kn ? d.Z[(size_t)b * d.hid + k0 + kk] : 0.f;
+  });
+  const float* wt = d.lin_wt[0] + (size_t)k0 * d.h1;
+  sg_stage<16>(ws, kn * d.h1, [&](int e) { return __ldg(wt + e); });
+  __syncthreads();
+  for (int o = threadIdx.x; o < d.B * d.h1; o += blockDim.x) {
+    const int b = o / d.h1, j = o % d.h1;
+    const float* zr = zs + (size_t)b * MLP_SLICE;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int kk = 0; kk < kn; ++kk) acc = fmaf(zr[kk], ws[kk * d.h1 + j], acc);
+    atomicAdd(d.H1 + o, acc);
+  }
+}
+
+__global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
+  extern __shared__ float sm[];
+  float* w1t = sm;                               // [h1][h2]  lin2 weights, input-major (forward)
+  float* w1n = w1t + (size_t)d.h1 * d.h2;        // [h2][h1]  lin2 weights, native (backward)
+  float* h1s = w1n + (size_t)d.h1 * d.h2;        // [h1]
+  float* h2s = h1s + d.h1;                       // [h2]
+  float* lg = h2s + d.h2;                        // [K]
+  float* dl = lg + d.n_classes;                  // [K]
+  float* g2 = dl + d.n_classes;                  // [h2]
+  const int b = blockIdx.x, tid = threadIdx.x, K = d.n_classes;
+  const bool bwd = d.training && d.dZ;
+  // both copies of the lin2 weights land in one staging pass (w1n directly follows w1t): 16 loads in flight per thread
+  const float* src_t = d.lin_wt[1];
+  const float* src_n = d.lin_w[1];
+  const int nw1 = d.h1 * d.h2;
+  sg_stage<16>(w1t, bwd ? 2 * nw1 : nw1, [&](int e) { return e < nw1 ? __ldg(src_t + e) : __ldg(src_n + e - nw1); });
+  for (int j = tid; j < d.h1; j += blockDim.x) {
+    float acc = fmaxf(d.H1[(size_t)b * d.h1 + j] + d.lin_b[0][j], 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
+    h1s[j] = acc;
+    d.H1[(size_t)b * d.h1 + j] = acc;
+  }
+  __syncthreads();
+  for (int j = tid; j < d.h2; j += blockDim.x) {
+    float acc = d.lin_b[1][j];
+#pragma unroll 8
+    for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], w1t[i * d.h2 + j], acc);
+    acc = fmaxf(acc, 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
+    h2s[j] = acc;
+    d.H2[(size_t)b * d.h2 + j] = acc;
+  }
+  __syncthreads();
+  {                                              // lin3: warp per class, lanes along h2
+    const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
+    for (int c = warp; c < K; c += nw) {
+      float acc = 0.f;
+      for (int i = lane; i < d.h2; i += 32) acc = fmaf(h2s[i], __ldg(d.lin_w[2] + (size_t)c * d.h2 + i), acc);
+      acc = warp_sum(acc);
+      if (lane == 0) {
+        acc += d.lin_b[2][c];
+        lg[c] = acc;
+        d.logits[(size_t)b * K + c] = acc;
+      }
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {                                // loss term and d logits (K is tiny)
+    const int sub = d.batch_idx[b];
+    float loss = 0.f;
+    if (!d.multilabel) {
+      float mx = lg[0];
+      for (int c = 1; c < K; ++c) mx = fmaxf(mx, lg[c]);
+      float se = 0.f;
+      for (int c = 0; c < K; ++c) se += expf(lg[c] - mx);
+      const float lse = mx + logf(se);
+      const int y = d.labels ? d.labels[sub] : 0;
+      loss = (lse - lg[y]) / (float)d.B;
+      for (int c = 0; c < K; ++c) {
+        dl[c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)d.B;
+        if (d.dlogits) d.dlogits[(size_t)b * K + c] = dl[c];
+      }
+    } else {
+      const float inv = 1.f / ((float)d.B * (float)K);
+      for (int c = 0; c < K; ++c) {
+        const float x = lg[c], y = d.labels_multi[(size_t)sub * K + c];
+        loss += (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)))) * inv;
+        dl[c] = (1.f / (1.f + expf(-x)) - y) * inv;
+        if (d.dlogits) d.dlogits[(size_t)b * K + c] = dl[c];
+      }
+    }
+    d.loss_b[b] = loss;
+  }
+  if (!bwd) return;
+  __syncthreads();
+  for (int j = tid; j < d.h2; j += blockDim.x) {
+    float acc = 0.f;
+    for (int c = 0; c < K; ++c) acc = fmaf(dl[c], __ldg(d.lin_w[2] + (size_t)c * d.h2 + j), acc);
+    const float sc = sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
+    acc = h2s[j] > 0.f ? acc * sc : 0.f;
+    g2[j] = acc;
+    d.dH2[(size_t)b * d.h2 + j] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < d.h1; i += blockDim.x) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < d.h2; ++j) acc = fmaf(g2[j], w1n[j * d.h1 + i], acc);
+    const float sc = sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + i, d.lin_dropout);
+    d.dH1[(size_t)b * d.h1 + i] = h1s[i] > 0.f ? acc * sc : 0.f;
+  }
+}
+
+__global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
+  extern __shared__ float sm[];
+  float* g1s = sm;                               // [B][h1]
+  float* ws = sm + (size_t)d.B * d.h1;           // [h1][MLP_SLICE]
+  const int i0 = blockIdx.x * MLP_SLICE, in = min(MLP_SLICE, d.hid - i0);
+  sg_stage<8>(g1s, d.B * d.h1, [&](int e) { return d.dH1[e]; });
+  const float* w0 = d.lin_w[0];
+  sg_stage<16>(ws, d.h1 * MLP_SLICE, [&](int e) {
+    const int j = e / MLP_SLICE, ii = e % MLP_SLICE;
+    return ii < in ? __ldg(w0 + (size_t)j * d.hid + i0 + ii) : 0.f;
+  });
+  __syncthreads();
+  for (int o = threadIdx.x; o < d.B * MLP_SLICE; o += blockDim.x) {
+    const int b = o / MLP_SLICE, ii = o % MLP_SLICE;
+    if (ii >= in) continue;
+    const float* gr = g1s + (size_t)b * d.h1;
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < d.h1; ++j) acc = fmaf(gr[j], ws[j * MLP_SLICE + ii], acc);
+    d.dZ[(size_t)b * d.hid + i0 + ii] = acc;
+  }
 }
 
 template <int DPL>
@@ -742,7 +794,10 @@ static int check_desc(const Desc* d) {
   if (!d) { subgnn_set_error("null descriptor"); return SUBGNN_ERR_ARG; }
   if (d->D < 1 || d->D > 32 * MAXDPL) { subgnn_set_error("node_embed_size must be in [1, %d]", 32 * MAXDPL); return SUBGNN_ERR_ARG; }
   if (d->B < 1 || d->L < 1) { subgnn_set_error("bad batch / layer count"); return SUBGNN_ERR_ARG; }
-  if (mlp_smem(*d) > 200 * 1024) { subgnn_set_error("hidden dimension too large for shared memory"); return SUBGNN_ERR_ARG; }
+  if ((size_t)(d->hid + d->h1 + d->h2 + d->n_classes + 8) * sizeof(float) > 200 * 1024) {
+    subgnn_set_error("hidden dimension too large for shared memory");
+    return SUBGNN_ERR_ARG;
+  }
   return SUBGNN_OK;
 }
 
@@ -809,13 +864,30 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) 
   return subgnn_check_launch("row_fwd_kernel");
 }
 
+// requires d->H1 zeroed on entry (it is the split-K accumulation target of the first layer)
 int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  const size_t ms = mlp_smem(*d);
-  if (ms > 48 * 1024) cudaFuncSetAttribute(mlp_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ms);
-  mlp_kernel<<<d->B, MLP_THREADS, ms, (cudaStream_t)stream>>>(*d);
-  return subgnn_check_launch("mlp_kernel");
+  cudaStream_t st = (cudaStream_t)stream;
+  const int slices = sg_div_up(d->hid, MLP_SLICE);
+  const size_t s1 = (size_t)(d->B * MLP_SLICE + MLP_SLICE * d->h1) * sizeof(float);
+  const size_t s2 = (size_t)(2 * d->h1 * d->h2 + d->h1 + 2 * d->h2 + 2 * d->n_classes + 8) * sizeof(float);
+  const size_t s3 = (size_t)(d->B * d->h1 + d->h1 * MLP_SLICE) * sizeof(float);
+  if (s1 > 200 * 1024 || s2 > 200 * 1024 || s3 > 200 * 1024) { subgnn_set_error("MLP dimensions too large for shared memory"); return SUBGNN_ERR_ARG; }
+  if (s1 > 48 * 1024) cudaFuncSetAttribute(mlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
+  if (s2 > 48 * 1024) cudaFuncSetAttribute(mlp_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
+  if (s3 > 48 * 1024) cudaFuncSetAttribute(mlp_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
+  mlp_lin1_kernel<<<slices, 256, s1, st>>>(*d);
+  rc = subgnn_check_launch("mlp_lin1_kernel");
+  if (rc) return rc;
+  mlp_rest_kernel<<<d->B, 256, s2, st>>>(*d);
+  rc = subgnn_check_launch("mlp_rest_kernel");
+  if (rc) return rc;
+  if (d->training && d->dZ) {
+    mlp_dz_kernel<<<slices, 256, s3, st>>>(*d);
+    rc = subgnn_check_launch("mlp_dz_kernel");
+  }
+  return rc;
 }
 
 int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {

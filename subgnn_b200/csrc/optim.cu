@@ -52,15 +52,24 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
   const float bc2 = 1.f - powf(beta2, (float)t);
   const float step_size = lr / bc1;
   const float inv_sqrt_bc2 = 1.f / sqrtf(bc2);
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-    const float gi = g[i] * coef;
-    const float mi = beta1 * m[i] + (1.f - beta1) * gi;
-    const float vi = beta2 * v[i] + (1.f - beta2) * gi * gi;
-    m[i] = mi;
-    v[i] = vi;
+  auto upd = [&](float gi_raw, float& pi, float& mi_, float& vi_) {
+    const float gi = gi_raw * coef;
+    const float mi = beta1 * mi_ + (1.f - beta1) * gi;
+    const float vi = beta2 * vi_ + (1.f - beta2) * gi * gi;
+    mi_ = mi;
+    vi_ = vi;
     const float denom = sqrtf(vi) * inv_sqrt_bc2 + eps;
-    p[i] -= step_size * (mi / denom);
+    pi -= step_size * (mi / denom);
+  };
+  const long long n4 = n >> 2;                    // the arenas are 16-byte aligned (checked by the host wrapper)
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+    const float4 g4 = reinterpret_cast<const float4*>(g)[i];
+    float4 p4 = reinterpret_cast<float4*>(p)[i], m4 = reinterpret_cast<float4*>(m)[i], v4 = reinterpret_cast<float4*>(v)[i];
+    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
+    reinterpret_cast<float4*>(p)[i] = p4; reinterpret_cast<float4*>(m)[i] = m4; reinterpret_cast<float4*>(v)[i] = v4;
   }
+  for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    upd(g[i], p[i], m[i], v[i]);
 }
 
 __global__ void sum_to_scalar_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
@@ -99,7 +108,8 @@ int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq, void* strea
 int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                      const int* step_dev, const float* sumsq_dev, float clip_norm, float grad_scale, void* stream) {
   if (n <= 0) return SUBGNN_OK;
-  adam_kernel<<<sg_grid_for(n, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, sumsq_dev, clip_norm,
+  SG_REQUIRE((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0, "buffers must be 16-byte aligned");
+  adam_kernel<<<sg_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, sumsq_dev, clip_norm,
                                                                         grad_scale);
   return subgnn_check_launch("adam_kernel");
 }

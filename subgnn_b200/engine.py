@@ -220,8 +220,7 @@ class LstmRunner:
         self.whh_t = [z(2 * H * 4 * H) for _ in range(self.nl)]
         self.bsum = [z(8 * H) for _ in range(self.nl)]
         # head: the walks of a patch are summed BEFORE the (linear) head, so it runs on one row per patch (n_groups rows)
-        self.AGG, self.dAGG = z(n_groups, 2 * H), z(n_groups, 2 * H)
-        self.bias_scaled = z(self.D)
+        self.AGG = z(n_groups, 2 * H)
         self.EMB, self.dEMB = z(n_groups, self.D), z(n_groups, self.D)
         self._aux = None
         t = torch.arange(M, device=self.dev, dtype=torch.int64)
@@ -278,10 +277,8 @@ class LstmRunner:
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
                 cur.wait_stream(aux[0])
             call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
-        call('subgnn_lstm_agg_group_fwd', ptr(self.OUT[-1]), ptr(self.AGG), self.n_groups, self.W, T, 2 * H, self.sum_mode,
-             a.addr('lstm.linear.bias'), ptr(self.bias_scaled), D, st)
-        call('subgnn_linear_fwd', ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight'), 2 * H, ptr(self.bias_scaled),
-             ptr(self.EMB), D, self.n_groups, D, 2 * H, 0, st)
+        call('subgnn_lstm_head_fwd', ptr(self.OUT[-1]), ptr(self.AGG), ptr(self.EMB), a.addr('lstm.linear.weight'), a.addr('lstm.linear.bias'),
+             self.n_groups, self.W, T, 2 * H, D, self.sum_mode, st)
 
     def _wgrad(self, dy, ldy, x, ldx, ids, dw, lddw, db, M, N, K, st):
         if self.use_tc and M >= 256:
@@ -323,10 +320,8 @@ class LstmRunner:
         with torch.cuda.stream(aux[1]):
             call('subgnn_linear_bwd_weight', ptr(self.dEMB), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
                  None, self.n_groups, D, 2 * H, None, aux[1].cuda_stream)
-        call('subgnn_linear_bwd_input', ptr(self.dEMB), D, a.addr('lstm.linear.weight'), 2 * H, ptr(self.dAGG), 2 * H, None, self.n_groups, D,
-             2 * H, 0, st)
-        call('subgnn_lstm_agg_group_bwd', ptr(self.dAGG), ptr(self.dOUT[-1]), self.n_groups, self.W, T, 2 * H, self.sum_mode,
-             ptr(self.dEMB), a.addr('lstm.linear.bias', g), D, st)
+        call('subgnn_lstm_head_bwd', ptr(self.dEMB), a.addr('lstm.linear.weight'), ptr(self.dOUT[-1]), a.addr('lstm.linear.bias', g),
+             self.n_groups, self.W, T, 2 * H, D, self.sum_mode, st)
         for k in range(self.nl - 1, -1, -1):
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
@@ -398,7 +393,7 @@ class StepContext:
         A_pi, A_pb, A_s = eng.A['pi'], eng.A['pb'], eng.A['s']
         # gradient-side scratch that must start at zero every step lives in ONE buffer (single fill)
         n_dq = L * (B * A_pi + A_pb + 2 * A_s)
-        self.zero_scratch = z(_align(n_dq) + 8)
+        self.zero_scratch = z(_align(n_dq) + 8 + _align(B * hid) + _align(B * h1))
         self.dq_pi = self.zero_scratch[:L * B * A_pi]
         self.dq_pb = self.zero_scratch[L * B * A_pi:L * B * A_pi + L * A_pb]
         self.dq_s = self.zero_scratch[L * (B * A_pi + A_pb):n_dq]
@@ -409,7 +404,12 @@ class StepContext:
         self.X0 = z(self.R_cap, D)
         nN = L if hp['use_neighborhood'] else 0
         self.Nh, self.Nagg, self.Ndpre = z((nN + 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D), z(max(nN, 1) * 2 * self.R_cap * D)
-        self.Z, self.H1, self.H2, self.logits, self.loss_b = z(_align(B * hid)), z(B, h1), z(B, h2), z(B, K), z(B)   # Z: atomic readout target, zeroed per step
+        # Z (atomic readout target) and H1 (split-K target of the first MLP layer) are zeroed per step with the scratch
+        self.grad_zero = self.zero_scratch[:_align(n_dq) + 8]
+        self.fwd_zero = self.zero_scratch[_align(n_dq) + 8:]
+        self.Z = self.fwd_zero[:_align(B * hid)]
+        self.H1 = self.fwd_zero[_align(B * hid):_align(B * hid) + B * h1].view(B, h1)
+        self.H2, self.logits, self.loss_b = z(B, h2), z(B, K), z(B)
         self.dlogits, self.dH2, self.dH1, self.dZ = z(B, K), z(B, h2), z(B, h1), z(B, hid)
         self.loss = z(1)
         d = ModelDesc()
@@ -609,16 +609,19 @@ class Engine:
             self._side = torch.cuda.Stream(device=self.device)
         return self._side
 
-    def _forward_launches(self, c, st):
+    def _forward_launches(self, c, st, zero_grads=False):
         main = torch.cuda.current_stream()
-        call('subgnn_fill_zero', ptr(c.Z), c.Z.numel(), st)
         fork = self.lstm is not None and self.concurrent
-        if fork:
+        if fork:                                  # the LSTM chain is the longest of the step: it starts before the zero fills
             side = self._side_stream()
             side.wait_stream(main)
             with torch.cuda.stream(side):
                 self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
-        elif self.lstm is not None:
+        if zero_grads:
+            self.zero_grads(c, st, include_fwd=True)
+        else:
+            call('subgnn_fill_zero', ptr(c.fwd_zero), c.fwd_zero.numel(), st)
+        if self.lstm is not None and not fork:
             self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
         call('subgnn_model_prep_batch', c.dptr, st)
         call('subgnn_model_prep_weights', c.dptr, st)
@@ -650,9 +653,12 @@ class Engine:
         if fork:
             main.wait_stream(side)
 
-    def zero_grads(self, c, st):
+    def zero_grads(self, c, st, include_fwd=False):
+        """gradient arena + gradient-side scratch; include_fwd also clears the forward accumulation targets (Z, H1) that share
+        the scratch buffer — only valid BEFORE the forward pass (the backward pass reads both)."""
         call('subgnn_fill_zero', ptr(self.arena.grads), self.arena.size, st)
-        call('subgnn_fill_zero', ptr(c.zero_scratch), c.zero_scratch.numel(), st)
+        z = c.zero_scratch if include_fwd else c.grad_zero
+        call('subgnn_fill_zero', ptr(z), z.numel(), st)
 
     def _optimizer_launches(self, c, st):
         a = self.arena
@@ -723,8 +729,7 @@ class Engine:
 
     def _grad_launches(self, c, st):
         call('subgnn_inc_step', ptr(self.step_dev), st)
-        self.zero_grads(c, st)
-        self._forward_launches(c, st)
+        self._forward_launches(c, st, zero_grads=True)
         self._backward_launches(c, st)
 
     def _step_launches(self, c, st):
