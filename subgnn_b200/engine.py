@@ -245,7 +245,7 @@ class LstmRunner:
     # under graph capture they become parallel branches of the step graph.
     def _aux_streams(self):
         if self._aux is None:
-            self._aux = [torch.cuda.Stream(device=self.dev), torch.cuda.Stream(device=self.dev)]
+            self._aux = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
         return self._aux
 
     def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None):
@@ -335,19 +335,18 @@ class LstmRunner:
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
             # ---- weight gradients: off the critical chain ----
-            aux[0].wait_stream(cur)
-            aux[1].wait_stream(cur)
+            for a_ in aux:
+                a_.wait_stream(cur)
             with torch.cuda.stream(aux[0]):
                 s0 = aux[0].cuda_stream
                 self._wgrad(dG, 8 * H, x_ptr, ldx, ids, gw_ih, din, None, M, n_out, din, s0)
                 if not full:
                     xl, ldxl, idsl = self._last_rows(k, x_ptr, ldx, ids)
                     self._wgrad(dG_last, T * 8 * H, xl, ldxl, idsl, gw_ih + 4 * (4 * H * din), din, None, self.n_seq, 4 * H, din, s0)
-            with torch.cuda.stream(aux[1]):
-                s1 = aux[1].cuda_stream
-                for d_ in range(2 if full else 1):                 # reverse direction took one step from h = 0: no W_hh gradient
+            for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
+                with torch.cuda.stream(aux[1 + d_]):
                     self._wgrad(dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H, ptr(self.hprev[d_]),
-                                a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, s1)
+                                a.base_addr(o['weight_hh'], g) + 4 * (d_ * 4 * H * H), H, None, M, 4 * H, H, aux[1 + d_].cuda_stream)
             # ---- input gradient: the chain ----
             if k > 0:
                 dx_ptr, lddx, scat = ptr(self.dOUT[k - 1]), 2 * H, None
@@ -370,8 +369,8 @@ class LstmRunner:
                          None, self.n_seq, 4 * H, din, 1, st)
             if k > 0 and self.p_drop > 0 and training:
                 call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
-        cur.wait_stream(aux[0])
-        cur.wait_stream(aux[1])
+        for a_ in aux:
+            cur.wait_stream(a_)
 
 
 # ------------------------------------------------------------------------------------------------------
