@@ -182,6 +182,27 @@ def measured_peaks():
     return {'hbm': 6650.0, 'tensor': 1590.0, 'tensor_sustained': 1400.0, 'src': 'fallback'}
 
 
+# entry point -> CUDA kernel(s) it launches, for the ncu traffic table (tools/ncu_traffic.py -> profiles/r01_traffic_<workload>.json)
+ENTRY_KERNELS = {'subgnn_tc_linear_bwd_weight': ['tc_linear_bwd_weight_kernel'], 'subgnn_tc_linear_fwd': ['tc_linear_fwd_kernel'],
+                 'subgnn_tc_linear_bwd_input': ['tc_linear_bwd_input_kernel'], 'subgnn_lstm_recur_fwd': ['lstm_fwd_tile_kernel'],
+                 'subgnn_lstm_recur_bwd': ['lstm_bwd_tile_kernel'], 'subgnn_model_rows_fwd': ['row_fwd_kernel'],
+                 'subgnn_model_rows_bwd': ['row_bwd_kernel'], 'subgnn_adam_step': ['adam_kernel'], 'subgnn_grad_sumsq': ['sumsq_kernel'],
+                 'subgnn_fill_zero': ['fill_zero_kernel']}
+
+
+def ncu_traffic(workload, entry):
+    """mean DRAM bytes per launch of the entry point's kernel from the committed ncu --set full capture of this workload, or None."""
+    f = ROOT / 'profiles' / ('r01_traffic_%s.json' % workload)
+    if not f.exists() or entry not in ENTRY_KERNELS:
+        return None, None
+    tab = json.loads(f.read_text())
+    ks = [tab['kernels'][k] for k in ENTRY_KERNELS[entry] if k in tab['kernels']]
+    if not ks:
+        return None, None
+    n = sum(k['launches_per_step'] for k in ks)
+    return sum(k['dram_bytes_per_launch'] * k['launches_per_step'] for k in ks) / n, 'profiles/%s (%s)' % (f.name, tab.get('source', ''))
+
+
 # fp32 FFMA issue peak of the part (not in MEASURED_PEAKS.json): 148 SMs x 128 lanes x 2 flop x 1.965 GHz
 FP32_FFMA_TFLOPS = 148 * 128 * 2 * 1.965e9 / 1e12
 
@@ -418,6 +439,16 @@ def main():
                 'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': ach / FP32_FFMA_TFLOPS,
                 'note': 'sequential fp32 FFMA matvec chain (T dependent steps of n_seq x 4H x H), not a tensor-core shape: the relevant ceiling '
                         'is the nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz), reported beside the contract\'s bf16 peak'}
+
+    _roof = roof
+
+    def roof(name):
+        r = _roof(name)
+        if r is not None:
+            r['traffic'], src = ncu_traffic(args.workload, name)
+            if src:
+                r['traffic_source'] = src + ': dram__bytes_read.sum + dram__bytes_write.sum per launch, cold caches (upper bound for the in-graph launch)'
+        return r
 
     ranked = sorted(per_entry, key=lambda k: -per_entry[k][0])
     roofline = next((r for r in (roof(k) for k in ranked) if r), None)

@@ -21,6 +21,7 @@
 #include "common.cuh"
 #include "../../include/subgnn_b200.h"
 #include "lstm_reg.cuh"
+#include <cstdlib>
 
 namespace {
 
@@ -367,21 +368,25 @@ int pick_tile(int n_seq, int cl, int threads_per_4seq, size_t smem_fixed, size_t
   const int sms = subgnn_sm_count();
   int best = -1;
   long long best_cost = -1;
+  int forced = 0;
+  if (const char* e = getenv("SUBGNN_LSTM_TILE")) forced = atoi(e);     // tuning aid (tools/lstm_bench.py)
   for (int tile = 4; tile <= 32; tile += 4) {
+    if (forced > 0 && tile != forced) continue;
     const size_t smem = smem_fixed + smem_per_seq * tile;
     if (smem > 220 * 1024) continue;
     const int threads = threads_per_4seq * (tile / 4);
     if (threads > 512) continue;
     int occ = (int)((220 * 1024) / smem);
+    const int occ_regs = 65536 / (threads * 128);           // both kernels compile to ~128 registers per thread
+    if (occ > occ_regs) occ = occ_regs;
     if (occ < 1) occ = 1;
     if (occ > 4) occ = 4;
     const long long ctas = 2LL * sg_div_up(n_seq, tile) * cl;
     const long long waves = (ctas + (long long)sms * occ - 1) / ((long long)sms * occ);
-    long long resident = (ctas + sms - 1) / sms;
-    if (resident > occ) resident = occ;
-    // time ~ waves x (per-step latency floor + issue time of the warps that share a sub-partition)
-    const long long warps = resident * ((threads + 31) / 32);
-    const long long cost = waves * (4 + (warps + 3) / 4) * 100 + (32 - tile);
+    // measured (tools/lstm_bench.py, B200): a step costs ~ fixed + c * tile per resident CTA and the CTAs of a wave run side
+    // by side, so the fewest waves win and, among those, the smallest tile (most SMs busy): e.g. H = 128, 720 sequences:
+    // tile 20 (144 CTAs) 9.0 us/step, 24 (120 CTAs) 9.6, 28 (104) 10.9, 16 (180 CTAs, two waves) 13.8
+    const long long cost = waves * 1000 + tile;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tile; }
   }
   return best;

@@ -192,3 +192,24 @@ def test_train_config_style_driver_on_the_stand_ins(tmp_path, fused):
         assert {'test_micro_f1', 'test_acc', 'test_auroc'} <= set(fresh.test_results)
     rows = [json.loads(l) for l in open(os.path.join(run_config['models'][0][2], 'metrics.jsonl'))]
     assert sum('val_micro_f1' in r for r in rows) == 4
+
+
+def test_resample_anchor_patches_each_epoch(tmp_path):
+    """SubGNN.py:449-457: with resample_anchor_patches the N / P / S anchors are redrawn at validation_epoch_end (patches, walks,
+    border sets and similarities are kept); parameters and optimizer state carry over and training continues."""
+    root = _copy_task(tmp_path)
+    m = _model(root, resample_anchor_patches=True)
+    before = {k: np.array(v) for k, v in m.engine.prepared['anchors_neigh_int']['train'].items()}
+    pos_before = np.array(m.engine.prepared['anchors_pos_ext'][0])
+    sims_before = np.array(m.engine.prepared['I_S_sim']['train'])
+    w_before = m.state_dict()['lin.weight'].clone()
+    losses = []
+    for epoch in range(3):
+        losses.append(np.mean([float(m.training_step_fused(b)['loss']) for b in m.train_dataloader()]))
+        res = m.validation_epoch_end([m.validation_step(b, i) for i, b in enumerate(m.val_dataloader())])
+        assert np.isfinite(float(res['log']['val_loss']))
+    after = m.engine.prepared['anchors_neigh_int']['train']
+    assert any(not np.array_equal(before[l], after[l]) for l in before) and not np.array_equal(pos_before, m.engine.prepared['anchors_pos_ext'][0])
+    assert np.array_equal(sims_before, m.engine.prepared['I_S_sim']['train'])
+    assert not torch.equal(w_before, m.state_dict()['lin.weight']) and int(m.engine.step_dev.item()) == 3 * len(m.train_dataloader())
+    assert losses[-1] < losses[0] and len(m.metric_scores) == 3
