@@ -166,11 +166,19 @@ def algorithmic_work(eng, ctx):
             rows_dir[-1][1] = ls.n_seq
         flops_proj = sum(2 * (rows_dir[k][0] + rows_dir[k][1]) * 4 * H * (D if k == 0 else 2 * H) for k in range(ls.nl))
         flops_rec = sum(2 * (rows_dir[k][0] + rows_dir[k][1]) * 4 * H * H for k in range(ls.nl))
-        work['subgnn_tc_linear_fwd'] = ('tensor', flops_proj)
-        work['subgnn_tc_linear_bwd_weight'] = ('tensor', flops_proj + flops_rec)         # d W_ih and d W_hh
-        work['subgnn_tc_linear_bwd_input'] = ('tensor', flops_proj)
-        work['subgnn_lstm_recur_fwd'] = ('fp32', flops_rec)
-        work['subgnn_lstm_recur_bwd'] = ('fp32', flops_rec)
+        # algorithmic bytes of the same launches (every operand read once, every result written once, fp32): the GEMMs have
+        # K <= 2H <= 256, i.e. an arithmetic intensity of N K / (2 (N + K)) ~ 28-60 flop/B, far below the ridge of the part
+        # (measured tensor peak / measured HBM peak ~ 210 flop/B): by the roofline they are HBM-bound, not tensor-bound
+        rows_all = sum(rows_dir[k][0] + rows_dir[k][1] for k in range(ls.nl))
+        b_proj = sum(4 * (M * (D if k == 0 else 2 * H) + (rows_dir[k][0] + rows_dir[k][1]) * 4 * H + 8 * H * (D if k == 0 else 2 * H)) for k in range(ls.nl))
+        b_whh = 4 * (rows_all * (4 * H + H) + ls.nl * 8 * H * H)
+        b_rec_f = 4 * rows_all * (4 * H + 4 * H + H + H) + 4 * ls.nl * 8 * H * H          # G in, gates out, c, h; W_hh once
+        b_rec_b = 4 * rows_all * (4 * H + 4 * H + 2 * H + 2 * H) + 4 * ls.nl * 8 * H * H  # gates, dG out, c_t / c_{t-1}, h / dh
+        work['subgnn_tc_linear_fwd'] = ('gemm', flops_proj, b_proj)
+        work['subgnn_tc_linear_bwd_weight'] = ('gemm', flops_proj + flops_rec, b_proj + b_whh)   # d W_ih and d W_hh
+        work['subgnn_tc_linear_bwd_input'] = ('gemm', flops_proj, b_proj)
+        work['subgnn_lstm_recur_fwd'] = ('fp32', flops_rec, b_rec_f)
+        work['subgnn_lstm_recur_bwd'] = ('fp32', flops_rec, b_rec_b)
     return work, {'rows': R, 'component_nodes': n_nodes}
 
 
@@ -419,7 +427,7 @@ def main():
         if name not in work or name not in per_entry:
             return None
         ms, calls = per_entry[name]
-        bound, amount = work[name]
+        bound, amount = work[name][0], work[name][1]
         per_launch_s = ms * 1e-3 / calls
         amount_launch = amount / calls
         if bound == 'hbm':
@@ -427,18 +435,25 @@ def main():
             return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'],
                     'traffic': None, 'algorithmic_bytes_per_launch': amount_launch, 'launches_per_step': calls,
                     'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
-        ach = amount_launch / per_launch_s / 1e12
-        if bound == 'tensor':
-            return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
-                    'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount_launch,
-                    'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
-                    'note': 'tcgen05 kind::tf32 with 3xTF32 error compensation (3 MMAs per algorithmic product) measured against the bf16 tensor peak'}
-        return {'kernel': name, 'bound': 'tensor', 'achieved': ach, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s',
-                'frac': ach / peaks['tensor_sustained'], 'traffic': None, 'algorithmic_flops_per_launch': amount_launch,
-                'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
-                'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': ach / FP32_FFMA_TFLOPS,
-                'note': 'sequential fp32 FFMA matvec chain (T dependent steps of n_seq x 4H x H), not a tensor-core shape: the relevant ceiling '
-                        'is the nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz), reported beside the contract\'s bf16 peak'}
+        # GEMM-shaped entries: the roofline bound follows from the arithmetic intensity against the ridge of the measured peaks
+        flops_launch, bytes_launch = amount_launch, work[name][2] / calls
+        ai, ridge = flops_launch / bytes_launch, peaks['tensor_sustained'] * 1e12 / (peaks['hbm'] * 1e9)
+        tf, gbs = flops_launch / per_launch_s / 1e12, bytes_launch / per_launch_s / 1e9
+        common = {'kernel': name, 'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
+                  'algorithmic_flops_per_launch': flops_launch, 'algorithmic_bytes_per_launch': bytes_launch,
+                  'arithmetic_intensity_flop_per_byte': ai, 'ridge_flop_per_byte': ridge, 'traffic': None,
+                  'achieved_tflops': tf, 'frac_of_tensor_peak': tf / peaks['tensor_sustained'], 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm']}
+        if bound == 'fp32':
+            common.update({'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': tf / FP32_FFMA_TFLOPS,
+                           'note': 'T dependent steps of an (n_seq x H)(H x 4H) fp32 FFMA product + 5H activations per sequence; latency bound: the '
+                                   'nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz) is reported beside the two contract peaks'})
+        else:
+            common['note'] = 'tcgen05 kind::tf32, 3xTF32 error compensation (3 MMAs per algorithmic product), accumulator in TMEM'
+        if ai < ridge:
+            common.update({'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm']})
+        else:
+            common.update({'bound': 'tensor', 'achieved': tf, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tensor_sustained']})
+        return common
 
     _roof = roof
 
