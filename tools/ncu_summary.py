@@ -8,7 +8,8 @@ WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'sm__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__warps_active.avg.pct_of_peak_sustained_active',
         'smsp__issue_active.avg.pct_of_peak_sustained_active', 'sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active',
         'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active', 'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct',
-        'l1tex__average_t_sectors_per_request_pipe_lsu_mem_global_op_ld.ratio', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
+        'smsp__sass_average_data_bytes_per_sector_mem_global_op_ld.ratio', 'smsp__sass_average_data_bytes_per_sector_mem_global_op_st.ratio',
+        'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio',
         'smsp__average_warps_issue_stalled_barrier_per_issue_active.ratio', 'launch__registers_per_thread', 'launch__grid_size', 'launch__block_size',
         'launch__waves_per_multiprocessor', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
         'sm__maximum_warps_per_active_cycle_pct']
