@@ -53,6 +53,17 @@ template <int CL>
 __device__ __forceinline__ void step_sync() {
   if (CL > 1) cluster_sync_all(); else __syncthreads();
 }
+// split form: everything written to (distributed) shared memory before step_arrive is visible to the cluster after step_wait.
+// The release fence of the arrive waits for the thread's outstanding stores, so fire-and-forget GLOBAL stores of a step are
+// issued between the two (profiles/r01_ncu_lstm_h128.txt: MEMBAR + ERRBAR of the arrive were ~8 % of the samples).
+template <int CL>
+__device__ __forceinline__ void step_arrive() {
+  if (CL > 1) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+}
+template <int CL>
+__device__ __forceinline__ void step_wait() {
+  if (CL > 1) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); else __syncthreads();
+}
 
 // 1-D TMA bulk copies global -> shared completing on one mbarrier (SASS UBLKCP); issued by one thread.
 __device__ __forceinline__ void bulk_begin(uint64_t* bar, uint32_t total_bytes) {
@@ -171,6 +182,7 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
     }
     __syncthreads();
     float* hnxt = hS + (size_t)(cur ^ 1) * tile * H;
+    float2 gate_i[NF], gate_f[NF], gate_g[NF], gate_o[NF], h_new[NF];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int s = s0 + ks + f * KS;
@@ -192,22 +204,30 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
         c[f].x = fmaf(af.x, c[f].x, ai.x * ag.x);
         c[f].y = fmaf(af.y, c[f].y, ai.y * ag.y);
         hn = make_float2(ao.x * tanh_fast(c[f].x), ao.y * tanh_fast(c[f].y));
-        const size_t row = (size_t)(seq0 + s) * T + t;
-        float* gr = G + (row * 2 + dir) * H4 + unit0;
-        *reinterpret_cast<float2*>(gr) = ai;
-        *reinterpret_cast<float2*>(gr + H) = af;
-        *reinterpret_cast<float2*>(gr + 2 * H) = ag;
-        *reinterpret_cast<float2*>(gr + 3 * H) = ao;
-        *reinterpret_cast<float2*>(CS + (row * 2 + dir) * H + unit0) = c[f];
-        *reinterpret_cast<float2*>(OUT + row * 2 * H + dir * H + unit0) = hn;
       }
       if (CL == 1) *reinterpret_cast<float2*>(hnxt + (size_t)s * H + unit0) = hn;      // rows s >= ns stay zero
       else {
 #pragma unroll
         for (unsigned r = 0; r < (unsigned)CL; ++r) st_cluster_v2(hnxt + (size_t)s * H + unit0, r, hn);
       }
+      gate_i[f] = ai; gate_f[f] = af; gate_g[f] = ag; gate_o[f] = ao; h_new[f] = hn;
     }
-    step_sync<CL>();
+    step_arrive<CL>();
+#pragma unroll
+    for (int f = 0; f < NF; ++f) {
+      const int s = s0 + ks + f * KS;
+      if (s < ns) {
+        const size_t row = (size_t)(seq0 + s) * T + t;
+        float* gr = G + (row * 2 + dir) * H4 + unit0;
+        *reinterpret_cast<float2*>(gr) = gate_i[f];
+        *reinterpret_cast<float2*>(gr + H) = gate_f[f];
+        *reinterpret_cast<float2*>(gr + 2 * H) = gate_g[f];
+        *reinterpret_cast<float2*>(gr + 3 * H) = gate_o[f];
+        *reinterpret_cast<float2*>(CS + (row * 2 + dir) * H + unit0) = c[f];
+        *reinterpret_cast<float2*>(OUT + row * 2 * H + dir * H + unit0) = h_new[f];
+      }
+    }
+    step_wait<CL>();
     cur ^= 1;
   }
   // steps not taken (top-layer reverse direction with the 'last' aggregator): outputs are never read
