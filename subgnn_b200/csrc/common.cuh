@@ -31,6 +31,38 @@ static inline int sg_grid_for(long long work_items, int per_block, int max_block
 }
 
 // ---------------------------------------------------------------------------------------------
+// Programmatic dependent launch (PDL).  The training step is a chain of ~25 dependent launches of a few microseconds each, so
+// the launch / scheduling gap between two of them is a visible share of the step.  Every kernel of the step starts with
+// sg_pdl_sync(): griddepcontrol.wait returns once ALL prerequisite grids have completed and flushed (full dependency, so the
+// kernel body is unchanged), then griddepcontrol.launch_dependents lets the next launch in stream order be scheduled while this
+// grid runs.  Kernels are launched through sg_launch_pdl, which sets cudaLaunchAttributeProgrammaticStreamSerialization (also
+// honoured by stream capture: the step graph gets programmatic edges).  Triggering only after the wait keeps completion
+// transitive along a stream (C waits for B, B passed its wait only after A completed).  SUBGNN_B200_PDL=0 disables the
+// attribute; the two instructions are no-ops for a normally launched kernel.
+__device__ __forceinline__ void sg_pdl_sync() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// kernel classes for the SUBGNN_B200_PDL bit mask (bit = class): small element-wise / per-patch kernels, tensor-core GEMMs,
+// LSTM recurrences, row (component) kernels
+enum { SG_PDL_SMALL = 0, SG_PDL_GEMM = 1, SG_PDL_RECUR = 2, SG_PDL_ROW = 3 };
+int subgnn_pdl_enabled(int kernel_class);
+template <int CLASS = SG_PDL_SMALL, class... KArgs, class... Args>
+static inline void sg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(CLASS);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+// ---------------------------------------------------------------------------------------------
 // Philox4x32-10 (counter-based); identical construction in oracle/rng.py
 struct Philox4 { uint32_t x, y, z, w; };
 

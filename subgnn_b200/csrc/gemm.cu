@@ -57,6 +57,7 @@ __global__ void __launch_bounds__(256)
 linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
                          float* __restrict__ dw, int lddw, float* __restrict__ db, int M, int N, int K, int m_chunk,
                          const int* __restrict__ m_dev) {
+  sg_pdl_sync();
   if (m_dev) M = min(M, *m_dev);
   const int m_beg = blockIdx.z * m_chunk;
   const int m_end = min(M, m_beg + m_chunk);
@@ -121,7 +122,7 @@ int subgnn_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, 
   const int m_chunk = sg_div_up(sg_div_up(M, splits), BK) * BK;
   splits = sg_div_up(M, m_chunk);
   dim3 grid(sg_div_up(K, BN), sg_div_up(N, BM), splits);
-  linear_bwd_weight_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, db, M, N, K, m_chunk, m_dev);
+  sg_launch_pdl(linear_bwd_weight_kernel, grid, dim3(256), 0, (cudaStream_t)stream, dy, ldy, x, ldx, gather_ids, dw, lddw, db, M, N, K, m_chunk, m_dev);
   return subgnn_check_launch("linear_bwd_weight_kernel");
 }
 

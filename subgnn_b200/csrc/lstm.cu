@@ -295,6 +295,7 @@ __global__ void group_bcast_kernel(const float* __restrict__ dEMB, float* __rest
 __global__ void __launch_bounds__(512) lstm_head_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGG, float* __restrict__ EMB,
                                                             const float* __restrict__ W, const float* __restrict__ bias, int n_groups,
                                                             int group, int T, int H2, int D, int sum_mode) {
+  sg_pdl_sync();
   extern __shared__ float sm_head[];
   const int g = blockIdx.x;
   const int rows = sum_mode ? group * T : group;          // rows of OUT that are summed: every (w, t) or (w, T-1)
@@ -337,6 +338,7 @@ __global__ void __launch_bounds__(512) lstm_head_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restrict__ dEMB, const float* __restrict__ W, float* __restrict__ dOUT,
                                                             float* __restrict__ db, int n_groups, int group, int T, int H2, int D,
                                                             int sum_mode) {
+  sg_pdl_sync();
   extern __shared__ float sm_head[];
   float* dy = sm_head;          // [D]
   float* dagg = sm_head + D;    // [H2]
@@ -379,6 +381,7 @@ __global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restr
 // to gradients.  Counter-based mask: element index within the buffer, salt = layer / step counter.
 __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ y, long long n, float p, unsigned long long seed,
                                unsigned salt, const int* __restrict__ step_dev) {
+  sg_pdl_sync();
   if (step_dev) salt += 64u * (unsigned)*step_dev + 0x80000000u;
   // one Philox4x32 draw serves the four elements 4q .. 4q+3 (sg_dropout_scale uses word (idx & 3) of draw idx >> 2)
   const float keep = p > 0.f ? 1.f / (1.f - p) : 1.f;
@@ -405,6 +408,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 //            CTA's slice is one contiguous block for its bulk copy; a thread's two float4 per k are contiguous across the warp).
 __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                  float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
+  sg_pdl_sync();
   const int H4 = 4 * H;
   const long long total = (long long)2 * H4 * H;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -440,7 +444,7 @@ static int lstm_block(int H) { return ((4 * H + 31) / 32) * 32; }
 
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256, "hidden size must be in [1, 256]");
-  lstm_prep_kernel<<<sg_grid_for((long long)8 * H * H, 256, 4), 256, 0, (cudaStream_t)stream>>>(whh, b_ih, b_hh, whh_t, bsum, H,
+  sg_launch_pdl(lstm_prep_kernel, dim3(sg_grid_for((long long)8 * H * H, 256, 4)), dim3(256), 0, (cudaStream_t)stream, whh, b_ih, b_hh, whh_t, bsum, H,
                                                                                                   lstm_reg_supported(H) ? lstm_reg_cluster(H) : 0);
   return subgnn_check_launch("lstm_prep_kernel");
 }
@@ -527,7 +531,7 @@ int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, in
 int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,
                          int D, int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  lstm_head_fwd_kernel<<<n_groups, 512, (size_t)H2 * sizeof(float), (cudaStream_t)stream>>>(OUT, AGG, EMB, W, bias, n_groups, group, T, H2, D,
+  sg_launch_pdl(lstm_head_fwd_kernel, dim3(n_groups), dim3(512), (size_t)H2 * sizeof(float), (cudaStream_t)stream, OUT, AGG, EMB, W, bias, n_groups, group, T, H2, D,
                                                                                           sum_mode);
   return subgnn_check_launch("lstm_head_fwd_kernel");
 }
@@ -535,7 +539,7 @@ int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* 
 int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,
                          int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  lstm_head_bwd_kernel<<<n_groups, 512, (size_t)(H2 + D) * sizeof(float), (cudaStream_t)stream>>>(dEMB, W, dOUT, db, n_groups, group, T, H2, D,
+  sg_launch_pdl(lstm_head_bwd_kernel, dim3(n_groups), dim3(512), (size_t)(H2 + D) * sizeof(float), (cudaStream_t)stream, dEMB, W, dOUT, db, n_groups, group, T, H2, D,
                                                                                                 sum_mode);
   return subgnn_check_launch("lstm_head_bwd_kernel");
 }
@@ -543,7 +547,7 @@ int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* 
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
                    void* stream) {
   if (n == 0) return SUBGNN_OK;
-  dropout_kernel<<<sg_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(x, y, n, p, seed, salt, step_dev);
+  sg_launch_pdl(dropout_kernel, dim3(sg_grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, x, y, n, p, seed, salt, step_dev);
   return subgnn_check_launch("dropout_kernel");
 }
 

@@ -112,6 +112,7 @@ template <int CL, int KS>
 __global__ void __launch_bounds__(512)
 lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float* __restrict__ OUT, float* __restrict__ CS,
                      int n_seq, int T, int H, int steps_fwd, int steps_rev, int tile) {
+  sg_pdl_sync();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
   constexpr int NF = 4 / KS;                // sequences finished per thread
@@ -242,6 +243,7 @@ __global__ void __launch_bounds__(512)
 lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
                      const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd, int steps_rev, int zero_untaken,
                      float* __restrict__ db_ih, float* __restrict__ db_hh, int tile) {
+  sg_pdl_sync();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
   const int U = H / CL, U4 = 4 * U, H4 = 4 * H;
@@ -405,7 +407,8 @@ int pick_tile(int n_seq, int cl, int threads_per_4seq, size_t smem_fixed, size_t
     const long long waves = (ctas + (long long)sms * occ - 1) / ((long long)sms * occ);
     // measured (tools/lstm_bench.py, B200): a step costs ~ fixed + c * tile per resident CTA and the CTAs of a wave run side
     // by side, so the fewest waves win and, among those, the smallest tile (most SMs busy): e.g. H = 128, 720 sequences:
-    // tile 20 (144 CTAs) 9.0 us/step, 24 (120 CTAs) 9.6, 28 (104) 10.9, 16 (180 CTAs, two waves) 13.8
+    // tile 20 (144 CTAs) 9.0 us/step, 24 (120 CTAs) 9.6, 28 (104) 10.9, 16 (180 CTAs, two waves) 13.8; inside the training
+    // step (other graph branches share the GPU) EM-USER shape: 0.715 ms with tile 20 against 0.744 ms with tile 24
     const long long cost = waves * 1000 + tile;
     if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = tile; }
   }
@@ -425,11 +428,13 @@ int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int 
   cfg.blockDim = dim3(KS * (U / 2) * (tile / 4), 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;          // PDL: see sg_pdl_sync (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile);
   return subgnn_check_launch("lstm_fwd_tile_kernel");
 }
@@ -448,11 +453,13 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   cfg.blockDim = dim3(KS * (H / 8) * tile, 1, 1);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = st;
-  cudaLaunchAttribute attr[1];
+  cudaLaunchAttribute attr[2];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;          // PDL: see sg_pdl_sync (common.cuh)
+  attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
-  cfg.numAttrs = 1;
+  cfg.numAttrs = 2;
   cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile);
   return subgnn_check_launch("lstm_bwd_tile_kernel");
 }

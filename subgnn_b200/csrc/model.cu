@@ -42,6 +42,7 @@ __device__ __forceinline__ int col_s(const Desc& d, int l, int side) {
 // ------------------------------------------------------------------------------------------------
 // prep: batch row offsets, R, max component length; transposed weights
 __global__ void __launch_bounds__(256) prep_batch_kernel(Desc d) {
+  sg_pdl_sync();
   __shared__ int part[256];
   __shared__ int pmax[256];
   const int t = threadIdx.x;
@@ -76,6 +77,7 @@ __global__ void __launch_bounds__(256) prep_batch_kernel(Desc d) {
 
 // out[c][r] = in[r][c] for a list of matrices: job j -> (src, dst, rows, cols)
 __global__ void transpose_weights_kernel(Desc d) {
+  sg_pdl_sync();
   // jobs: N-channel projections (L*2 of D x 2D), then lin (h1 x hid), lin2 (h2 x h1), lin3 (K x h2)
   const int n_jobs_n = d.use_n ? d.L * 2 : 0;
   for (int job = blockIdx.y; job < n_jobs_n + 3; job += gridDim.y) {
@@ -164,6 +166,7 @@ __device__ __forceinline__ QEntry q_entry(const Desc& d, int l, int e) {
 
 // which: bit 0 = position-channel entries, bit 1 = structure-channel entries (these need the LSTM output emb_s)
 __global__ void __launch_bounds__(256) q_fwd_kernel(Desc d, int which) {
+  sg_pdl_sync();
   const int lane = threadIdx.x & 31;
   const int per_layer = q_entries_per_layer(d);
   const int total = per_layer * d.L;
@@ -185,6 +188,7 @@ __global__ void __launch_bounds__(256) q_fwd_kernel(Desc d, int which) {
 // grid (blocks_per_group, L * groups); group = one (channel side) parameter block, so that d w_p is reduced
 // inside the CTA and added once per CTA.
 __global__ void __launch_bounds__(256) q_bwd_kernel(Desc d) {
+  sg_pdl_sync();
   __shared__ float s_dwp[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = (d.use_p ? 2 : 0) + (d.use_s ? 2 : 0);
@@ -309,6 +313,7 @@ static size_t row_smem_bytes(int D) { return (size_t)(D + 2 * D + 4 * D + 2 * SI
 // phases: bit 0 = pooling + neighbourhood channel, bit 1 = position / structure property-aware outputs (needs q)
 template <int DPL>
 __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases) {
+  sg_pdl_sync();
   extern __shared__ float sm[];
   const int D = d.D;
   const RowSmem S = row_smem(sm, D);
@@ -483,6 +488,7 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
 //   mlp_dz_kernel    CTA per 64-column slice of hid: dZ[b][i] = sum_j dH1[b][j] W1[j][i]
 #define MLP_SLICE 64
 __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
+  sg_pdl_sync();
   extern __shared__ float sm[];
   float* zs = sm;                               // [B][MLP_SLICE]
   float* ws = sm + (size_t)d.B * MLP_SLICE;     // [MLP_SLICE][h1]
@@ -505,6 +511,7 @@ __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
 }
 
 __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
+  sg_pdl_sync();
   extern __shared__ float sm[];
   float* w1t = sm;                               // [h1][h2]  lin2 weights, input-major (forward)
   float* w1n = w1t + (size_t)d.h1 * d.h2;        // [h2][h1]  lin2 weights, native (backward)
@@ -598,6 +605,7 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
 }
 
 __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
+  sg_pdl_sync();
   extern __shared__ float sm[];
   float* g1s = sm;                               // [B][h1]
   float* ws = sm + (size_t)d.B * d.h1;           // [h1][MLP_SLICE]
@@ -622,6 +630,7 @@ __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
 
 template <int DPL>
 __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases) {
+  sg_pdl_sync();
   extern __shared__ float sm[];
   const int D = d.D;
   float* dx0 = sm;                  // [D]
@@ -763,6 +772,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases
 // dW[z] (D x 2D) += dpre[z]^T [Nh[z] | Nagg[z]] over the valid rows; db[z] += column sums of dpre[z]
 #include "gemm_tile.cuh"
 __global__ void __launch_bounds__(256) n_wgrad_kernel(Desc d, int splits, int m_chunk) {
+  sg_pdl_sync();
   const int D = d.D;
   const int z = blockIdx.z / splits, sp = blockIdx.z % splits;
   const int R = d.meta[0];
@@ -804,10 +814,10 @@ static int check_desc(const Desc* d) {
 #define DISPATCH_DPL(D, KERNEL, ...)                                   \
   do {                                                                 \
     const int dpl_ = ((D) + 31) / 32;                                  \
-    if (dpl_ <= 1) { KERNEL<1> __VA_ARGS__; }                          \
-    else if (dpl_ <= 2) { KERNEL<2> __VA_ARGS__; }                     \
-    else if (dpl_ <= 4) { KERNEL<4> __VA_ARGS__; }                     \
-    else { KERNEL<8> __VA_ARGS__; }                                    \
+    if (dpl_ <= 1) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<1>, __VA_ARGS__); }          \
+    else if (dpl_ <= 2) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<2>, __VA_ARGS__); }     \
+    else if (dpl_ <= 4) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<4>, __VA_ARGS__); }     \
+    else { sg_launch_pdl<SG_PDL_ROW>(KERNEL<8>, __VA_ARGS__); }                    \
   } while (0)
 
 static int row_grid(const Desc* d) {
@@ -822,7 +832,7 @@ int subgnn_model_desc_size(void) { return (int)sizeof(subgnn_model_desc); }
 int subgnn_model_prep_batch(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  prep_batch_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(*d);
+  sg_launch_pdl(prep_batch_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, *d);
   return subgnn_check_launch("prep_batch_kernel");
 }
 
@@ -830,7 +840,7 @@ int subgnn_model_prep_weights(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   dim3 grid(32, (d->use_n ? 2 * d->L : 0) + 3);
-  transpose_weights_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  sg_launch_pdl(transpose_weights_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d);
   return subgnn_check_launch("transpose_weights_kernel");
 }
 
@@ -848,7 +858,7 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
   if (!d->use_p) which &= ~SUBGNN_Q_POS;
   if (!d->use_s) which &= ~SUBGNN_Q_STRUC;
   if (!which) return SUBGNN_OK;
-  q_fwd_kernel<<<sg_grid_for(total, 8, 8), 256, 0, (cudaStream_t)stream>>>(*d, which);
+  sg_launch_pdl(q_fwd_kernel, dim3(sg_grid_for(total, 8, 8)), dim3(256), 0, (cudaStream_t)stream, *d, which);
   return subgnn_check_launch("q_fwd_kernel");
 }
 
@@ -860,7 +870,7 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) 
   if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
   if (!phases) return SUBGNN_OK;
   const size_t smem = row_smem_bytes(d->D);
-  DISPATCH_DPL(d->D, row_fwd_kernel, <<<row_grid(d), ROW_THREADS, smem, (cudaStream_t)stream>>>(*d, phases));
+  DISPATCH_DPL(d->D, row_fwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), smem, (cudaStream_t)stream, *d, phases);
   return subgnn_check_launch("row_fwd_kernel");
 }
 
@@ -877,14 +887,14 @@ int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   if (s1 > 48 * 1024) cudaFuncSetAttribute(mlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (s2 > 48 * 1024) cudaFuncSetAttribute(mlp_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
   if (s3 > 48 * 1024) cudaFuncSetAttribute(mlp_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
-  mlp_lin1_kernel<<<slices, 256, s1, st>>>(*d);
+  sg_launch_pdl(mlp_lin1_kernel, dim3(slices), dim3(256), s1, st, *d);
   rc = subgnn_check_launch("mlp_lin1_kernel");
   if (rc) return rc;
-  mlp_rest_kernel<<<d->B, 256, s2, st>>>(*d);
+  sg_launch_pdl(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
   rc = subgnn_check_launch("mlp_rest_kernel");
   if (rc) return rc;
   if (d->training && d->dZ) {
-    mlp_dz_kernel<<<slices, 256, s3, st>>>(*d);
+    sg_launch_pdl(mlp_dz_kernel, dim3(slices), dim3(256), s3, st, *d);
     rc = subgnn_check_launch("mlp_dz_kernel");
   }
   return rc;
@@ -910,7 +920,7 @@ int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) 
   if (rc) return rc;
   if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
   if (!phases) return SUBGNN_OK;
-  DISPATCH_DPL(d->D, row_bwd_kernel, <<<row_grid(d), ROW_THREADS, bwd_smem(*d), (cudaStream_t)stream>>>(*d, phases));
+  DISPATCH_DPL(d->D, row_bwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), bwd_smem(*d), (cudaStream_t)stream, *d, phases);
   return subgnn_check_launch("row_bwd_kernel");
 }
 
@@ -928,7 +938,7 @@ int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
   int gx = sg_div_up(max_cnt, 24);
   gx = gx < 8 ? 8 : (gx > 96 ? 96 : gx);
   dim3 grid(gx, d->L * groups);
-  q_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d);
+  sg_launch_pdl(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d);
   return subgnn_check_launch("q_bwd_kernel");
 }
 
@@ -941,7 +951,7 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
     const int m_chunk = sg_div_up(sg_div_up(d->R_cap, splits), 16) * 16;
     splits = sg_div_up(d->R_cap, m_chunk);
     dim3 grid(sg_div_up(2 * D, 64), sg_div_up(D, 64), d->L * 2 * splits);
-    n_wgrad_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(*d, splits, m_chunk);
+    sg_launch_pdl(n_wgrad_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d, splits, m_chunk);
     rc = subgnn_check_launch("n_wgrad_kernel");
     if (rc) return rc;
   }

@@ -11,12 +11,14 @@
 #include "../../include/subgnn_b200.h"
 
 __global__ void fill_zero_kernel(float4* __restrict__ p4, long long n4, float* __restrict__ tail, int ntail) {
+  sg_pdl_sync();
   const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) p4[i] = z;
   if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
 
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
+  sg_pdl_sync();
   float s = 0.f;
   const long long n4 = n / 4;
   const float4* g4 = reinterpret_cast<const float4*>(g);
@@ -41,6 +43,7 @@ __global__ void __launch_bounds__(256)
 adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v, long long n, float lr,
             float beta1, float beta2, float eps, const int* __restrict__ step_dev, const float* __restrict__ sumsq, float clip_norm,
             float grad_scale) {
+  sg_pdl_sync();
   const int t = *step_dev;
   float coef = grad_scale;
   if (clip_norm > 0.f && sumsq) {
@@ -73,6 +76,7 @@ adam_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restric
 }
 
 __global__ void sum_to_scalar_kernel(const float* __restrict__ x, int n, float* __restrict__ out) {
+  sg_pdl_sync();
   float s = 0.f;
   for (int i = threadIdx.x; i < n; i += blockDim.x) s += x[i];
   __shared__ float ws[32];
@@ -94,14 +98,14 @@ int subgnn_fill_zero(float* p, long long n, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE(((size_t)p & 15) == 0, "buffer must be 16-byte aligned");
   const long long n4 = n / 4;
-  fill_zero_kernel<<<sg_grid_for(n4 > 0 ? n4 : 1, 256, 8), 256, 0, (cudaStream_t)stream>>>(reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4));
+  sg_launch_pdl(fill_zero_kernel, dim3(sg_grid_for(n4 > 0 ? n4 : 1, 256, 8)), dim3(256), 0, (cudaStream_t)stream, reinterpret_cast<float4*>(p), n4, p + n4 * 4, (int)(n - n4 * 4));
   return subgnn_check_launch("fill_zero_kernel");
 }
 
 int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE(((size_t)g & 15) == 0, "buffer must be 16-byte aligned");
-  sumsq_kernel<<<sg_grid_for(n / 4 + 1, 256, 4), 256, 0, (cudaStream_t)stream>>>(g, n, out_sumsq);
+  sg_launch_pdl(sumsq_kernel, dim3(sg_grid_for(n / 4 + 1, 256, 4)), dim3(256), 0, (cudaStream_t)stream, g, n, out_sumsq);
   return subgnn_check_launch("sumsq_kernel");
 }
 
@@ -109,13 +113,13 @@ int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, 
                      const int* step_dev, const float* sumsq_dev, float clip_norm, float grad_scale, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0, "buffers must be 16-byte aligned");
-  adam_kernel<<<sg_grid_for((n + 3) / 4, 256, 8), 256, 0, (cudaStream_t)stream>>>(p, g, m, v, n, lr, beta1, beta2, eps, step_dev, sumsq_dev, clip_norm,
-                                                                        grad_scale);
+  sg_launch_pdl(adam_kernel, dim3(sg_grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
+                sumsq_dev, clip_norm, grad_scale);
   return subgnn_check_launch("adam_kernel");
 }
 
 int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream) {
-  sum_to_scalar_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  sg_launch_pdl(sum_to_scalar_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, x, n, out);
   return subgnn_check_launch("sum_to_scalar_kernel");
 }
 

@@ -1,5 +1,6 @@
 // Error reporting / device queries for the C-ABI.
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
 #include "../../include/subgnn_b200.h"
@@ -13,6 +14,12 @@ void subgnn_set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+// default classes launched with programmatic stream serialization (see sg_pdl_sync in common.cuh).  Measured on B200, ms/step
+// (ppi_bp / hpo_metab / em_user shapes, same box): mask 0: 0.445 / 0.860 / 0.712; 4 (recurrences): 0.442 / 0.843 / 0.727;
+// 14 (GEMMs + recurrences + row kernels): 0.431 / 0.800 / 0.739; 15 (everything): 0.426 / 0.879 / 0.827 — early-scheduled
+// small kernels take SM slots from the other graph branches at the two H = 128 shapes.
+#define SUBGNN_PDL_DEFAULT_MASK 14
+
 static unsigned long long g_launches = 0;
 
 int subgnn_check_launch(const char* what) {
@@ -23,6 +30,15 @@ int subgnn_check_launch(const char* what) {
     return SUBGNN_ERR_CUDA;
   }
   return SUBGNN_OK;
+}
+
+int subgnn_pdl_enabled(int kernel_class) {
+  static int mask = -1;
+  if (mask < 0) {
+    const char* e = getenv("SUBGNN_B200_PDL");
+    mask = e ? atoi(e) : SUBGNN_PDL_DEFAULT_MASK;
+  }
+  return (mask >> kernel_class) & 1;
 }
 
 int subgnn_sm_count() {

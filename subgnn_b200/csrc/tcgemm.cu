@@ -257,6 +257,7 @@ template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
                      const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
+  sg_pdl_sync();
   __shared__ __align__(16) float s_bias[N_TILE];
   const int m0 = blockIdx.y * TC_M, n0 = blockIdx.x * N_TILE;
   for (int i = threadIdx.x; i < N_TILE; i += TC_THREADS) s_bias[i] = (bias && n0 + i < N) ? bias[n0 + i] : 0.f;   // visible after tc_tile's barriers
@@ -294,6 +295,7 @@ template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w, int ldw, float* __restrict__ dx, int lddx,
                            const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
+  sg_pdl_sync();
   const int m0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;      // output tile: rows m, columns k
   const int nr0 = blockIdx.z * n_chunk, nr1 = min(N, nr0 + n_chunk);
   if (nr0 >= nr1) return;
@@ -337,6 +339,7 @@ template <int N_TILE>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
                             float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk) {
+  sg_pdl_sync();
   const int n0 = blockIdx.y * TC_M, k0o = blockIdx.x * N_TILE;       // output tile: rows n, columns k
   const int mr0 = blockIdx.z * m_chunk, mr1 = min(M, mr0 + m_chunk);
   if (mr0 >= mr1) return;
@@ -374,7 +377,7 @@ template <int NT>
 static void launch_bwd_input(dim3 grid, cudaStream_t st, const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx,
                              const int* scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
   cudaFuncSetAttribute(tc_linear_bwd_input_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<NT>());
-  tc_linear_bwd_input_kernel<NT><<<grid, TC_THREADS, tc_smem<NT>(), st>>>(dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+  sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_input_kernel<NT>, grid, dim3(TC_THREADS), tc_smem<NT>(), st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
 }
 
 extern "C" {
@@ -387,11 +390,11 @@ int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const f
   if (N <= 64) {
     cudaFuncSetAttribute(tc_linear_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
     dim3 grid(sg_div_up(N, 64), sg_div_up(M, TC_M));
-    tc_linear_fwd_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_fwd_kernel<64>, grid, dim3(TC_THREADS), tc_smem<64>(), (cudaStream_t)stream, x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
   } else {
     cudaFuncSetAttribute(tc_linear_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
     dim3 grid(sg_div_up(N, 128), sg_div_up(M, TC_M));
-    tc_linear_fwd_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
+    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_fwd_kernel<128>, grid, dim3(TC_THREADS), tc_smem<128>(), (cudaStream_t)stream, x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
   }
   return subgnn_check_launch("tc_linear_fwd_kernel");
 }
@@ -440,10 +443,10 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
   dim3 grid(sg_div_up(K, nt), sg_div_up(N, TC_M), splits);
   if (nt == 64) {
     cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
-    tc_linear_bwd_weight_kernel<64><<<grid, TC_THREADS, tc_smem<64>(), (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_weight_kernel<64>, grid, dim3(TC_THREADS), tc_smem<64>(), (cudaStream_t)stream, dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
   } else {
     cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
-    tc_linear_bwd_weight_kernel<128><<<grid, TC_THREADS, tc_smem<128>(), (cudaStream_t)stream>>>(dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
+    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_weight_kernel<128>, grid, dim3(TC_THREADS), tc_smem<128>(), (cudaStream_t)stream, dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
   }
   int rc = subgnn_check_launch("tc_linear_bwd_weight_kernel");
   if (rc) return rc;
