@@ -128,6 +128,15 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
 /* db_ih / db_hh (optional, [2][4H]): += column sums of d(pre-activation), the gradient of both bias vectors */
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
                           int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream);
+/* the same recurrences with nn.LSTM's inter-layer dropout fused in (training, p > 0): forward also writes xdrop = dropout_p(OUT), the
+   next layer's input; backward applies the same mask to dOUT (then the gradient w.r.t. xdrop) on load.  Mask stream = the one of
+   subgnn_dropout(seed, salt, step_dev).  Available when subgnn_lstm_fused_dropout_supported(H). */
+int subgnn_lstm_fused_dropout_supported(int H);
+int subgnn_lstm_recur_fwd_drop(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
+                               float* xdrop, float p, unsigned long long seed, unsigned salt, const int* step_dev, void* stream);
+int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
+                               int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed,
+                               unsigned salt, const int* step_dev, void* stream);
 int subgnn_add_inplace(float* dst, const float* src, int n, void* stream);
 int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
 int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);

@@ -46,6 +46,8 @@ SIGNATURES = {
     'subgnn_lstm_prep': [P, P, P, P, P, I, P],
     'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
     'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P, P],
+    'subgnn_lstm_recur_fwd_drop': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
+    'subgnn_lstm_recur_bwd_drop': [P, P, P, P, P, I, I, I, I, I, I, P, P, F, U64, U32, P, P],
     'subgnn_add_inplace': [P, P, I, P],
     'subgnn_lstm_agg_fwd': [P, P, I, I, I, I, P],
     'subgnn_lstm_agg_bwd': [P, P, I, I, I, I, P],
@@ -81,6 +83,7 @@ _OTHER = {
     'subgnn_device_sm_count': ([], I),
     'subgnn_model_desc_size': ([], I),
     'subgnn_launch_count': ([], U64),
+    'subgnn_lstm_fused_dropout_supported': ([I], I),
 }
 
 

@@ -454,7 +454,7 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   SG_REQUIRE(steps_fwd >= 0 && steps_fwd <= T && steps_rev >= 0 && steps_rev <= T, "bad step counts");
   if (n_seq == 0) return SUBGNN_OK;
-  if (lstm_reg_supported(H)) return lstm_reg_fwd(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev, (cudaStream_t)stream);
+  if (lstm_reg_supported(H)) return lstm_reg_fwd(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev, nullptr, 0.f, 0ull, 0u, nullptr, (cudaStream_t)stream);
   size_t smem = (size_t)(2 * S_TILE * H + S_TILE * 4 * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
   const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh_t) & 15) == 0;   // two CTAs per SM stay resident; bulk copy: 16-byte granules
@@ -476,12 +476,33 @@ int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, i
   return subgnn_check_launch("lstm_recur_fwd_kernel");
 }
 
+int subgnn_lstm_fused_dropout_supported(int H) { return lstm_reg_supported(H) ? 1 : 0; }
+
+int subgnn_lstm_recur_fwd_drop(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
+                               float* xdrop, float p, unsigned long long seed, unsigned salt, const int* step_dev, void* stream) {
+  SG_REQUIRE(lstm_reg_supported(H), "fused inter-layer dropout needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
+  SG_REQUIRE(n_seq >= 0 && T >= 1 && p >= 0.f && p < 1.f, "bad sizes");
+  SG_REQUIRE(steps_fwd >= 0 && steps_fwd <= T && steps_rev >= 0 && steps_rev <= T, "bad step counts");
+  if (n_seq == 0) return SUBGNN_OK;
+  return lstm_reg_fwd(G, whh_t, OUT, CS, n_seq, T, H, steps_fwd, steps_rev, xdrop, p, seed, salt, step_dev, (cudaStream_t)stream);
+}
+
+int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
+                               int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed,
+                               unsigned salt, const int* step_dev, void* stream) {
+  SG_REQUIRE(lstm_reg_supported(H), "fused inter-layer dropout needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
+  SG_REQUIRE(n_seq >= 0 && T >= 1 && p >= 0.f && p < 1.f, "bad sizes");
+  if (n_seq == 0) return SUBGNN_OK;
+  return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, p, seed, salt, step_dev,
+                      (cudaStream_t)stream);
+}
+
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
                           int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream) {
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
   if (lstm_reg_supported(H))
-    return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, (cudaStream_t)stream);
+    return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, 0.f, 0ull, 0u, nullptr, (cudaStream_t)stream);
   size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
   const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh) & 15) == 0;

@@ -25,6 +25,17 @@
 
 namespace {
 
+// inter-layer dropout fused into the recurrence (nn.LSTM dropout=p between layers, training only; same Philox stream as
+// dropout_kernel in lstm.cu: element index within the (n_seq*T, 2H) buffer, salt = layer + 64 * step counter)
+struct DropArgs {
+  float* xd;                  // forward: dropped-out copy of OUT (input of the next layer), or nullptr
+  float p;                    // 0: no dropout
+  unsigned long long seed;
+  unsigned salt;
+  const int* step_dev;
+};
+__device__ __forceinline__ unsigned drop_salt(const DropArgs& d) { return d.step_dev ? d.salt + 64u * (unsigned)*d.step_dev + 0x80000000u : d.salt; }
+
 // sigmoid / tanh from ex2.approx + rcp.approx: relative error ~1e-7 on the sigmoid, absolute error ~2e-7 on tanh — inside the
 // fp32 tolerance of the parity tests; 5 instructions instead of ~25 for the libm versions (40 activations per thread and step).
 __device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
@@ -111,7 +122,7 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[4][4], const float4 x, co
 template <int CL, int KS>
 __global__ void __launch_bounds__(512)
 lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float* __restrict__ OUT, float* __restrict__ CS,
-                     int n_seq, int T, int H, int steps_fwd, int steps_rev, int tile) {
+                     int n_seq, int T, int H, int steps_fwd, int steps_rev, int tile, DropArgs drop) {
   sg_pdl_sync();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
@@ -138,6 +149,7 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
   float2 c[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) c[f] = make_float2(0.f, 0.f);
+  const unsigned dsalt = drop.xd ? drop_salt(drop) : 0u;
   step_sync<CL>();                          // every CTA's h tile is zeroed before a peer writes into it; mbarrier init published
   bulk_wait(&wbar);
   int cur = 0;
@@ -225,7 +237,18 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
         *reinterpret_cast<float2*>(gr + 2 * H) = gate_g[f];
         *reinterpret_cast<float2*>(gr + 3 * H) = gate_o[f];
         *reinterpret_cast<float2*>(CS + (row * 2 + dir) * H + unit0) = c[f];
-        *reinterpret_cast<float2*>(OUT + row * 2 * H + dir * H + unit0) = h_new[f];
+        const size_t e = row * 2 * H + dir * H + unit0;                       // even: units come in pairs
+        *reinterpret_cast<float2*>(OUT + e) = h_new[f];
+        if (drop.xd) {
+          float2 hd = h_new[f];
+          if (drop.p > 0.f) {
+            const Philox4 r = sg_draw(drop.seed, (uint64_t)(e >> 2), dsalt, SG_TAG_DROP);
+            const float keep = 1.f / (1.f - drop.p);
+            hd.x *= sg_unit((e & 2) ? r.z : r.x) >= drop.p ? keep : 0.f;
+            hd.y *= sg_unit((e & 2) ? r.w : r.y) >= drop.p ? keep : 0.f;
+          }
+          *reinterpret_cast<float2*>(drop.xd + e) = hd;
+        }
       }
     }
     step_wait<CL>();
@@ -242,7 +265,7 @@ template <int CL, int KS>
 __global__ void __launch_bounds__(512)
 lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
                      const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd, int steps_rev, int zero_untaken,
-                     float* __restrict__ db_ih, float* __restrict__ db_hh, int tile) {
+                     float* __restrict__ db_ih, float* __restrict__ db_hh, int tile, DropArgs drop) {
   sg_pdl_sync();
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
@@ -277,6 +300,7 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
   step_sync<CL>();
   bulk_wait(&wbar);
   const int n_el = ns * U;
+  const unsigned dsalt = drop.p > 0.f ? drop_salt(drop) : 0u;
   for (int st = n_steps - 1; st >= 0; --st) {
     const int t = dir == 0 ? st : T - 1 - st;
     const int t_prev = dir == 0 ? t - 1 : t + 1;
@@ -297,6 +321,8 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
         cc[q] = CS[(row * 2 + dir) * H + ug];
         cp[q] = st > 0 ? CS[((((size_t)(seq0 + s) * T + t_prev) * 2) + dir) * H + ug] : 0.f;
         dho[q] = dOUT[row * 2 * H + dir * H + ug];
+        // dOUT holds the gradient w.r.t. the DROPPED-OUT copy of this layer's output: apply the same mask
+        if (drop.p > 0.f) dho[q] *= sg_dropout_scale(drop.seed, dsalt, (uint64_t)(row * 2 * H + dir * H + ug), drop.p);
         float r = 0.f;
 #pragma unroll
         for (int sl = 0; sl < SLOTS; ++sl) r += red[(size_t)sl * tile * U + s * U + u];
@@ -416,7 +442,7 @@ int pick_tile(int n_seq, int cl, int threads_per_4seq, size_t smem_fixed, size_t
 }
 
 template <int CL, int KS>
-int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, cudaStream_t st) {
+int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, DropArgs drop, cudaStream_t st) {
   const int U = H / CL;
   const size_t fixed = (size_t)H * 4 * U * sizeof(float), per_seq = (size_t)(2 * H + KS * 4 * U) * sizeof(float);
   const int tile = pick_tile(n_seq, CL, KS * (U / 2), fixed, per_seq);
@@ -435,13 +461,13 @@ int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int 
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile);
+  cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile, drop);
   return subgnn_check_launch("lstm_fwd_tile_kernel");
 }
 
 template <int CL, int KS>
 int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
-               int zero_untaken, float* db_ih, float* db_hh, cudaStream_t st) {
+               int zero_untaken, float* db_ih, float* db_hh, DropArgs drop, cudaStream_t st) {
   const int U = H / CL;
   const size_t fixed = (size_t)(4 * U * H + 4 * U) * sizeof(float), per_seq = (size_t)(4 * U + U + 4 * KS * CL * U) * sizeof(float);
   const int tile = pick_tile(n_seq, CL, KS * 4 * (H / 8), fixed, per_seq);
@@ -460,7 +486,7 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile);
+  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile, drop);
   return subgnn_check_launch("lstm_bwd_tile_kernel");
 }
 
@@ -470,15 +496,19 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
 bool lstm_reg_supported(int H) { return H >= 8 && H <= 128 && (H % 8) == 0 && (H <= 64 || (H % 16) == 0); }
 int lstm_reg_cluster(int H) { return H <= 64 ? 1 : 2; }
 
-int lstm_reg_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, cudaStream_t st) {
-  if (lstm_reg_cluster(H) == 2) return launch_fwd<2, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
-  if (H % 16 == 0) return launch_fwd<1, 4>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
-  return launch_fwd<1, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, st);
+int lstm_reg_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, float* xdrop, float p,
+                 unsigned long long seed, unsigned salt, const int* step_dev, cudaStream_t st) {
+  const DropArgs drop = {xdrop, p, seed, salt, step_dev};
+  if (lstm_reg_cluster(H) == 2) return launch_fwd<2, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (H % 16 == 0) return launch_fwd<1, 4>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  return launch_fwd<1, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
 }
 
 int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
-                 int zero_untaken, float* db_ih, float* db_hh, cudaStream_t st) {
-  if (lstm_reg_cluster(H) == 2) return launch_bwd<2, 1>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
-  if (H % 16 == 0) return launch_bwd<1, 4>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
-  return launch_bwd<1, 2>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, st);
+                 int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed, unsigned salt, const int* step_dev,
+                 cudaStream_t st) {
+  const DropArgs drop = {nullptr, p, seed, salt, step_dev};
+  if (lstm_reg_cluster(H) == 2) return launch_bwd<2, 1>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
+  if (H % 16 == 0) return launch_bwd<1, 4>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
+  return launch_bwd<1, 2>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
 }

@@ -3,6 +3,10 @@
 #include <cuda_runtime.h>
 bool lstm_reg_supported(int H);
 int lstm_reg_cluster(int H);   // CTAs per cluster (1 or 2) == how many unit ranges the forward weights are permuted for
-int lstm_reg_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev, cudaStream_t st);
+// xdrop != nullptr: also write dropout_p(OUT) (the next layer's input) with the Philox stream (seed, salt [+ 64 * *step_dev]);
+// backward p > 0: dOUT is the gradient w.r.t. that dropped-out copy, the same mask is applied on load
+int lstm_reg_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev, float* xdrop,
+                 float p, unsigned long long seed, unsigned salt, const int* step_dev, cudaStream_t st);
 int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int steps_fwd,
-                 int steps_rev, int zero_untaken, float* db_ih, float* db_hh, cudaStream_t st);
+                 int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed, unsigned salt,
+                 const int* step_dev, cudaStream_t st);

