@@ -362,7 +362,7 @@ def main():
     sampler.mark_begin()
     t0 = time.perf_counter()
     for hb in host_batches:
-        out = model.training_step_fused(hb, use_graph=use_graph)
+        out = model.training_step_fused(hb, use_graph=use_graph, sync_loss=True)
         _ = float(out['loss'])                                        # device -> host read of the step result
     barrier()
     e2e_s = time.perf_counter() - t0
@@ -372,7 +372,7 @@ def main():
         dist.all_reduce(tm, op=dist.ReduceOp.MAX)
         e2e_s = float(tm.item())
     e2e = {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 4,
-           'note': 'SubGNN.training_step_fused(host batch dict): pinned H2D of the subgraph indices, fused step, loss.item(); all tables are '
+           'note': 'SubGNN.training_step_fused(host batch dict): pinned H2D of the subgraph indices, fused step graph ending in a D2H copy node of the loss, stream sync + host read every step; all tables are '
                    'device-resident after prepare_data (the reference re-uploads the dense similarity slab every step)'}
 
     # the timed region of a launch-bound step can be shorter than nvidia-smi's polling period: keep the GPU under the

@@ -26,6 +26,7 @@ extern "C" {
 #define SUBGNN_ABI_VERSION 1
 #define SUBGNN_DTW_EXACT 0
 #define SUBGNN_DTW_FASTDTW_R1 1
+#define SUBGNN_DTW_EXACT_THREAD 2   /* exact DTW on the thread-per-pair mapping (same values as SUBGNN_DTW_EXACT) */
 
 const char* subgnn_last_error(void);
 int subgnn_abi_version(void);

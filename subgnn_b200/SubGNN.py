@@ -280,11 +280,15 @@ class SubGNN(nn.Module):
         acc = calc_accuracy(logits.detach(), labels, self.multilabel)
         return {'loss': loss, 'log': {'train_loss': loss, 'train_acc': acc}}
 
-    def training_step_fused(self, train_batch, use_graph=True):
+    def training_step_fused(self, train_batch, use_graph=True, sync_loss=False):
         """Whole optimisation step on the device (forward, loss, backward, clip_grad_norm_, Adam) — the fast path.
-        ``train_batch['subgraph_idx']`` may be a host tensor; it is the only per-step input."""
+        ``train_batch['subgraph_idx']`` may be a host tensor; it is the only per-step input.  The returned loss is a device
+        tensor of an asynchronously enqueued step; with ``sync_loss`` the call waits for the step and returns the loss as a
+        host tensor (copied by the D2H node that ends the step graph), so ``float(loss)`` costs no further transfer."""
         idx = train_batch['subgraph_idx'].reshape(-1).numpy() if not train_batch['subgraph_idx'].is_cuda else train_batch['subgraph_idx'].reshape(-1).cpu().numpy()
         loss = self.engine.train_step(idx, use_graph=use_graph)
+        if sync_loss:
+            return {'loss': torch.tensor(self.engine.loss_value())}
         return {'loss': loss}
 
     def val_test_step(self, batch, batch_idx=0, is_test=False):

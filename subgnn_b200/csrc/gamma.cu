@@ -254,6 +254,92 @@ __global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __rest
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Exact DTW, wavefront mapping: a group of G lanes (G = 4 ... 32, 32/G pairs per warp) owns one (a, b) pair.  Lane l of the
+// group holds rows l*R ... l*R+R-1 of the DP (the component sequence, the short side) in registers and walks the columns of
+// the patch sequence one per iteration, one anti-diagonal step behind lane l-1: D[i-1][j] arrives by __shfl_up_sync, D[i-1][j-1]
+// is the value received one iteration earlier, D[i][j-1] is the lane's own previous result.  No DP state in shared memory (only
+// the patch sequence is staged there).  Values are identical to the row-by-row evaluation: every cell is cost + min of the same
+// three fp64 numbers, and min(a+c, b+c, d+c) == min(a, b, d) + c in floating point (rounding is monotonic).
+template <int G, int R>
+__global__ void __launch_bounds__(128) dtw_exact_wave_kernel(const int* __restrict__ seqA, const int* __restrict__ lenA, int nA, int strideA,
+                                                             const int* __restrict__ seqB, const int* __restrict__ lenB, int nB, int strideB,
+                                                             int LB, float* __restrict__ out) {
+  extern __shared__ __align__(16) int smem[];
+  const int lane = threadIdx.x & 31;
+  const int gl = lane % G;                                  // lane inside the group
+  const int gw = lane / G;                                  // group inside the warp
+  const int groups_per_cta = blockDim.x / G;
+  int* ys = smem + (threadIdx.x / G) * LB;
+  const double INF = __longlong_as_double(0x7ff0000000000000LL);
+  const long long total = (long long)nA * nB;
+  const long long stride = (long long)gridDim.x * groups_per_cta;
+  // all groups of a warp run the same number of rounds (shuffles use the full mask)
+  for (long long base = (long long)blockIdx.x * groups_per_cta + threadIdx.x / G - gw; base < total; base += stride) {
+    const long long p = base + gw;
+    const bool valid = p < total;
+    int n = 0, m = 0, a = 0, b = 0;
+    if (valid) {
+      a = (int)(p / nB); b = (int)(p % nB);
+      n = lenA[a]; m = lenB[b];
+      if (n == 0 || m == 0) {                               // SubGNN.py:831
+        if (gl == 0) out[p] = 0.f;
+        n = 0; m = 0;
+      }
+    }
+    for (int j = gl; j < m; j += G) ys[j] = seqB[(size_t)b * strideB + j];
+    double x[R], col[R];
+#pragma unroll
+    for (int r = 0; r < R; ++r) {
+      const int row = gl * R + r;
+      x[r] = row < n ? (double)seqA[(size_t)a * strideA + row] : 0.0;
+      col[r] = INF;                                          // D[row][-1]
+    }
+    __syncwarp();
+    const int iters = __reduce_max_sync(0xffffffffu, m > 0 ? m + (n - 1) / R : 0);
+    double last = INF, diag_in = INF;
+    for (int t = 0; t < iters; ++t) {
+      const double recv = __shfl_up_sync(0xffffffffu, last, 1, G);      // D[l*R-1][t-l], produced one iteration ago
+      const int j = t - gl;
+      if (j >= 0 && j < m) {
+        double up = gl == 0 ? INF : recv;
+        double dg = gl == 0 ? (j == 0 ? 0.0 : INF) : diag_in;
+        const double y = (double)ys[j];
+#pragma unroll
+        for (int r = 0; r < R; ++r) {
+          const double left = col[r];
+          const double mx = x[r] > y ? x[r] : y, mn = x[r] > y ? y : x[r];
+          const double best = fmin(fmin(up, left), dg) + ((mx + 1.0) / (mn + 1.0) - 1.0);    // gamma.py:51-52
+          dg = left; up = best; col[r] = best;
+        }
+        last = up;
+      }
+      diag_in = recv;
+    }
+    if (n > 0 && gl == (n - 1) / R) {
+      double d = col[0];
+#pragma unroll
+      for (int r = 1; r < R; ++r) if (r == (n - 1) % R) d = col[r];
+      out[p] = (float)(1.0 / (d + 1.0));                     // gamma.py:59, cast SubGNN.py:822
+    }
+    __syncwarp();
+  }
+}
+
+template <int G, int R>
+static int launch_dtw_wave(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
+                           int LB, float* out, cudaStream_t st) {
+  const int threads = 128, groups = threads / G;
+  const size_t smem = (size_t)groups * LB * sizeof(int);
+  if (smem > 200 * 1024) return -1;
+  cudaFuncSetAttribute(dtw_exact_wave_kernel<G, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  const long long total = (long long)nA * nB;
+  const long long want = (total + groups - 1) / groups;
+  const int grid = (int)(want < 148LL * 16 ? want : 148LL * 16);
+  dtw_exact_wave_kernel<G, R><<<grid, threads, smem, st>>>(seqA, lenA, nA, strideA, seqB, lenB, nB, strideB, LB, out);
+  return 0;
+}
+
 extern "C" {
 
 int subgnn_sp_min_dense(const unsigned char* hop, int n_nodes, long long hop_stride, const int* cc_ptr, const int* cc_nodes,
@@ -289,9 +375,23 @@ int subgnn_degree_seq(const int* rowptr, const int* col, const int* rows, int n_
 int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
                      int max_len_a, int max_len_b, int mode, float* out, void* stream) {
   SG_REQUIRE(nA >= 0 && nB >= 0 && max_len_a >= 1 && max_len_b >= 1, "bad sizes");
-  SG_REQUIRE(mode == SUBGNN_DTW_EXACT || mode == SUBGNN_DTW_FASTDTW_R1, "unknown DTW mode");
+  SG_REQUIRE(mode == SUBGNN_DTW_EXACT || mode == SUBGNN_DTW_FASTDTW_R1 || mode == SUBGNN_DTW_EXACT_THREAD, "unknown DTW mode");
   SG_REQUIRE(max_len_a <= strideA && max_len_b <= strideB && max_len_a < 32000 && max_len_b < 32000, "bad max lengths");
   if ((long long)nA * nB == 0) return SUBGNN_OK;
+  if (mode == SUBGNN_DTW_EXACT && max_len_a <= 256) {         // lanes own the rows of the component sequence
+    cudaStream_t st = (cudaStream_t)stream;
+    int rc;
+#define SG_WAVE(G, R) rc = launch_dtw_wave<G, R>(seqA, lenA, nA, strideA, seqB, lenB, nB, strideB, max_len_b, out, st)
+    if (max_len_a <= 4) SG_WAVE(4, 1);
+    else if (max_len_a <= 8) SG_WAVE(8, 1);
+    else if (max_len_a <= 16) SG_WAVE(16, 1);
+    else if (max_len_a <= 32) SG_WAVE(32, 1);
+    else if (max_len_a <= 64) SG_WAVE(32, 2);
+    else if (max_len_a <= 128) SG_WAVE(32, 4);
+    else SG_WAVE(32, 8);
+#undef SG_WAVE
+    if (rc == 0) return subgnn_check_launch("dtw_exact_wave_kernel");
+  }
   const DtwWs L = dtw_layout(max_len_a, max_len_b);
   const size_t per_thread = (size_t)L.total * 4;
   int threads = (int)((200 * 1024) / per_thread) / 32 * 32;

@@ -399,7 +399,11 @@ class StepContext:
         zi = lambda *s: torch.zeros(*s, dtype=torch.int32, device=dev)
         h1, h2, K, hid = hp['linear_hidden_dim_1'], hp['linear_hidden_dim_2'], eng.num_classes, eng.hid_dim
         self.batch_idx = zi(B)
-        self.batch_host = torch.zeros(B, dtype=torch.int32).pin_memory()
+        # pinned staging ring for the step's only host input: a slot is rewritten only after the copy that read it has retired
+        # (steps are enqueued asynchronously, the host may run several steps ahead of the device)
+        self.batch_ring = [[torch.zeros(B, dtype=torch.int32).pin_memory(), None] for _ in range(8)]
+        self.ring_pos = 0
+        self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()     # written by a D2H copy node at the end of the step
         self.b_rowptr, self.meta = zi(B + 1), zi(4)
         self.row_b, self.row_g = zi(self.R_cap), zi(self.R_cap)
         A_pi, A_pb, A_s = eng.A['pi'], eng.A['pb'], eng.A['s']
@@ -683,8 +687,15 @@ class Engine:
         """host -> device copy of the step's only input: the subgraph indices."""
         idx = torch.as_tensor(np.asarray(indices), dtype=torch.int32)
         assert idx.numel() == c.B
-        c.batch_host.copy_(idx)
-        c.batch_idx.copy_(c.batch_host, non_blocking=True)
+        slot = c.batch_ring[c.ring_pos]
+        c.ring_pos = (c.ring_pos + 1) % len(c.batch_ring)
+        if slot[1] is None:
+            slot[1] = torch.cuda.Event()
+        else:
+            slot[1].synchronize()
+        slot[0].copy_(idx)
+        c.batch_idx.copy_(slot[0], non_blocking=True)
+        slot[1].record()
 
     # ---- public API --------------------------------------------------------------------------------
     def forward(self, split, indices, training=False):
@@ -710,34 +721,55 @@ class Engine:
 
     def train_step(self, indices, use_graph=False):
         """one optimisation step on the train split: forward, loss, backward, [allreduce,] clip, Adam (in place).
-        With use_graph the launches are captured once into CUDA graphs (two halves around the NCCL allreduce when
-        data parallel) and replayed: the per-step host work is one pinned copy of the indices + graph launches."""
-        c = self.context('train', len(indices), True)
+        With use_graph the launches are captured once and replayed: ONE CUDA graph for the whole step on a single GPU, two
+        halves around the NCCL allreduce when data parallel.  The graph ends with a D2H copy node of the loss into pinned
+        host memory (read it with ``loss_value``); per-step host work is one pinned copy of the indices + the graph launch."""
+        c = self._last_ctx = self.context('train', len(indices), True)
         self.set_batch(c, indices)
         st = _abi.stream_ptr()
         if not use_graph:
             self._grad_launches(c, st)
             self.allreduce_grads()
             self._optimizer_launches(c, st)
+            c.loss_host.copy_(c.loss, non_blocking=True)
             return c.loss
         if c.graph is None:
             self._grad_launches(c, st)                         # warm-up (sets function attributes) — a real step
             self.allreduce_grads()
             self._optimizer_launches(c, st)
+            c.loss_host.copy_(c.loss, non_blocking=True)
             torch.cuda.synchronize()
             n0 = _abi.lib.subgnn_launch_count()
-            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g1):
-                self._grad_launches(c, _abi.stream_ptr())
-            with torch.cuda.graph(g2):
-                self._optimizer_launches(c, _abi.stream_ptr())
-            c.graph = (g1, g2)
+            if self.world_size > 1:
+                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g1):
+                    self._grad_launches(c, _abi.stream_ptr())
+                with torch.cuda.graph(g2):
+                    self._optimizer_launches(c, _abi.stream_ptr())
+                    c.loss_host.copy_(c.loss, non_blocking=True)
+                c.graph = (g1, g2)
+            else:
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._grad_launches(c, _abi.stream_ptr())
+                    self._optimizer_launches(c, _abi.stream_ptr())
+                    c.loss_host.copy_(c.loss, non_blocking=True)
+                c.graph = (g,)
             self.launches_per_step = int(_abi.lib.subgnn_launch_count() - n0)
             return c.loss
-        c.graph[0].replay()
-        self.allreduce_grads()
-        c.graph[1].replay()
+        if self.world_size > 1:
+            c.graph[0].replay()
+            self.allreduce_grads()
+            c.graph[1].replay()
+        else:
+            c.graph[0].replay()
         return c.loss
+
+    def loss_value(self, B=None):
+        """loss of the last enqueued train step as a Python float: waits for the stream, reads the pinned copy."""
+        c = self.context('train', B, True) if B is not None else self._last_ctx
+        torch.cuda.current_stream().synchronize()
+        return float(c.loss_host[0])
 
     def _grad_launches(self, c, st):
         call('subgnn_inc_step', ptr(self.step_dev), st)

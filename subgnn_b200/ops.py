@@ -5,7 +5,7 @@ import torch
 from . import _abi
 from ._abi import call, ptr, stream_ptr
 
-DTW_EXACT, DTW_FASTDTW_R1 = 0, 1
+DTW_EXACT, DTW_FASTDTW_R1, DTW_EXACT_THREAD = 0, 1, 2      # include/subgnn_b200.h
 
 
 def _i32(t):

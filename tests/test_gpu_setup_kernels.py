@@ -170,12 +170,42 @@ def test_degree_sequences_and_dtw(env):
     LA = torch.from_numpy(la[:20]).cuda()
     B = torch.from_numpy(sb).cuda()
     LB = torch.from_numpy(lb).cuda()
-    for mode, name in ((ops.DTW_FASTDTW_R1, 'fastdtw_r1'), (ops.DTW_EXACT, 'exact')):
+    for mode, name in ((ops.DTW_FASTDTW_R1, 'fastdtw_r1'), (ops.DTW_EXACT, 'exact'), (ops.DTW_EXACT_THREAD, 'exact')):
         got = ops.dtw_batch(A, LA, B, LB, mode).cpu().numpy()
         for i in range(20):
             for j in range(rows.shape[0]):
                 want = np.float32(og.calc_dtw(sa[i, :la[i]].tolist(), sb[j, :lb[j]].tolist(), name))
                 assert got[i, j] == want, (i, j, mode)
+
+
+@pytest.mark.parametrize('max_a', [1, 3, 4, 7, 13, 32, 33, 100, 150, 256, 300])
+def test_dtw_exact_wavefront_equals_thread_mapping(max_a):
+    """SUBGNN_DTW_EXACT (sub-warp wavefront, DP carried in registers through shuffles; every lanes-per-pair / rows-per-lane
+    instantiation) against SUBGNN_DTW_EXACT_THREAD (row-by-row, one thread per pair) and the oracle: bit-identical fp32
+    similarities, empty sequences and ragged lengths included."""
+    from oracle import gamma as og
+    from subgnn_b200 import ops
+    rnd = np.random.RandomState(100 + max_a)
+    nA, nB, max_b = 37, 53, 50
+    la = rnd.randint(0, max_a + 1, size=nA).astype(np.int32)
+    la[0], la[-1] = max_a, 0
+    lb = rnd.randint(0, max_b + 1, size=nB).astype(np.int32)
+    lb[0], lb[1], lb[2] = max_b, 0, 1
+    A = np.zeros((nA, max_a), dtype=np.int32)
+    B = np.zeros((nB, max_b), dtype=np.int32)
+    for i in range(nA):
+        A[i, :la[i]] = np.sort(rnd.randint(0, 60, size=la[i]))
+    for j in range(nB):
+        B[j, :lb[j]] = np.sort(rnd.randint(0, 400, size=lb[j]))
+    dev = [torch.from_numpy(x).cuda() for x in (A, la, B, lb)]
+    wave = ops.dtw_batch(*dev, ops.DTW_EXACT, max_len_a=max_a, max_len_b=max_b).cpu().numpy()
+    thread = ops.dtw_batch(*dev, ops.DTW_EXACT_THREAD, max_len_a=max_a, max_len_b=max_b).cpu().numpy()
+    assert np.array_equal(wave, thread)
+    assert np.all(wave[la == 0] == 0) and np.all(wave[:, lb == 0] == 0)
+    for i in rnd.choice(nA, 6, replace=False):
+        for j in rnd.choice(nB, 6, replace=False):
+            want = np.float32(og.calc_dtw(A[i, :la[i]].tolist(), B[j, :lb[j]].tolist(), 'exact'))
+            assert wave[i, j] == want, (i, j)
 
 
 def test_dtw_golden_reference_pairs():
