@@ -11,6 +11,8 @@ from pathlib import Path
 import torch
 
 _LIB_PATH = Path(__file__).resolve().parent / 'libsubgnn_b200.so'
+if os.environ.get('SUBGNN_B200_LIB'):           # tuning aid: A/B another BUILD of the same library (tools/ab_bench.sh)
+    _LIB_PATH = Path(os.environ['SUBGNN_B200_LIB']).resolve()
 
 
 class SubgnnError(RuntimeError):

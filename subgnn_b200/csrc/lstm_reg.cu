@@ -38,8 +38,15 @@ __device__ __forceinline__ unsigned drop_salt(const DropArgs& d) { return d.step
 
 // sigmoid / tanh from ex2.approx + rcp.approx: relative error ~1e-7 on the sigmoid, absolute error ~2e-7 on tanh — inside the
 // fp32 tolerance of the parity tests; 5 instructions instead of ~25 for the libm versions (40 activations per thread and step).
-__device__ __forceinline__ float sigmoid_fast(float x) { return __frcp_rn(1.f + __expf(-x)); }
-__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * __frcp_rn(1.f + __expf(2.f * x)); }
+// (rcp.approx.ftz is a bare MUFU.RCP, 1 ulp; __frcp_rn adds a fix-up sequence with a divergent slow path: BSSY / BRA / BSYNC were
+// 13 % of the forward kernel's stall samples, profiles/r01_ncu_lstm_recur_v4.txt)
+__device__ __forceinline__ float rcp_fast(float x) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ float sigmoid_fast(float x) { return rcp_fast(1.f + __expf(-x)); }
+__device__ __forceinline__ float tanh_fast(float x) { return 1.f - 2.f * rcp_fast(1.f + __expf(2.f * x)); }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ unsigned cluster_rank() {
@@ -119,11 +126,12 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[4][4], const float4 x, co
 // shared memory and each of the KS threads finishes 4/KS of the tile's sequences (activations, cell update, outputs).
 // Wp: permuted transposed weights written by lstm_prep_kernel: [dir][rank][k][half][p][4] with the 4 = (gate 2 half + {0,1}) x
 // (unit 2p + {0,1}): a thread's two float4 loads per k are contiguous across the warp (conflict free).
-template <int CL, int KS>
+template <int CL, int KS, int HC>
 __global__ void __launch_bounds__(512)
 lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float* __restrict__ OUT, float* __restrict__ CS,
-                     int n_seq, int T, int H, int steps_fwd, int steps_rev, int tile, DropArgs drop) {
+                     int n_seq, int T, int H_arg, int steps_fwd, int steps_rev, int tile, DropArgs drop) {
   sg_pdl_sync();
+  const int H = HC > 0 ? HC : H_arg;         // HC: hidden size known at compile time (32 / 64 / 128), 0: generic
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
   constexpr int NF = 4 / KS;                // sequences finished per thread
@@ -153,18 +161,32 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
   step_sync<CL>();                          // every CTA's h tile is zeroed before a peer writes into it; mbarrier init published
   bulk_wait(&wbar);
   int cur = 0;
-  for (int st = 0; st < n_steps; ++st) {
+  // gate pre-activations of the sequences this thread finishes, one step ahead: the loads of step st+1 are issued after the
+  // k loop of step st (its accumulators are dead by then) and land during the activations, the barrier and the next k loop.
+  // G is rewritten in place, but only by the thread that read the same addresses.
+  float2 gin[NF][4];
+  // element offsets of this thread's (sequence, unit pair) at t = 0; a step adds t * 2*H4 (gates) or t * 2*H (cell / output)
+  size_t g_off[NF], o_off[NF];
+#pragma unroll
+  for (int f = 0; f < NF; ++f) {
+    const int s = min(s0 + ks + f * KS, max(ns - 1, 0));
+    g_off[f] = ((size_t)(seq0 + s) * T * 2 + dir) * H4 + unit0;
+    o_off[f] = ((size_t)(seq0 + s) * T * 2 + dir) * H + unit0;
+  }
+  auto load_gin = [&](int st, float2 (&gv)[NF][4]) {
     const int t = dir == 0 ? st : T - 1 - st;
-    // gate pre-activations of the sequences this thread finishes: issued now, consumed after the k loop
-    float2 gin[NF][4];
 #pragma unroll
     for (int f = 0; f < NF; ++f) {
       const int s = s0 + ks + f * KS;
+      const float* gp = G + g_off[f] + (size_t)t * 2 * H4;
 #pragma unroll
       for (int g = 0; g < 4; ++g)
-        gin[f][g] = s < ns ? *reinterpret_cast<const float2*>(G + (((size_t)(seq0 + s) * T + t) * 2 + dir) * H4 + g * H + unit0)
-                           : make_float2(0.f, 0.f);
+        gv[f][g] = s < ns ? *reinterpret_cast<const float2*>(gp + g * H) : make_float2(0.f, 0.f);
     }
+  };
+  if (n_steps > 0) load_gin(0, gin);
+  for (int st = 0; st < n_steps; ++st) {
+    const int t = dir == 0 ? st : T - 1 - st;
     float2 acc[4][4];
 #pragma unroll
     for (int s = 0; s < 4; ++s)
@@ -193,6 +215,8 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
         *reinterpret_cast<float4*>(pw + (size_t)s * U4 + 2 * U) = make_float4(acc[s][2].x, acc[s][2].y, acc[s][3].x, acc[s][3].y);
       }
     }
+    float2 gnx[NF][4];
+    if (st + 1 < n_steps) load_gin(st + 1, gnx);
     __syncthreads();
     float* hnxt = hS + (size_t)(cur ^ 1) * tile * H;
     float2 gate_i[NF], gate_f[NF], gate_g[NF], gate_o[NF], h_new[NF];
@@ -230,14 +254,13 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
     for (int f = 0; f < NF; ++f) {
       const int s = s0 + ks + f * KS;
       if (s < ns) {
-        const size_t row = (size_t)(seq0 + s) * T + t;
-        float* gr = G + (row * 2 + dir) * H4 + unit0;
+        float* gr = G + g_off[f] + (size_t)t * 2 * H4;
         *reinterpret_cast<float2*>(gr) = gate_i[f];
         *reinterpret_cast<float2*>(gr + H) = gate_f[f];
         *reinterpret_cast<float2*>(gr + 2 * H) = gate_g[f];
         *reinterpret_cast<float2*>(gr + 3 * H) = gate_o[f];
-        *reinterpret_cast<float2*>(CS + (row * 2 + dir) * H + unit0) = c[f];
-        const size_t e = row * 2 * H + dir * H + unit0;                       // even: units come in pairs
+        const size_t e = o_off[f] + (size_t)t * 2 * H;                        // even: units come in pairs
+        *reinterpret_cast<float2*>(CS + e) = c[f];
         *reinterpret_cast<float2*>(OUT + e) = h_new[f];
         if (drop.xd) {
           float2 hd = h_new[f];
@@ -253,6 +276,10 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
     }
     step_wait<CL>();
     cur ^= 1;
+#pragma unroll
+    for (int f = 0; f < NF; ++f)
+#pragma unroll
+      for (int g = 0; g < 4; ++g) gin[f][g] = gnx[f][g];
   }
   // steps not taken (top-layer reverse direction with the 'last' aggregator): outputs are never read
 }
@@ -261,12 +288,13 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
 // BPTT.  dOUT [n_seq*T][2H]; G holds gate activations on entry and d(pre-activation) on exit.  Whh [2][4H][H] native layout.
 // block = KS * (tile/4) * 4 * (H/8) threads: thread (ks, sgroup, gate, kgroup) reduces over a 1/KS slice of the U columns of one
 // gate for 4 sequences x 8 hidden units (k in kg*4..+3 and H/2 + kg*4..+3: both weight loads contiguous across the warp).
-template <int CL, int KS>
+template <int CL, int KS, int HC>
 __global__ void __launch_bounds__(512)
 lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
-                     const float* __restrict__ dOUT, int n_seq, int T, int H, int steps_fwd, int steps_rev, int zero_untaken,
+                     const float* __restrict__ dOUT, int n_seq, int T, int H_arg, int steps_fwd, int steps_rev, int zero_untaken,
                      float* __restrict__ db_ih, float* __restrict__ db_hh, int tile, DropArgs drop) {
   sg_pdl_sync();
+  const int H = HC > 0 ? HC : H_arg;
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
   const int U = H / CL, U4 = 4 * U, H4 = 4 * H;
@@ -301,51 +329,86 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
   bulk_wait(&wbar);
   const int n_el = ns * U;
   const unsigned dsalt = drop.p > 0.f ? drop_salt(drop) : 0u;
-  for (int st = n_steps - 1; st >= 0; --st) {
+  // Global operands of the element-wise BPTT step (gate activations, cell states, output gradient), one step ahead: the loads of
+  // step st-1 are issued at the end of the element-wise phase of step st and land during the bias / matvec phases and the two
+  // barriers.  G is rewritten in place, but only by the thread that read the same addresses (element -> thread map is fixed).
+  constexpr int NIT = (4 + KS * CL - 1) / (KS * CL);     // element-wise iterations per thread: n_el <= tile*U = NIT * 2 * blockDim
+  struct Pre { float ig, fg, gg, og, cc, cp, dho; };
+  Pre pv[NIT][2];
+  // time-invariant part of the element -> address maps (the divisions by U happen once, not every step)
+  bool on[NIT][2];
+  int dg_off[NIT][2];                      // s * U4 + u: this element's column in dgS
+  size_t g_off[NIT][2], o_off[NIT][2];     // element offsets at t = 0 into G, and into CS / OUT / dOUT
+#pragma unroll
+  for (int it = 0; it < NIT; ++it) {
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+      const int e = tid + (it * 2 + q) * (int)blockDim.x;
+      on[it][q] = e < n_el;
+      const int s = on[it][q] ? e / U : 0, u = on[it][q] ? e % U : 0;
+      const int ug = (int)rank * U + u;
+      dg_off[it][q] = s * U4 + u;
+      g_off[it][q] = ((size_t)(seq0 + s) * T * 2 + dir) * H4 + ug;
+      o_off[it][q] = ((size_t)(seq0 + s) * T * 2 + dir) * H + ug;
+    }
+  }
+  auto load_step = [&](int st) {
     const int t = dir == 0 ? st : T - 1 - st;
     const int t_prev = dir == 0 ? t - 1 : t + 1;
-    // ---- element-wise BPTT step over this CTA's (sequence, unit) pairs, two per iteration with all loads issued up front ----
-    for (int e0 = tid; e0 < n_el; e0 += 2 * blockDim.x) {
-      float ig[2], fg[2], gg[2], og[2], cc[2], cp[2], dho[2], dhr[2];
-      size_t gbase[2];
-      bool on[2];
+#pragma unroll
+    for (int it = 0; it < NIT; ++it) {
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        const int e = e0 + q * blockDim.x;
-        on[q] = e < n_el;
-        const int s = on[q] ? e / U : 0, u = on[q] ? e % U : 0;
-        const int ug = (int)rank * U + u;
-        const size_t row = (size_t)(seq0 + s) * T + t;
-        gbase[q] = (row * 2 + dir) * H4 + ug;
-        ig[q] = G[gbase[q]]; fg[q] = G[gbase[q] + H]; gg[q] = G[gbase[q] + 2 * H]; og[q] = G[gbase[q] + 3 * H];
-        cc[q] = CS[(row * 2 + dir) * H + ug];
-        cp[q] = st > 0 ? CS[((((size_t)(seq0 + s) * T + t_prev) * 2) + dir) * H + ug] : 0.f;
-        dho[q] = dOUT[row * 2 * H + dir * H + ug];
-        // dOUT holds the gradient w.r.t. the DROPPED-OUT copy of this layer's output: apply the same mask
-        if (drop.p > 0.f) dho[q] *= sg_dropout_scale(drop.seed, dsalt, (uint64_t)(row * 2 * H + dir * H + ug), drop.p);
-        float r = 0.f;
+        const float* gp = G + g_off[it][q] + (size_t)t * 2 * H4;
+        const size_t oe = o_off[it][q] + (size_t)t * 2 * H;
+        Pre& v = pv[it][q];
+        v.ig = gp[0]; v.fg = gp[H]; v.gg = gp[2 * H]; v.og = gp[3 * H];
+        v.cc = CS[oe];
+        v.cp = st > 0 ? CS[o_off[it][q] + (size_t)t_prev * 2 * H] : 0.f;
+        v.dho = dOUT[oe];
+      }
+    }
+  };
+  if (n_steps > 0) load_step(n_steps - 1);
+  for (int st = n_steps - 1; st >= 0; --st) {
+    const int t = dir == 0 ? st : T - 1 - st;
+    // ---- element-wise BPTT step over this CTA's (sequence, unit) pairs, two per iteration ----
 #pragma unroll
-        for (int sl = 0; sl < SLOTS; ++sl) r += red[(size_t)sl * tile * U + s * U + u];
+    for (int it = 0; it < NIT; ++it) {
+      if (!on[it][0]) break;
+      float dhr[2], dho[2];
+#pragma unroll
+      for (int q = 0; q < 2; ++q) {
+        const int e = tid + (it * 2 + q) * (int)blockDim.x;
+        dho[q] = pv[it][q].dho;
+        // dOUT holds the gradient w.r.t. the DROPPED-OUT copy of this layer's output: apply the same mask
+        if (drop.p > 0.f) dho[q] *= sg_dropout_scale(drop.seed, dsalt, (uint64_t)(o_off[it][q] + (size_t)t * 2 * H), drop.p);
+        float r = 0.f;
+        const float* rp = red + (on[it][q] ? e : 0);
+#pragma unroll
+        for (int sl = 0; sl < SLOTS; ++sl) r += rp[(size_t)sl * tile * U];
         dhr[q] = r;
       }
 #pragma unroll
       for (int q = 0; q < 2; ++q) {
-        if (!on[q]) continue;
-        const int e = e0 + q * blockDim.x;
-        const int s = e / U, u = e % U;
-        const float tc = tanhf(cc[q]);
+        if (!on[it][q]) continue;
+        const int e = tid + (it * 2 + q) * (int)blockDim.x;
+        const Pre& v = pv[it][q];
+        const float tc = tanh_fast(v.cc);               // the forward kernel's tanh: same value as in h = o * tanh(c)
         const float dh = dho[q] + dhr[q];
-        const float dc = dc_rec[e] + dh * og[q] * (1.f - tc * tc);
-        const float dai = dc * gg[q] * ig[q] * (1.f - ig[q]);
-        const float daf = dc * cp[q] * fg[q] * (1.f - fg[q]);
-        const float dag = dc * ig[q] * (1.f - gg[q] * gg[q]);
-        const float dao = dh * tc * og[q] * (1.f - og[q]);
-        dc_rec[e] = dc * fg[q];
-        float* dr = dgS + (size_t)s * U4 + u;
+        const float dc = dc_rec[e] + dh * v.og * (1.f - tc * tc);
+        const float dai = dc * v.gg * v.ig * (1.f - v.ig);
+        const float daf = dc * v.cp * v.fg * (1.f - v.fg);
+        const float dag = dc * v.ig * (1.f - v.gg * v.gg);
+        const float dao = dh * tc * v.og * (1.f - v.og);
+        dc_rec[e] = dc * v.fg;
+        float* dr = dgS + dg_off[it][q];
         dr[0] = dai; dr[U] = daf; dr[2 * U] = dag; dr[3 * U] = dao;
-        G[gbase[q]] = dai; G[gbase[q] + H] = daf; G[gbase[q] + 2 * H] = dag; G[gbase[q] + 3 * H] = dao;
+        float* gp = G + g_off[it][q] + (size_t)t * 2 * H4;
+        gp[0] = dai; gp[H] = daf; gp[2 * H] = dag; gp[3 * H] = dao;
       }
     }
+    if (st > 0) load_step(st - 1);
     step_sync<CL>();                        // dgS complete; every CTA of the cluster has finished reading its reduction slots
     // ---- bias gradient: column sums over the tile's sequences (rows s >= ns of dgS stay zero) ----
     for (int col = tid; col < U4; col += blockDim.x) {
@@ -441,14 +504,14 @@ int pick_tile(int n_seq, int cl, int threads_per_4seq, size_t smem_fixed, size_t
   return best;
 }
 
-template <int CL, int KS>
+template <int CL, int KS, int HC>
 int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, DropArgs drop, cudaStream_t st) {
   const int U = H / CL;
   const size_t fixed = (size_t)H * 4 * U * sizeof(float), per_seq = (size_t)(2 * H + KS * 4 * U) * sizeof(float);
   const int tile = pick_tile(n_seq, CL, KS * (U / 2), fixed, per_seq);
   if (tile < 0) { subgnn_set_error("lstm_fwd_tile: no feasible tile"); return SUBGNN_ERR_ARG; }
   const size_t smem = fixed + per_seq * tile;
-  cudaFuncSetAttribute(lstm_fwd_tile_kernel<CL, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(lstm_fwd_tile_kernel<CL, KS, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sg_div_up(n_seq, tile) * CL, 2, 1);
   cfg.blockDim = dim3(KS * (U / 2) * (tile / 4), 1, 1);
@@ -461,11 +524,11 @@ int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int 
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile, drop);
+  cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS, HC>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile, drop);
   return subgnn_check_launch("lstm_fwd_tile_kernel");
 }
 
-template <int CL, int KS>
+template <int CL, int KS, int HC>
 int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
                int zero_untaken, float* db_ih, float* db_hh, DropArgs drop, cudaStream_t st) {
   const int U = H / CL;
@@ -473,7 +536,7 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   const int tile = pick_tile(n_seq, CL, KS * 4 * (H / 8), fixed, per_seq);
   if (tile < 0) { subgnn_set_error("lstm_bwd_tile: no feasible tile"); return SUBGNN_ERR_ARG; }
   const size_t smem = fixed + per_seq * tile;
-  cudaFuncSetAttribute(lstm_bwd_tile_kernel<CL, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaFuncSetAttribute(lstm_bwd_tile_kernel<CL, KS, HC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(sg_div_up(n_seq, tile) * CL, 2, 1);
   cfg.blockDim = dim3(KS * (H / 8) * tile, 1, 1);
@@ -486,7 +549,7 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
-  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile, drop);
+  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS, HC>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile, drop);
   return subgnn_check_launch("lstm_bwd_tile_kernel");
 }
 
@@ -499,16 +562,24 @@ int lstm_reg_cluster(int H) { return H <= 64 ? 1 : 2; }
 int lstm_reg_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int T, int H, int sf, int sr, float* xdrop, float p,
                  unsigned long long seed, unsigned salt, const int* step_dev, cudaStream_t st) {
   const DropArgs drop = {xdrop, p, seed, salt, step_dev};
-  if (lstm_reg_cluster(H) == 2) return launch_fwd<2, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
-  if (H % 16 == 0) return launch_fwd<1, 4>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
-  return launch_fwd<1, 2>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (H == 128) return launch_fwd<2, 2, 128>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (H == 64) return launch_fwd<1, 4, 64>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (H == 32) return launch_fwd<1, 4, 32>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (lstm_reg_cluster(H) == 2) return launch_fwd<2, 2, 0>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  if (H % 16 == 0) return launch_fwd<1, 4, 0>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
+  return launch_fwd<1, 2, 0>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
 }
 
 int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
                  int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed, unsigned salt, const int* step_dev,
                  cudaStream_t st) {
   const DropArgs drop = {nullptr, p, seed, salt, step_dev};
-  if (lstm_reg_cluster(H) == 2) return launch_bwd<2, 1>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
-  if (H % 16 == 0) return launch_bwd<1, 4>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
-  return launch_bwd<1, 2>(G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st);
+#define SG_BWD_ARGS G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st
+  if (H == 128) return launch_bwd<2, 1, 128>(SG_BWD_ARGS);
+  if (H == 64) return launch_bwd<1, 4, 64>(SG_BWD_ARGS);
+  if (H == 32) return launch_bwd<1, 4, 32>(SG_BWD_ARGS);
+  if (lstm_reg_cluster(H) == 2) return launch_bwd<2, 1, 0>(SG_BWD_ARGS);
+  if (H % 16 == 0) return launch_bwd<1, 4, 0>(SG_BWD_ARGS);
+  return launch_bwd<1, 2, 0>(SG_BWD_ARGS);
+#undef SG_BWD_ARGS
 }

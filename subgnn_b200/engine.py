@@ -13,6 +13,7 @@ Data layout in HBM:
   * per step: only the batch's subgraph indices travel host -> device.
 """
 import ctypes as C
+import os
 import math
 
 import numpy as np
@@ -23,6 +24,12 @@ from ._abi import ModelDesc, call, ptr
 
 CHANNELS = ('neighborhood', 'position', 'structure')
 SIDES = ('internal', 'border')
+
+
+def _flag(env, default):
+    """tuning switch: environment variable (0/1) over the hyper-parameter / built-in default."""
+    v = os.environ.get(env)
+    return bool(default) if v is None else v not in ('0', '', 'false')
 
 
 def _align(n, a=4):
@@ -621,9 +628,16 @@ class Engine:
     # anchor_patch_samplers.py:381-386), the neighbourhood chains only on the batch: they are launched on two streams
     # (fork / join with events, captured into the step graph as parallel branches).
     def _side_stream(self):
+        # optional high priority for the LSTM chain (the critical path of the step).  Measured on B200 (tools/ab_bench.sh, PPI-BP
+        # shape, same box): no effect (0.4362 -> 0.4366 ms/step), so it is off by default; kept as a tuning switch
         if getattr(self, '_side', None) is None:
-            self._side = torch.cuda.Stream(device=self.device)
+            self._side = torch.cuda.Stream(device=self.device, priority=-1 if _flag('SUBGNN_CHAIN_PRIORITY', self.hp.get('b200_chain_priority', False)) else 0)
         return self._side
+
+    def _prep_stream(self):
+        if getattr(self, '_prep', None) is None:
+            self._prep = torch.cuda.Stream(device=self.device)
+        return self._prep
 
     def _forward_launches(self, c, st, zero_grads=False):
         main = torch.cuda.current_stream()
@@ -631,6 +645,7 @@ class Engine:
         if fork:                                  # the LSTM chain is the longest of the step: it starts before the zero fills
             side = self._side_stream()
             side.wait_stream(main)
+            self._prep_stream().wait_stream(main)
             with torch.cuda.stream(side):
                 self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
         if zero_grads:
@@ -639,9 +654,17 @@ class Engine:
             call('subgnn_fill_zero', ptr(c.fwd_zero), c.fwd_zero.numel(), st)
         if self.lstm is not None and not fork:
             self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
+        pfork = fork and _flag('SUBGNN_PREP_BRANCH', False)
+        if pfork:                                 # tuning switch (off: measured +4 us/step): weight transposes on their own branch
+            prep = self._prep_stream()
+            with torch.cuda.stream(prep):
+                call('subgnn_model_prep_weights', c.dptr, prep.cuda_stream)
         call('subgnn_model_prep_batch', c.dptr, st)
-        call('subgnn_model_prep_weights', c.dptr, st)
+        if not pfork:
+            call('subgnn_model_prep_weights', c.dptr, st)
         call('subgnn_model_q_fwd_part', c.dptr, 1, st)               # position anchors
+        if pfork:
+            main.wait_stream(prep)
         call('subgnn_model_rows_fwd', c.dptr, 1, st)                 # pooling + neighbourhood channel
         if fork:
             main.wait_stream(side)
