@@ -266,8 +266,32 @@ def cpu_baseline(hp, g, prepared, seconds, n_threads=None, anomaly=False):
 
 
 # ----------------------------------------------------------------------------------------------------
+_RESULT_FD = None
+
+
+def _claim_stdout():
+    """stdout carries exactly ONE JSON line (rank 0).  Native libraries write there too (NCCL prints its version banner to fd 1
+    whatever NCCL_DEBUG says under torchrun), so fd 1 is pointed at stderr for the life of the process and the result line is
+    written to a private duplicate of the original stdout."""
+    global _RESULT_FD
+    if _RESULT_FD is None:
+        sys.stdout.flush()
+        _RESULT_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + '\n').encode()
+    if _RESULT_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_RESULT_FD, data)
+
+
 def main():
     args = parse()
+    _claim_stdout()
     rank = int(os.environ.get('RANK', 0))
     local_rank = int(os.environ.get('LOCAL_RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -278,7 +302,7 @@ def main():
             return 0
         dev = 'cuda:0' if torch.cuda.is_available() else None
         if dev is None:
-            print(json.dumps({'impl': 'reference', 'unavailable': 'workload preparation needs the CUDA setup kernels; no GPU visible'}))
+            emit({'impl': 'reference', 'unavailable': 'workload preparation needs the CUDA setup kernels; no GPU visible'})
             return 0
         torch.cuda.set_device(0)
         hp, g, prepared, _ = build_workload(args.workload, dev, args.batch_size)
@@ -288,7 +312,7 @@ def main():
                 'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
                 'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_gpu': hp['batch_size'], 'channels': 'N+P+S'},
                 'cpu_baseline': info, 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        print(json.dumps(line))
+        emit(line)
         return 0
 
     assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
@@ -296,8 +320,6 @@ def main():
     dev = 'cuda:%d' % local_rank
     if world > 1:
         import torch.distributed as dist
-        if os.environ.get('NCCL_DEBUG', '').upper() in ('', 'VERSION'):
-            os.environ['NCCL_DEBUG'] = 'WARN'          # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
         dist.init_process_group('nccl', device_id=torch.device(dev))
     from subgnn_b200 import _abi
     from subgnn_b200.engine import Engine
@@ -484,7 +506,7 @@ def main():
                        'prepare_data_s': round(prep_s, 2)},
             'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
             'breakdown_ms': breakdown, 'final_loss': final_loss, 'wall_s_timed_region': wall}
-    print(json.dumps(line))
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
     return 0

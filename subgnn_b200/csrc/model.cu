@@ -297,18 +297,24 @@ struct RowSmem {
   float* x0;      // [D]
   float* h;       // [2][D]
   float* in;      // [2][2D]   [h ; agg]
-  float* part;    // [2][SIDE_WARPS][D] partial aggregates / partial matvec sums
+  float* part;    // [2][SIDE_WARPS][D] partial matvec sums
+  float* aggl;    // [L][2][D]              similarity-weighted aggregates of every layer
+  float* partl;   // [L][2][SIDE_WARPS][D]  their per-warp partials
 };
 
-__device__ __forceinline__ RowSmem row_smem(float* sm, int D) {
+__device__ __forceinline__ RowSmem row_smem(float* sm, int D, int L) {
   RowSmem r;
   r.x0 = sm;
   r.h = r.x0 + D;
   r.in = r.h + 2 * D;
   r.part = r.in + 4 * D;
+  r.aggl = r.part + 2 * SIDE_WARPS * D;
+  r.partl = r.aggl + (size_t)L * 2 * D;
   return r;
 }
-static size_t row_smem_bytes(int D) { return (size_t)(D + 2 * D + 4 * D + 2 * SIDE_WARPS * D + 16) * sizeof(float); }
+static size_t row_smem_bytes(int D, int L) {
+  return (size_t)(D + 2 * D + 4 * D + 2 * SIDE_WARPS * D + L * 2 * D + L * 2 * SIDE_WARPS * D + 16) * sizeof(float);
+}
 
 // phases: bit 0 = pooling + neighbourhood channel, bit 1 = position / structure property-aware outputs (needs q)
 template <int DPL>
@@ -316,7 +322,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
   sg_pdl_sync();
   extern __shared__ float sm[];
   const int D = d.D;
-  const RowSmem S = row_smem(sm, D);
+  const RowSmem S = row_smem(sm, D, d.L);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int side = warp / SIDE_WARPS, sw = warp % SIDE_WARPS, st = tid % SIDE_THREADS;
   const int R = d.meta[0], maxlen = d.meta[1];
@@ -361,51 +367,65 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
         S.h[side * D + k] = v;
         d.Nh[((size_t)(0 * 2 + side) * d.R_cap + r) * D + k] = v;
       }
-      __syncthreads();
+      // ---- gather-scale-reduce of EVERY layer first: agg_l = sum_a s_a E[id_a] depends on the anchors, the similarities and the
+      // embedding table only, not on the previous layer's output, so the L x 2 gathers run back to back (8 rows in flight per
+      // warp, ids / similarities of a warp's anchors fetched with one coalesced load and handed out by shuffles) and only the
+      // L small projections remain a dependent chain.  Summation order per warp is unchanged (anchors in increasing order).
       for (int l = 0; l < d.L; ++l) {
         const int* ids = d.n_ids[side] + ((size_t)l * d.n_cc + g) * A;
         const float* sims = d.n_sim[side] + ((size_t)l * d.n_cc + g) * A;
         float agg[DPL];
 #pragma unroll
         for (int q = 0; q < DPL; ++q) agg[q] = 0.f;
-        int a = sw;
-        for (; a + 3 * SIDE_WARPS < A; a += 4 * SIDE_WARPS) {       // 4 gathers in flight per warp, 16 per side
-          const int i0 = ids[a], i1 = ids[a + SIDE_WARPS], i2 = ids[a + 2 * SIDE_WARPS], i3 = ids[a + 3 * SIDE_WARPS];
-          const float s0 = sims[a], s1 = sims[a + SIDE_WARPS], s2 = sims[a + 2 * SIDE_WARPS], s3 = sims[a + 3 * SIDE_WARPS];
+        const int n_w = A > sw ? (A - sw + SIDE_WARPS - 1) / SIDE_WARPS : 0;       // anchors sw, sw + SIDE_WARPS, ... of this warp
+        for (int base = 0; base < n_w; base += 32) {
+          const int mine = base + lane;
+          const int id_l = mine < n_w ? ids[sw + mine * SIDE_WARPS] : 0;
+          const float s_l = mine < n_w ? sims[sw + mine * SIDE_WARPS] : 0.f;
+          const int cnt = min(32, n_w - base);
+          for (int i = 0; i < cnt; i += 8) {
+            int id8[8];
+            float s8[8], v8[8][DPL];
 #pragma unroll
-          for (int q = 0; q < DPL; ++q) {
-            const int k = lane + 32 * q;
-            if (k < D) {
-              const float v0 = i0 ? d.E[(size_t)i0 * D + k] : 0.f, v1 = i1 ? d.E[(size_t)i1 * D + k] : 0.f;
-              const float v2 = i2 ? d.E[(size_t)i2 * D + k] : 0.f, v3 = i3 ? d.E[(size_t)i3 * D + k] : 0.f;
-              agg[q] = fmaf(s0, v0, agg[q]); agg[q] = fmaf(s1, v1, agg[q]);
-              agg[q] = fmaf(s2, v2, agg[q]); agg[q] = fmaf(s3, v3, agg[q]);
+            for (int u = 0; u < 8; ++u) {
+              id8[u] = __shfl_sync(0xffffffffu, id_l, (i + u) & 31);
+              s8[u] = __shfl_sync(0xffffffffu, s_l, (i + u) & 31);
+              if (i + u >= cnt) id8[u] = 0;
             }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+#pragma unroll
+              for (int q = 0; q < DPL; ++q) {
+                const int k = lane + 32 * q;
+                v8[u][q] = (id8[u] && k < D) ? d.E[(size_t)id8[u] * D + k] : 0.f;
+              }
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+              if (i + u < cnt)
+#pragma unroll
+                for (int q = 0; q < DPL; ++q) agg[q] = fmaf(s8[u], v8[u][q], agg[q]);
           }
-        }
-        for (; a < A; a += SIDE_WARPS) {
-          const int i0 = ids[a];
-          const float s0 = sims[a];
-          if (i0)
-#pragma unroll
-            for (int q = 0; q < DPL; ++q) {
-              const int k = lane + 32 * q;
-              if (k < D) agg[q] = fmaf(s0, d.E[(size_t)i0 * D + k], agg[q]);
-            }
         }
 #pragma unroll
         for (int q = 0; q < DPL; ++q) {
           const int k = lane + 32 * q;
-          if (k < D) S.part[(side * SIDE_WARPS + sw) * D + k] = agg[q];
+          if (k < D) S.partl[((size_t)(l * 2 + side) * SIDE_WARPS + sw) * D + k] = agg[q];
         }
-        __syncthreads();
-        for (int k = st; k < D; k += SIDE_THREADS) {
-          float v = 0.f;
+      }
+      __syncthreads();
+      for (int idx = st; idx < d.L * D; idx += SIDE_THREADS) {
+        const int l = idx / D, k = idx % D;
+        float v = 0.f;
 #pragma unroll
-          for (int w = 0; w < SIDE_WARPS; ++w) v += S.part[(side * SIDE_WARPS + w) * D + k];
+        for (int w = 0; w < SIDE_WARPS; ++w) v += S.partl[((size_t)(l * 2 + side) * SIDE_WARPS + w) * D + k];
+        S.aggl[(size_t)(l * 2 + side) * D + k] = v;
+        d.Nagg[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = v;
+      }
+      __syncthreads();
+      for (int l = 0; l < d.L; ++l) {
+        for (int k = st; k < D; k += SIDE_THREADS) {
           S.in[side * 2 * D + k] = S.h[side * D + k];
-          S.in[side * 2 * D + D + k] = v;
-          d.Nagg[((size_t)(l * 2 + side) * d.R_cap + r) * D + k] = v;
+          S.in[side * 2 * D + D + k] = S.aggl[(size_t)(l * 2 + side) * D + k];
         }
         __syncthreads();
         if (d.use_proj) {
@@ -417,8 +437,8 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
             const int j = idx % D, part = idx / D;
             const int k0 = 2 * D * part / parts, k1 = 2 * D * (part + 1) / parts;
             float acc = 0.f;
-#pragma unroll 4
-            for (int kk = k0; kk < k1; ++kk) acc = fmaf(inp[kk], __ldg(wt + (size_t)kk * D + j), acc);
+#pragma unroll 16
+            for (int kk = k0; kk < k1; ++kk) acc = fmaf(inp[kk], __ldg(wt + (size_t)kk * D + j), acc);   // 16 weight loads in flight
             S.part[(side * SIDE_WARPS + part) * D + j] = acc;
           }
           __syncthreads();
@@ -869,7 +889,15 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) 
   if (rc) return rc;
   if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
   if (!phases) return SUBGNN_OK;
-  const size_t smem = row_smem_bytes(d->D);
+  const size_t smem = row_smem_bytes(d->D, d->L);
+  if (smem > 48 * 1024) {                       // deep / wide configurations: opt in to the large dynamic shared-memory window
+    SG_REQUIRE(smem <= 200 * 1024, "n_layers x node_embed_size too large for the row kernel's shared-memory aggregates");
+    const int dpl = (d->D + 31) / 32;
+    if (dpl <= 1) cudaFuncSetAttribute(row_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (dpl <= 2) cudaFuncSetAttribute(row_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else if (dpl <= 4) cudaFuncSetAttribute(row_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else cudaFuncSetAttribute(row_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  }
   DISPATCH_DPL(d->D, row_fwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), smem, (cudaStream_t)stream, *d, phases);
   return subgnn_check_launch("row_fwd_kernel");
 }

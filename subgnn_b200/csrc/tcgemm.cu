@@ -16,6 +16,7 @@
 //   K = 8 tf32 = 32 B, so MMA k of a 32-wide K block starts 2*k 16-B units further.
 //   Accumulator of an M = 128, cta_group::1 MMA: row m <-> TMEM lane m, column n <-> TMEM column n.
 #include "common.cuh"
+#include <cstdlib>
 #include "../../include/subgnn_b200.h"
 
 #define TC_M 128
@@ -170,15 +171,15 @@ struct MNMajorStager {
 // consumes the result.  The epilogue transposes each warp's 32 x 32 TMEM slab through shared memory so that 8 lanes
 // cover 128 contiguous bytes of one output row (coalesced 16-byte stores / vector atomics).
 #define TC_EPI_LD 36      // padded row length (floats) of the per-warp transposition slab: conflict-free float4 in both directions
-template <int N_TILE, class LoadA, class LoadB, class StoreA, class StoreB, class Epi>
+// STAGES = 2 double-buffers the operand tiles: the threads split / store block kb+1 while the tensor core still works on block
+// kb (the single-buffered loop serialises load latency, store and MMA of every block: ~1.5 us per 32-wide block measured
+// in the step timeline, profiles/r01_timeline_ppi_bp.txt); STAGES = 1 keeps 3 CTAs per SM for the short reductions.
+template <int N_TILE, int STAGES, class LoadA, class LoadB, class StoreA, class StoreB, class Epi>
 __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB load_b, StoreA store_a, StoreB store_b, Epi epi) {
   extern __shared__ unsigned char smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  unsigned char* a_hi = base;
-  unsigned char* a_lo = a_hi + TC_M * 128;
-  unsigned char* b_hi = a_lo + TC_M * 128;
-  unsigned char* b_lo = b_hi + N_TILE * 128;
-  __shared__ uint64_t mma_bar;
+  constexpr int STAGE_BYTES = 2 * TC_M * 128 + 2 * N_TILE * 128;
+  __shared__ uint64_t mma_bar[STAGES];
   __shared__ uint32_t tmem_base_s;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = (kr1 - kr0 + TC_KB - 1) / TC_KB;
@@ -188,7 +189,8 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB lo
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   if (threadIdx.x == 0) {
-    mbar_init(&mma_bar, 1);
+#pragma unroll
+    for (int i = 0; i < STAGES; ++i) mbar_init(&mma_bar[i], 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -197,7 +199,13 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB lo
   const uint32_t tmem_d = tmem_base_s;
   const uint32_t idesc = umma_idesc_tf32(TC_M, N_TILE);
   for (int kb = 0; kb < n_kb; ++kb) {
-    if (kb > 0) mbar_wait(&mma_bar, (uint32_t)((kb - 1) & 1));        // MMAs of the previous block have consumed the tiles
+    const int stg = kb % STAGES;
+    unsigned char* a_hi = base + stg * STAGE_BYTES;
+    unsigned char* a_lo = a_hi + TC_M * 128;
+    unsigned char* b_hi = a_lo + TC_M * 128;
+    unsigned char* b_lo = b_hi + N_TILE * 128;
+    // the MMAs of block kb - STAGES (the previous user of this buffer, completion kb/STAGES - 1 of its barrier) have consumed the tiles
+    if (kb >= STAGES) mbar_wait(&mma_bar[stg], (uint32_t)((kb / STAGES - 1) & 1));
     store_a(a_hi, a_lo);
     store_b(b_hi, b_lo);
     if (kb + 1 < n_kb) { load_a(kr0 + (kb + 1) * TC_KB); load_b(kr0 + (kb + 1) * TC_KB); }   // in flight while the tensor core works
@@ -214,10 +222,10 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB lo
         umma_tf32(tmem_d, dal + adv, dbh + adv, idesc, 1u);
         umma_tf32(tmem_d, dah + adv, dbl + adv, idesc, 1u);
       }
-      umma_commit(&mma_bar);                                            // arrives when every MMA issued so far has completed
+      umma_commit(&mma_bar[stg]);                                       // arrives when every MMA issued so far has completed
     }
   }
-  if (n_kb > 0) mbar_wait(&mma_bar, (uint32_t)((n_kb - 1) & 1));
+  if (n_kb > 0) mbar_wait(&mma_bar[(n_kb - 1) % STAGES], (uint32_t)(((n_kb - 1) / STAGES) & 1));
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   // epilogue: warp w owns TMEM lanes (= tile rows) 32w .. 32w+31, 32 columns per tcgen05.ld; the operand tiles are free now
   float* slab = reinterpret_cast<float*>(base) + warp * (32 * TC_EPI_LD);
@@ -253,7 +261,7 @@ __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB lo
 }
 
 // y[m][n] = act(sum_k X[row(m)][k] W[n][k] + bias[n])      (same contract as subgnn_linear_fwd)
-template <int N_TILE>
+template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict__ ids, const float* __restrict__ w, int ldw,
                      const float* __restrict__ bias, float* __restrict__ y, int ldy, int M, int N, int K, int relu) {
@@ -270,7 +278,7 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
     return x + row * ldx;
   });
   sb.init(K, [&](int r) -> const float* { return n0 + r < N ? w + (long long)(n0 + r) * ldw : nullptr; });
-  tc_tile<N_TILE>(
+  tc_tile<N_TILE, STAGES>(
       0, K, [&](int k0) { sa.load(k0); }, [&](int k0) { sb.load(k0); },
       [&](unsigned char* hi, unsigned char* lo) { sa.store(hi, lo); }, [&](unsigned char* hi, unsigned char* lo) { sb.store(hi, lo); },
       [&](int r, int c, float4 v) {
@@ -291,7 +299,7 @@ tc_linear_fwd_kernel(const float* __restrict__ x, int ldx, const int* __restrict
 // dx[row(m)][k] (+)= sum_n dy[m][n] W[n][k]       (same contract as subgnn_linear_bwd_input)
 // grid.z splits the reduction over n; with more than one split every output is added atomically (dx must then hold the
 // value to accumulate onto: the host wrapper only splits in scatter / accumulate mode).
-template <int N_TILE>
+template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ w, int ldw, float* __restrict__ dx, int lddx,
                            const int* __restrict__ scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
@@ -303,7 +311,7 @@ tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* _
   KMajorStager<TC_M> sa;
   MNMajorStager<N_TILE> sb;
   sa.init(nr1, [&](int r) -> const float* { return m0 + r < M ? dy + (long long)(m0 + r) * ldy : nullptr; });
-  tc_tile<N_TILE>(
+  tc_tile<N_TILE, STAGES>(
       nr0, nr1, [&](int n0) { sa.load(n0); },
       [&](int n0) {                                                    // B[k][n] = W[n][k]: rows k contiguous in memory for fixed n
         sb.load(n0, K - k0o, [&](int n) -> const float* { return n < nr1 ? w + (long long)n * ldw + k0o : nullptr; });
@@ -335,7 +343,7 @@ tc_linear_bwd_input_kernel(const float* __restrict__ dy, int ldy, const float* _
 }
 
 // dW[n][k] += sum_m dy[m][n] X[row(m)][k]          (same contract as subgnn_linear_bwd_weight, bias gradient excluded)
-template <int N_TILE>
+template <int N_TILE, int STAGES>
 __global__ void __launch_bounds__(TC_THREADS)
 tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* __restrict__ x, int ldx, const int* __restrict__ ids,
                             float* __restrict__ dw, int lddw, int M, int N, int K, int m_chunk) {
@@ -345,7 +353,7 @@ tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* 
   if (mr0 >= mr1) return;
   MNMajorStager<TC_M> sa;
   MNMajorStager<N_TILE> sb;
-  tc_tile<N_TILE>(
+  tc_tile<N_TILE, STAGES>(
       mr0, mr1,
       [&](int mb) {                                                    // A[n][m] = dy[m][n]
         sa.load(mb, N - n0, [&](int m) -> const float* { return m < mr1 ? dy + (long long)m * ldy + n0 : nullptr; });
@@ -371,14 +379,35 @@ tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* 
 }
 
 static bool tc_aligned(const void* p, int ld) { return (ld % 4) == 0 && (((size_t)p) & 15) == 0; }
-template <int NT> static size_t tc_smem() { return (size_t)(2 * TC_M * 128 + 2 * NT * 128) + 1024; }
+template <int NT, int STAGES> static size_t tc_smem() { return (size_t)STAGES * (2 * TC_M * 128 + 2 * NT * 128) + 1024; }
 
-template <int NT>
-static void launch_bwd_input(dim3 grid, cudaStream_t st, const float* dy, int ldy, const float* w, int ldw, float* dx, int lddx,
-                             const int* scatter_ids, int M, int N, int K, int accumulate, int n_chunk) {
-  cudaFuncSetAttribute(tc_linear_bwd_input_kernel<NT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<NT>());
-  sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_input_kernel<NT>, grid, dim3(TC_THREADS), tc_smem<NT>(), st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+// tuning aids (tools/gemm_bench.py sweeps them): SUBGNN_TC_STAGES, SUBGNN_TC_NT_{FWD,BWI,BWW}, SUBGNN_TC_SPLITS_{BWI,BWW}
+static int tc_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e && *e ? atoi(e) : dflt;
 }
+// operand buffers: measured on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep_ppi_bp.txt) double buffering never pays at the
+// LSTM shapes — these GEMMs stream 10-20 MB per launch and are bound by loads in flight per SM, which the extra 64 KB of
+// shared memory per CTA reduces (fewer resident CTAs) — so one buffer is the default and two stay available as a switch
+static int tc_stages(int n_kb) { (void)n_kb; return tc_env("SUBGNN_TC_STAGES", 1) >= 2 ? 2 : 1; }
+
+#define TC_LAUNCH(KERNEL, NT, STAGES, grid, st, ...)                                                                          \
+  do {                                                                                                                        \
+    cudaFuncSetAttribute(KERNEL<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<NT, STAGES>());          \
+    sg_launch_pdl<SG_PDL_GEMM>(KERNEL<NT, STAGES>, grid, dim3(TC_THREADS), tc_smem<NT, STAGES>(), st, __VA_ARGS__);             \
+  } while (0)
+#define TC_DISPATCH(KERNEL, nt, stages, grid, st, ...)                                                                        \
+  do {                                                                                                                        \
+    if (stages == 2) {                                                                                                        \
+      if (nt == 32) TC_LAUNCH(KERNEL, 32, 2, grid, st, __VA_ARGS__);                                                          \
+      else if (nt == 64) TC_LAUNCH(KERNEL, 64, 2, grid, st, __VA_ARGS__);                                                     \
+      else TC_LAUNCH(KERNEL, 128, 2, grid, st, __VA_ARGS__);                                                                  \
+    } else {                                                                                                                  \
+      if (nt == 32) TC_LAUNCH(KERNEL, 32, 1, grid, st, __VA_ARGS__);                                                          \
+      else if (nt == 64) TC_LAUNCH(KERNEL, 64, 1, grid, st, __VA_ARGS__);                                                     \
+      else TC_LAUNCH(KERNEL, 128, 1, grid, st, __VA_ARGS__);                                                                  \
+    }                                                                                                                         \
+  } while (0)
 
 extern "C" {
 
@@ -387,15 +416,14 @@ int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const f
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(x, ldx) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
-  if (N <= 64) {
-    cudaFuncSetAttribute(tc_linear_fwd_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
-    dim3 grid(sg_div_up(N, 64), sg_div_up(M, TC_M));
-    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_fwd_kernel<64>, grid, dim3(TC_THREADS), tc_smem<64>(), (cudaStream_t)stream, x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
-  } else {
-    cudaFuncSetAttribute(tc_linear_fwd_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
-    dim3 grid(sg_div_up(N, 128), sg_div_up(M, TC_M));
-    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_fwd_kernel<128>, grid, dim3(TC_THREADS), tc_smem<128>(), (cudaStream_t)stream, x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
-  }
+  // (stand-alone a 64-wide tile is 1 us faster at M = 10000, N = 256 — tools/gemm_sweep.py — but inside the step graph, next to
+  // the row kernels, the 128-wide launch with half the CTAs wins by 4 us per step: tools/ab_bench.sh)
+  int nt = tc_env("SUBGNN_TC_NT_FWD", N <= 64 ? 64 : 128);
+  if (nt != 32 && nt != 64) nt = 128;
+  const int stages = tc_stages(sg_div_up(K, TC_KB));
+  dim3 grid(sg_div_up(N, nt), sg_div_up(M, TC_M));
+  cudaStream_t st = (cudaStream_t)stream;
+  TC_DISPATCH(tc_linear_fwd_kernel, nt, stages, grid, st, x, ldx, gather_ids, w, ldw, bias, y, ldy, M, N, K, relu);
   return subgnn_check_launch("tc_linear_fwd_kernel");
 }
 
@@ -404,10 +432,14 @@ int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
-  // output tile width: the widest that still gives every SM a CTA
+  // output tile width: the widest that still gives every SM a CTA.  (Stand-alone, the scatter GEMM of layer 0 is faster with a
+  // 64-wide tile and 4 reduction splits, 16.9 against 26.9 us; inside the step graph, where it shares the GPU with three
+  // weight-gradient GEMMs, the narrow tile with 2 splits is 4 us per step better: tools/gemm_sweep.py, tools/ab_bench.sh)
   const int sms = subgnn_sm_count(), m_tiles = sg_div_up(M, TC_M);
   int nt = K <= 32 ? 32 : (K <= 64 ? 64 : 128);
   while (nt > 32 && sg_div_up(K, nt) * m_tiles < sms) nt >>= 1;
+  nt = tc_env("SUBGNN_TC_NT_BWI", nt);
+  if (nt != 32 && nt != 64) nt = 128;
   // reduction splits (atomic output) only where the destination already holds the value to add onto
   int splits = 1;
   if (scatter_ids || accumulate) {
@@ -415,15 +447,15 @@ int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw
     splits = sg_div_up(2 * sms, ctas);
     const int max_splits = sg_div_up(N, 4 * TC_KB);
     if (splits > max_splits) splits = max_splits;
+    splits = tc_env("SUBGNN_TC_SPLITS_BWI", splits);
     if (splits < 1) splits = 1;
   }
   const int n_chunk = sg_div_up(sg_div_up(N, splits), TC_KB) * TC_KB;
   splits = sg_div_up(N, n_chunk);
+  const int stages = tc_stages(n_chunk / TC_KB);
   dim3 grid(sg_div_up(K, nt), m_tiles, splits);
   cudaStream_t st = (cudaStream_t)stream;
-  if (nt == 32) launch_bwd_input<32>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
-  else if (nt == 64) launch_bwd_input<64>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
-  else launch_bwd_input<128>(grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
+  TC_DISPATCH(tc_linear_bwd_input_kernel, nt, stages, grid, st, dy, ldy, w, ldw, dx, lddx, scatter_ids, M, N, K, accumulate, n_chunk);
   return subgnn_check_launch("tc_linear_bwd_input_kernel");
 }
 
@@ -432,22 +464,20 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(x, ldx), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
-  const int nt = K <= 64 ? 64 : 128;
+  int nt = tc_env("SUBGNN_TC_NT_BWW", K <= 64 ? 64 : 128);
+  if (nt != 32 && nt != 64) nt = 128;
   const int tiles = sg_div_up(K, nt) * sg_div_up(N, TC_M);
   int splits = (3 * subgnn_sm_count() + tiles - 1) / tiles;          // ~3 resident CTAs per SM
-  const int max_splits = sg_div_up(M, 4 * TC_KB);
+  const int max_splits = sg_div_up(M, 4 * TC_KB);                    // (in-graph A/B: 79 splits 0.405 ms/step, 40: 0.412, 20: 0.420)
   if (splits > max_splits) splits = max_splits;
+  splits = tc_env("SUBGNN_TC_SPLITS_BWW", splits);
   if (splits < 1) splits = 1;
   const int m_chunk = sg_div_up(sg_div_up(M, splits), TC_KB) * TC_KB;
   splits = sg_div_up(M, m_chunk);
+  const int stages = tc_stages(m_chunk / TC_KB);
   dim3 grid(sg_div_up(K, nt), sg_div_up(N, TC_M), splits);
-  if (nt == 64) {
-    cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<64>());
-    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_weight_kernel<64>, grid, dim3(TC_THREADS), tc_smem<64>(), (cudaStream_t)stream, dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
-  } else {
-    cudaFuncSetAttribute(tc_linear_bwd_weight_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<128>());
-    sg_launch_pdl<SG_PDL_GEMM>(tc_linear_bwd_weight_kernel<128>, grid, dim3(TC_THREADS), tc_smem<128>(), (cudaStream_t)stream, dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
-  }
+  cudaStream_t st = (cudaStream_t)stream;
+  TC_DISPATCH(tc_linear_bwd_weight_kernel, nt, stages, grid, st, dy, ldy, x, ldx, gather_ids, dw, lddw, M, N, K, m_chunk);
   int rc = subgnn_check_launch("tc_linear_bwd_weight_kernel");
   if (rc) return rc;
   if (db) rc = subgnn_colsum(dy, ldy, db, M, N, nullptr, stream);
