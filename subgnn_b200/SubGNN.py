@@ -285,10 +285,13 @@ class SubGNN(nn.Module):
         ``train_batch['subgraph_idx']`` may be a host tensor; it is the only per-step input.  The returned loss is a device
         tensor of an asynchronously enqueued step; with ``sync_loss`` the call waits for the step and returns the loss as a
         host tensor (copied by the D2H node that ends the step graph), so ``float(loss)`` costs no further transfer."""
-        idx = train_batch['subgraph_idx'].reshape(-1).numpy() if not train_batch['subgraph_idx'].is_cuda else train_batch['subgraph_idx'].reshape(-1).cpu().numpy()
+        idx = train_batch['subgraph_idx']
+        if idx.is_cuda:
+            idx = idx.cpu()
         loss = self.engine.train_step(idx, use_graph=use_graph)
         if sync_loss:
-            return {'loss': torch.tensor(self.engine.loss_value())}
+            torch.cuda.current_stream().synchronize()
+            return {'loss': self.engine._last_ctx.loss_host}      # pinned host tensor written by the graph's D2H node (valid until the next step)
         return {'loss': loss}
 
     def val_test_step(self, batch, batch_idx=0, is_test=False):

@@ -43,9 +43,12 @@ __device__ __forceinline__ void sg_pdl_sync() {
   asm volatile("griddepcontrol.wait;" ::: "memory");
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }
+// Producers of DERIVED WEIGHTS (permuted / transposed copies that later kernels stage before their own wait) never trigger
+// early: their dependents are scheduled at grid completion, so a consumer's pre-wait prologue cannot overlap the producer.
+__device__ __forceinline__ void sg_pdl_wait_only() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 // kernel classes for the SUBGNN_B200_PDL bit mask (bit = class): small element-wise / per-patch kernels, tensor-core GEMMs,
 // LSTM recurrences, row (component) kernels
-enum { SG_PDL_SMALL = 0, SG_PDL_GEMM = 1, SG_PDL_RECUR = 2, SG_PDL_ROW = 3 };
+enum { SG_PDL_SMALL = 0, SG_PDL_GEMM = 1, SG_PDL_RECUR = 2, SG_PDL_ROW = 3, SG_PDL_CHAIN = 4 };   // CHAIN: small kernels ON the step's critical chain
 int subgnn_pdl_enabled(int kernel_class);
 template <int CLASS = SG_PDL_SMALL, class... KArgs, class... Args>
 static inline void sg_launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {

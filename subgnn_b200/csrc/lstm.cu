@@ -408,7 +408,7 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 //            CTA's slice is one contiguous block for its bulk copy; a thread's two float4 per k are contiguous across the warp).
 __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
                                  float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
-  sg_pdl_sync();
+  sg_pdl_wait_only();        // the recurrence kernels stage WhhT before their dependency wait (lstm_reg.cu)
   const int H4 = 4 * H;
   const long long total = (long long)2 * H4 * H;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -552,7 +552,7 @@ int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, in
 int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,
                          int D, int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  sg_launch_pdl(lstm_head_fwd_kernel, dim3(n_groups), dim3(512), (size_t)H2 * sizeof(float), (cudaStream_t)stream, OUT, AGG, EMB, W, bias, n_groups, group, T, H2, D,
+  sg_launch_pdl<SG_PDL_CHAIN>(lstm_head_fwd_kernel, dim3(n_groups), dim3(512), (size_t)H2 * sizeof(float), (cudaStream_t)stream, OUT, AGG, EMB, W, bias, n_groups, group, T, H2, D,
                                                                                           sum_mode);
   return subgnn_check_launch("lstm_head_fwd_kernel");
 }
@@ -560,7 +560,7 @@ int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* 
 int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,
                          int sum_mode, void* stream) {
   if (n_groups == 0) return SUBGNN_OK;
-  sg_launch_pdl(lstm_head_bwd_kernel, dim3(n_groups), dim3(512), (size_t)(H2 + D) * sizeof(float), (cudaStream_t)stream, dEMB, W, dOUT, db, n_groups, group, T, H2, D,
+  sg_launch_pdl<SG_PDL_CHAIN>(lstm_head_bwd_kernel, dim3(n_groups), dim3(512), (size_t)(H2 + D) * sizeof(float), (cudaStream_t)stream, dEMB, W, dOUT, db, n_groups, group, T, H2, D,
                                                                                                 sum_mode);
   return subgnn_check_launch("lstm_head_bwd_kernel");
 }

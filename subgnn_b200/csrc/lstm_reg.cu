@@ -130,7 +130,6 @@ template <int CL, int KS, int HC>
 __global__ void __launch_bounds__(512)
 lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float* __restrict__ OUT, float* __restrict__ CS,
                      int n_seq, int T, int H_arg, int steps_fwd, int steps_rev, int tile, DropArgs drop) {
-  sg_pdl_sync();
   const int H = HC > 0 ? HC : H_arg;         // HC: hidden size known at compile time (32 / 64 / 128), 0: generic
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
@@ -157,6 +156,10 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
   float2 c[NF];
 #pragma unroll
   for (int f = 0; f < NF; ++f) c[f] = make_float2(0.f, 0.f);
+  // Everything above reads only data that is at least two launches old (the permuted weights) or nothing at all, so it runs
+  // BEFORE the programmatic-dependency wait, i.e. while the projection GEMM that produces G is still executing (the trigger
+  // comes after the wait, so a dependent of this kernel still starts only once G's producer has completed: common.cuh)
+  sg_pdl_sync();
   const unsigned dsalt = drop.xd ? drop_salt(drop) : 0u;
   step_sync<CL>();                          // every CTA's h tile is zeroed before a peer writes into it; mbarrier init published
   bulk_wait(&wbar);
@@ -293,7 +296,6 @@ __global__ void __launch_bounds__(512)
 lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
                      const float* __restrict__ dOUT, int n_seq, int T, int H_arg, int steps_fwd, int steps_rev, int zero_untaken,
                      float* __restrict__ db_ih, float* __restrict__ db_hh, int tile, DropArgs drop) {
-  sg_pdl_sync();
   const int H = HC > 0 ? HC : H_arg;
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
@@ -325,6 +327,7 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
   for (int e = tid; e < tile * U; e += blockDim.x) dc_rec[e] = 0.f;
   for (int e = tid; e < U4; e += blockDim.x) bias_sm[e] = 0.f;
   for (int e = tid; e < SLOTS * tile * U; e += blockDim.x) red[e] = 0.f;
+  sg_pdl_sync();                            // weight staging (parameters) and the zero fills above overlap the producer of dOUT
   step_sync<CL>();
   bulk_wait(&wbar);
   const int n_el = ns * U;

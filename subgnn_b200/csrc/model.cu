@@ -77,7 +77,7 @@ __global__ void __launch_bounds__(256) prep_batch_kernel(Desc d) {
 
 // out[c][r] = in[r][c] for a list of matrices: job j -> (src, dst, rows, cols)
 __global__ void transpose_weights_kernel(Desc d) {
-  sg_pdl_sync();
+  sg_pdl_wait_only();        // the MLP kernels stage the transposed weights before their dependency wait
   // jobs: N-channel projections (L*2 of D x 2D), then lin (h1 x hid), lin2 (h2 x h1), lin3 (K x h2)
   const int n_jobs_n = d.use_n ? d.L * 2 : 0;
   for (int job = blockIdx.y; job < n_jobs_n + 3; job += gridDim.y) {
@@ -508,17 +508,19 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
 //   mlp_dz_kernel    CTA per 64-column slice of hid: dZ[b][i] = sum_j dH1[b][j] W1[j][i]
 #define MLP_SLICE 64
 __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
-  sg_pdl_sync();
   extern __shared__ float sm[];
   float* zs = sm;                               // [B][MLP_SLICE]
   float* ws = sm + (size_t)d.B * MLP_SLICE;     // [MLP_SLICE][h1]
   const int k0 = blockIdx.x * MLP_SLICE, kn = min(MLP_SLICE, d.hid - k0);
+  // the weight slice was transposed several launches ago (complete by transitivity of the dependency waits): staged before
+  // this kernel's own wait, while the row kernel that finishes Z is still running
+  const float* wt = d.lin_wt[0] + (size_t)k0 * d.h1;
+  sg_stage<16>(ws, kn * d.h1, [&](int e) { return __ldg(wt + e); });
+  sg_pdl_sync();
   sg_stage<8>(zs, d.B * MLP_SLICE, [&](int e) {
     const int b = e / MLP_SLICE, kk = e % MLP_SLICE;
     return kk < kn ? d.Z[(size_t)b * d.hid + k0 + kk] : 0.f;
   });
-  const float* wt = d.lin_wt[0] + (size_t)k0 * d.h1;
-  sg_stage<16>(ws, kn * d.h1, [&](int e) { return __ldg(wt + e); });
   __syncthreads();
   for (int o = threadIdx.x; o < d.B * d.h1; o += blockDim.x) {
     const int b = o / d.h1, j = o % d.h1;
@@ -531,7 +533,6 @@ __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
 }
 
 __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
-  sg_pdl_sync();
   extern __shared__ float sm[];
   float* w1t = sm;                               // [h1][h2]  lin2 weights, input-major (forward)
   float* w1n = w1t + (size_t)d.h1 * d.h2;        // [h2][h1]  lin2 weights, native (backward)
@@ -547,6 +548,7 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   const float* src_n = d.lin_w[1];
   const int nw1 = d.h1 * d.h2;
   sg_stage<16>(w1t, bwd ? 2 * nw1 : nw1, [&](int e) { return e < nw1 ? __ldg(src_t + e) : __ldg(src_n + e - nw1); });
+  sg_pdl_sync();                                 // (weights staged before the wait: not written by the preceding launch)
   for (int j = tid; j < d.h1; j += blockDim.x) {
     float acc = fmaxf(d.H1[(size_t)b * d.h1 + j] + d.lin_b[0][j], 0.f);
     if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
@@ -625,17 +627,19 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
 }
 
 __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
-  sg_pdl_sync();
   extern __shared__ float sm[];
   float* g1s = sm;                               // [B][h1]
   float* ws = sm + (size_t)d.B * d.h1;           // [h1][MLP_SLICE]
   const int i0 = blockIdx.x * MLP_SLICE, in = min(MLP_SLICE, d.hid - i0);
-  sg_stage<8>(g1s, d.B * d.h1, [&](int e) { return d.dH1[e]; });
+  // the W1 slice is a PARAMETER (last written by the previous step's Adam, a full stream dependency ago): staged before the
+  // programmatic-dependency wait, i.e. while mlp_rest_kernel is still running
   const float* w0 = d.lin_w[0];
   sg_stage<16>(ws, d.h1 * MLP_SLICE, [&](int e) {
     const int j = e / MLP_SLICE, ii = e % MLP_SLICE;
     return ii < in ? __ldg(w0 + (size_t)j * d.hid + i0 + ii) : 0.f;
   });
+  sg_pdl_sync();
+  sg_stage<8>(g1s, d.B * d.h1, [&](int e) { return d.dH1[e]; });
   __syncthreads();
   for (int o = threadIdx.x; o < d.B * MLP_SLICE; o += blockDim.x) {
     const int b = o / MLP_SLICE, ii = o % MLP_SLICE;
@@ -878,7 +882,10 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
   if (!d->use_p) which &= ~SUBGNN_Q_POS;
   if (!d->use_s) which &= ~SUBGNN_Q_STRUC;
   if (!which) return SUBGNN_OK;
-  sg_launch_pdl(q_fwd_kernel, dim3(sg_grid_for(total, 8, 8)), dim3(256), 0, (cudaStream_t)stream, *d, which);
+  if (which == SUBGNN_Q_STRUC)            // structure anchors: between the LSTM head and the readout, on the critical chain
+    sg_launch_pdl<SG_PDL_CHAIN>(q_fwd_kernel, dim3(sg_grid_for(total, 8, 8)), dim3(256), 0, (cudaStream_t)stream, *d, which);
+  else
+    sg_launch_pdl(q_fwd_kernel, dim3(sg_grid_for(total, 8, 8)), dim3(256), 0, (cudaStream_t)stream, *d, which);
   return subgnn_check_launch("q_fwd_kernel");
 }
 
@@ -915,14 +922,14 @@ int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   if (s1 > 48 * 1024) cudaFuncSetAttribute(mlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (s2 > 48 * 1024) cudaFuncSetAttribute(mlp_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
   if (s3 > 48 * 1024) cudaFuncSetAttribute(mlp_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
-  sg_launch_pdl(mlp_lin1_kernel, dim3(slices), dim3(256), s1, st, *d);
+  sg_launch_pdl<SG_PDL_CHAIN>(mlp_lin1_kernel, dim3(slices), dim3(256), s1, st, *d);
   rc = subgnn_check_launch("mlp_lin1_kernel");
   if (rc) return rc;
-  sg_launch_pdl(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
+  sg_launch_pdl<SG_PDL_CHAIN>(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
   rc = subgnn_check_launch("mlp_rest_kernel");
   if (rc) return rc;
   if (d->training && d->dZ) {
-    sg_launch_pdl(mlp_dz_kernel, dim3(slices), dim3(256), s3, st, *d);
+    sg_launch_pdl<SG_PDL_CHAIN>(mlp_dz_kernel, dim3(slices), dim3(256), s3, st, *d);
     rc = subgnn_check_launch("mlp_dz_kernel");
   }
   return rc;
@@ -966,7 +973,7 @@ int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
   int gx = sg_div_up(max_cnt, 24);
   gx = gx < 8 ? 8 : (gx > 96 ? 96 : gx);
   dim3 grid(gx, d->L * groups);
-  sg_launch_pdl(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d);
+  sg_launch_pdl<SG_PDL_CHAIN>(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d);
   return subgnn_check_launch("q_bwd_kernel");
 }
 

@@ -105,7 +105,7 @@ int subgnn_fill_zero(float* p, long long n, void* stream) {
 int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE(((size_t)g & 15) == 0, "buffer must be 16-byte aligned");
-  sg_launch_pdl(sumsq_kernel, dim3(sg_grid_for(n / 4 + 1, 256, 4)), dim3(256), 0, (cudaStream_t)stream, g, n, out_sumsq);
+  sg_launch_pdl<SG_PDL_CHAIN>(sumsq_kernel, dim3(sg_grid_for(n / 4 + 1, 256, 4)), dim3(256), 0, (cudaStream_t)stream, g, n, out_sumsq);
   return subgnn_check_launch("sumsq_kernel");
 }
 
@@ -113,13 +113,13 @@ int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, 
                      const int* step_dev, const float* sumsq_dev, float clip_norm, float grad_scale, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE((((size_t)p | (size_t)g | (size_t)m | (size_t)v) & 15) == 0, "buffers must be 16-byte aligned");
-  sg_launch_pdl(adam_kernel, dim3(sg_grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
+  sg_launch_pdl<SG_PDL_CHAIN>(adam_kernel, dim3(sg_grid_for((n + 3) / 4, 256, 8)), dim3(256), 0, (cudaStream_t)stream, p, g, m, v, n, lr, beta1, beta2, eps, step_dev,
                 sumsq_dev, clip_norm, grad_scale);
   return subgnn_check_launch("adam_kernel");
 }
 
 int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream) {
-  sg_launch_pdl(sum_to_scalar_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, x, n, out);
+  sg_launch_pdl<SG_PDL_CHAIN>(sum_to_scalar_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, x, n, out);
   return subgnn_check_launch("sum_to_scalar_kernel");
 }
 

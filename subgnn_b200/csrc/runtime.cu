@@ -18,7 +18,7 @@ void subgnn_set_error(const char* fmt, ...) {
 // (ppi_bp / hpo_metab / em_user shapes, same box): mask 0: 0.445 / 0.860 / 0.712; 4 (recurrences): 0.442 / 0.843 / 0.727;
 // 14 (GEMMs + recurrences + row kernels): 0.431 / 0.800 / 0.739; 15 (everything): 0.426 / 0.879 / 0.827 — early-scheduled
 // small kernels take SM slots from the other graph branches at the two H = 128 shapes.
-#define SUBGNN_PDL_DEFAULT_MASK 14
+#define SUBGNN_PDL_DEFAULT_MASK 30
 
 static unsigned long long g_launches = 0;
 

@@ -408,7 +408,8 @@ class StepContext:
         self.batch_idx = zi(B)
         # pinned staging ring for the step's only host input: a slot is rewritten only after the copy that read it has retired
         # (steps are enqueued asynchronously, the host may run several steps ahead of the device)
-        self.batch_ring = [[torch.zeros(B, dtype=torch.int32).pin_memory(), None] for _ in range(8)]
+        self.batch_ring = [torch.zeros(B, dtype=torch.int32).pin_memory() for _ in range(8)]
+        self.ring_events = [None, None]
         self.ring_pos = 0
         self.loss_host = torch.zeros(1, dtype=torch.float32).pin_memory()     # written by a D2H copy node at the end of the step
         self.b_rowptr, self.meta = zi(B + 1), zi(4)
@@ -707,18 +708,28 @@ class Engine:
              c.sumsq.data_ptr(), clip, 1.0 / self.world_size, st)
 
     def set_batch(self, c, indices):
-        """host -> device copy of the step's only input: the subgraph indices."""
-        idx = torch.as_tensor(np.asarray(indices), dtype=torch.int32)
-        assert idx.numel() == c.B
-        slot = c.batch_ring[c.ring_pos]
-        c.ring_pos = (c.ring_pos + 1) % len(c.batch_ring)
-        if slot[1] is None:
-            slot[1] = torch.cuda.Event()
+        """host -> device copy of the step's only input: the subgraph indices (numpy array, list or CPU tensor, any int type).
+        Staged through a ring of pinned buffers guarded by two events (one per half ring), so that the host, which may run
+        several steps ahead of the device, never rewrites a buffer whose copy is still in flight."""
+        ring = c.batch_ring
+        pos, half = c.ring_pos, len(ring) // 2
+        c.ring_pos = (pos + 1) % len(ring)
+        if pos % half == 0:                       # entering a half ring: the copies issued from it one lap ago must have retired
+            ev = c.ring_events[pos // half]
+            if ev is not None:
+                ev.synchronize()
+        buf = ring[pos]
+        if isinstance(indices, torch.Tensor):
+            buf.copy_(indices.view(-1))           # converts int64 -> int32 on the fly; raises on a size mismatch
         else:
-            slot[1].synchronize()
-        slot[0].copy_(idx)
-        c.batch_idx.copy_(slot[0], non_blocking=True)
-        slot[1].record()
+            idx = np.asarray(indices)
+            assert idx.size == c.B
+            buf.copy_(torch.from_numpy(idx.reshape(-1)))
+        c.batch_idx.copy_(buf, non_blocking=True)
+        if pos % half == half - 1:                # leaving a half ring
+            if c.ring_events[pos // half] is None:
+                c.ring_events[pos // half] = torch.cuda.Event()
+            c.ring_events[pos // half].record()
 
     # ---- public API --------------------------------------------------------------------------------
     def forward(self, split, indices, training=False):
@@ -747,7 +758,7 @@ class Engine:
         With use_graph the launches are captured once and replayed: ONE CUDA graph for the whole step on a single GPU, two
         halves around the NCCL allreduce when data parallel.  The graph ends with a D2H copy node of the loss into pinned
         host memory (read it with ``loss_value``); per-step host work is one pinned copy of the indices + the graph launch."""
-        c = self._last_ctx = self.context('train', len(indices), True)
+        c = self._last_ctx = self.context('train', indices.numel() if isinstance(indices, torch.Tensor) else len(indices), True)
         self.set_batch(c, indices)
         st = _abi.stream_ptr()
         if not use_graph:
@@ -792,7 +803,7 @@ class Engine:
         """loss of the last enqueued train step as a Python float: waits for the stream, reads the pinned copy."""
         c = self.context('train', B, True) if B is not None else self._last_ctx
         torch.cuda.current_stream().synchronize()
-        return float(c.loss_host[0])
+        return c.loss_host.item()
 
     def _grad_launches(self, c, st):
         call('subgnn_inc_step', ptr(self.step_dev), st)
