@@ -338,27 +338,37 @@ __global__ void __launch_bounds__(512) lstm_head_fwd_kernel(const float* __restr
 __global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restrict__ dEMB, const float* __restrict__ W, float* __restrict__ dOUT,
                                                             float* __restrict__ db, int n_groups, int group, int T, int H2, int D,
                                                             int sum_mode) {
-  sg_pdl_sync();
   extern __shared__ float sm_head[];
   float* dy = sm_head;          // [D]
   float* dagg = sm_head + D;    // [H2]
   const int g = blockIdx.x;
+  // thread (c, part): the D reduction is split over blockDim / H2 parts; the thread's weights (a parameter, <= 16 values) are
+  // loaded BEFORE the dependency wait, i.e. while the kernel that produces dEMB is still running
+  const int parts = max(1, (int)blockDim.x / H2);
+  const int c = threadIdx.x % H2, part = threadIdx.x / H2;
+  const int d_lo = (int)((long long)D * part / parts), d_hi = (int)((long long)D * (part + 1) / parts);
+  const bool pre = part < parts && d_hi - d_lo <= 16;
+  float wreg[16];
+#pragma unroll
+  for (int i = 0; i < 16; ++i) wreg[i] = (pre && d_lo + i < d_hi) ? __ldg(W + (size_t)(d_lo + i) * H2 + c) : 0.f;
+  sg_pdl_sync();
   for (int d = threadIdx.x; d < D; d += blockDim.x) {
     const float v = dEMB[(size_t)g * D + d];
     dy[d] = v;
     if (db && v != 0.f) atomicAdd(db + d, (float)group * v);
   }
-  for (int c = threadIdx.x; c < H2; c += blockDim.x) dagg[c] = 0.f;
+  for (int c2 = threadIdx.x; c2 < H2; c2 += blockDim.x) dagg[c2] = 0.f;
   __syncthreads();
-  // thread (c, part): the D reduction is split over blockDim / H2 parts so that every thread has few, independent loads
   {
-    const int parts = max(1, (int)blockDim.x / H2);
-    const int c = threadIdx.x % H2, part = threadIdx.x / H2;
     if (part < parts) {
-      const int d_lo = (int)((long long)D * part / parts), d_hi = (int)((long long)D * (part + 1) / parts);
       float acc = 0.f;
+      if (pre) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) acc = fmaf(dy[min(d_lo + i, D - 1)], wreg[i], acc);      // zero-padded tail: exact
+      } else {
 #pragma unroll 16
-      for (int d = d_lo; d < d_hi; ++d) acc = fmaf(dy[d], __ldg(W + (size_t)d * H2 + c), acc);
+        for (int d = d_lo; d < d_hi; ++d) acc = fmaf(dy[d], __ldg(W + (size_t)d * H2 + c), acc);
+      }
       if (parts == 1) dagg[c] = acc; else atomicAdd(dagg + c, acc);
     }
     if (parts == 1)
@@ -371,9 +381,18 @@ __global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restr
   __syncthreads();
   const int rows = group * T;
   float* base = dOUT + (size_t)g * rows * H2;
-  for (int e = threadIdx.x; e < rows * H2; e += blockDim.x) {
-    const int c = e % H2, t = (e / H2) % T;
-    base[e] = (sum_mode || t == T - 1) ? dagg[c] : 0.f;
+  if ((H2 & 3) == 0 && ((((size_t)base) & 15) == 0)) {           // 16-byte stores
+    const int h4 = H2 >> 2;
+    for (int e = threadIdx.x; e < rows * h4; e += blockDim.x) {
+      const int c4 = (e % h4) * 4, t = (e / h4) % T;
+      const float4 v = (sum_mode || t == T - 1) ? make_float4(dagg[c4], dagg[c4 + 1], dagg[c4 + 2], dagg[c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      reinterpret_cast<float4*>(base)[e] = v;
+    }
+  } else {
+    for (int e = threadIdx.x; e < rows * H2; e += blockDim.x) {
+      const int c2 = e % H2, t = (e / H2) % T;
+      base[e] = (sum_mode || t == T - 1) ? dagg[c2] : 0.f;
+    }
   }
 }
 

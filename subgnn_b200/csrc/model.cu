@@ -751,10 +751,18 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases
     if (phases & 2) {
       const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
       const int per_layer = wp_ + ws_;
-      for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
+      // every warp runs the same number of iterations (out-of-range lanes carry key -1): the bias-gradient terms of a warp are
+      // reduced with shuffles per (layer, slot) key before ONE shared-memory atomic — the keys of consecutive entries coincide,
+      // and 32-way same-address shared atomics were the bulk of this phase
+      const int n_ent = d.L * per_layer;
+      for (int e0 = 0; e0 < n_ent; e0 += ROW_THREADS) {
+        const int e = e0 + tid;
+        int key = -1;
+        float g_ = 0.f;
+        if (e < n_ent) {
         const int l = e / per_layer;
         int o = e % per_layer;
-        float s, q, bp, g_;
+        float s, q, bp;
         float* dq;
         int slot;
         if (o < wp_) {
@@ -777,7 +785,15 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases
         }
         if (fmaf(s, q, bp) > 0.f && g_ != 0.f) {
           if (s != 0.f) atomicAdd(dq, s * g_);
-          atomicAdd(acc_bp + l * 4 + slot, g_);
+          key = l * 4 + slot;
+        }
+        }
+        int kmax = __reduce_max_sync(0xffffffffu, key);
+        while (kmax >= 0) {
+          const float c = warp_sum(key == kmax ? g_ : 0.f);
+          if (lane == 0) atomicAdd(acc_bp + kmax, c);
+          if (key == kmax) key = -1;
+          kmax = __reduce_max_sync(0xffffffffu, key);
         }
       }
       __syncthreads();
