@@ -126,7 +126,13 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
                           void* stream);
-/* db_ih / db_hh (optional, [2][4H]): += column sums of d(pre-activation), the gradient of both bias vectors */
+/* db_ih / db_hh (optional, [2][4H]): += column sums of d(pre-activation), the gradient of both bias vectors.
+   zero_untaken is a flag word: SUBGNN_LSTM_ZERO_UNTAKEN = zero the gate slots of time steps that were never taken;
+   SUBGNN_LSTM_DOUT_LAST_ONLY = dOUT carries gradient (and has been written) only in its rows t = T-1 — the 'last' aggregator's
+   top layer, SubGNN.py:83 — every other row is taken as zero without being read (register-tiled recurrence only:
+   subgnn_lstm_fused_dropout_supported(H)). */
+#define SUBGNN_LSTM_ZERO_UNTAKEN 1
+#define SUBGNN_LSTM_DOUT_LAST_ONLY 2
 int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
                           int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, void* stream);
 /* the same recurrences with nn.LSTM's inter-layer dropout fused in (training, p > 0): forward also writes xdrop = dropout_p(OUT), the
@@ -143,7 +149,10 @@ int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, 
 int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);
 /* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out)), SubGNN.py:83-88).
    The head is linear, so the walks are summed first: fwd  AGG[g] = sum_w agg(OUT[g*group+w]),  EMB[g] = W AGG[g] + group * bias;
-   bwd  dOUT rows <- W^T dEMB[g] (t = T-1 only for 'last'),  db += group * sum_g dEMB[g]   (dW = dEMB^T AGG: subgnn_linear_bwd_weight) */
+   bwd  dOUT rows <- W^T dEMB[g] (t = T-1 only for 'last'),  db += group * sum_g dEMB[g]   (dW = dEMB^T AGG: subgnn_linear_bwd_weight).
+   sum_mode: 0 = 'last', 1 = 'sum', SUBGNN_HEAD_LAST_NO_FILL (bwd only) = 'last' writing the rows t = T-1 alone: the other rows of
+   dOUT are left untouched, for a BPTT launched with SUBGNN_LSTM_DOUT_LAST_ONLY */
+#define SUBGNN_HEAD_LAST_NO_FILL 2
 int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,
                          int D, int sum_mode, void* stream);
 int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,

@@ -385,13 +385,17 @@ __global__ void __launch_bounds__(512) lstm_head_bwd_kernel(const float* __restr
     const int h4 = H2 >> 2;
     for (int e = threadIdx.x; e < rows * h4; e += blockDim.x) {
       const int c4 = (e % h4) * 4, t = (e / h4) % T;
-      const float4 v = (sum_mode || t == T - 1) ? make_float4(dagg[c4], dagg[c4 + 1], dagg[c4 + 2], dagg[c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      const bool live = sum_mode == 1 || t == T - 1;
+      if (!live && sum_mode == SUBGNN_HEAD_LAST_NO_FILL) continue;
+      const float4 v = live ? make_float4(dagg[c4], dagg[c4 + 1], dagg[c4 + 2], dagg[c4 + 3]) : make_float4(0.f, 0.f, 0.f, 0.f);
       reinterpret_cast<float4*>(base)[e] = v;
     }
   } else {
     for (int e = threadIdx.x; e < rows * H2; e += blockDim.x) {
       const int c2 = e % H2, t = (e / H2) % T;
-      base[e] = (sum_mode || t == T - 1) ? dagg[c2] : 0.f;
+      const bool live = sum_mode == 1 || t == T - 1;
+      if (!live && sum_mode == SUBGNN_HEAD_LAST_NO_FILL) continue;
+      base[e] = live ? dagg[c2] : 0.f;
     }
   }
 }
@@ -522,6 +526,8 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
   if (n_seq == 0) return SUBGNN_OK;
   if (lstm_reg_supported(H))
     return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, 0.f, 0ull, 0u, nullptr, (cudaStream_t)stream);
+  SG_REQUIRE(!(zero_untaken & SUBGNN_LSTM_DOUT_LAST_ONLY), "SUBGNN_LSTM_DOUT_LAST_ONLY needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
+  zero_untaken &= SUBGNN_LSTM_ZERO_UNTAKEN;
   size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);
   const size_t wbytes = (size_t)4 * H * H * sizeof(float);
   const bool w_smem = smem + wbytes <= 100 * 1024 && (H % 2 == 0) && (((size_t)whh) & 15) == 0;

@@ -368,7 +368,8 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
         v.ig = gp[0]; v.fg = gp[H]; v.gg = gp[2 * H]; v.og = gp[3 * H];
         v.cc = CS[oe];
         v.cp = st > 0 ? CS[o_off[it][q] + (size_t)t_prev * 2 * H] : 0.f;
-        v.dho = dOUT[oe];
+        // flag 2: the caller's dOUT is non-zero (and written) only at t = T-1 ('last' aggregator, top layer)
+        v.dho = (!(zero_untaken & SUBGNN_LSTM_DOUT_LAST_ONLY) || t == T - 1) ? dOUT[oe] : 0.f;
       }
     }
   };
@@ -467,7 +468,7 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
   }
   // steps that were never taken carry no gradient: zero their slots (they still hold pre-activations) unless the caller
   // never reads them (zero_untaken == 0)
-  for (int st = n_steps; zero_untaken && st < T; ++st) {
+  for (int st = n_steps; (zero_untaken & SUBGNN_LSTM_ZERO_UNTAKEN) && st < T; ++st) {
     const int t = dir == 0 ? st : T - 1 - st;
     for (int e = tid; e < ns * U4; e += blockDim.x) {
       const int s = e / U4, lc = e % U4;

@@ -433,18 +433,19 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
           const float* wt = d.n_wt + (size_t)(2 * l + side) * 2 * D * D;
           const int parts = (D <= SIDE_THREADS && SIDE_THREADS % D == 0) ? min(SIDE_THREADS / D, SIDE_WARPS) : 1;
           const float* inp = S.in + side * 2 * D;
+          const float* bias = d.mpn_params[0] + (size_t)(2 * l + side) * blk + 2 * D * D;
+          const float bias_j = st < D ? __ldg(bias + st) : 0.f;          // issued with the weight loads, used after the barrier
           for (int idx = st; idx < parts * D; idx += SIDE_THREADS) {
             const int j = idx % D, part = idx / D;
             const int k0 = 2 * D * part / parts, k1 = 2 * D * (part + 1) / parts;
             float acc = 0.f;
-#pragma unroll 16
-            for (int kk = k0; kk < k1; ++kk) acc = fmaf(inp[kk], __ldg(wt + (size_t)kk * D + j), acc);   // 16 weight loads in flight
+#pragma unroll 32
+            for (int kk = k0; kk < k1; ++kk) acc = fmaf(inp[kk], __ldg(wt + (size_t)kk * D + j), acc);   // 32 weight loads in flight
             S.part[(side * SIDE_WARPS + part) * D + j] = acc;
           }
           __syncthreads();
-          const float* bias = d.mpn_params[0] + (size_t)(2 * l + side) * blk + 2 * D * D;
           for (int j = st; j < D; j += SIDE_THREADS) {
-            float acc = bias[j];
+            float acc = j == st ? bias_j : bias[j];
             for (int p_ = 0; p_ < parts; ++p_) acc += S.part[(side * SIDE_WARPS + p_) * D + j];
             S.h[side * D + j] = fmaxf(acc, 0.f);
           }

@@ -244,6 +244,9 @@ class LstmRunner:
         self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
         # inter-layer dropout fused into the recurrence kernels (mask written / applied in place of two element-wise launches per layer)
         self.fused_drop = bool(_abi.lib.subgnn_lstm_fused_dropout_supported(self.H)) and hp.get('b200_fused_lstm_dropout', True)
+        # 'last' aggregator: the head's gradient reaches the top layer's output only at t = T-1; the head then writes those rows
+        # alone and the BPTT kernel takes every other row of dOUT as zero without reading it (include/subgnn_b200.h flags)
+        self.last_only = (not self.sum_mode) and bool(_abi.lib.subgnn_lstm_fused_dropout_supported(self.H)) and _flag('SUBGNN_LSTM_LAST_ONLY', True)
 
     def steps(self, k):
         top = k == self.nl - 1
@@ -335,20 +338,21 @@ class LstmRunner:
             call('subgnn_linear_bwd_weight', ptr(self.dEMB), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
                  None, self.n_groups, D, 2 * H, None, aux[1].cuda_stream)
         call('subgnn_lstm_head_bwd', ptr(self.dEMB), a.addr('lstm.linear.weight'), ptr(self.dOUT[-1]), a.addr('lstm.linear.bias', g),
-             self.n_groups, self.W, T, 2 * H, D, self.sum_mode, st)
+             self.n_groups, self.W, T, 2 * H, D, 2 if self.last_only else self.sum_mode, st)
         for k in range(self.nl - 1, -1, -1):
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
             full = sr == T
             # the bias gradients (d b_ih == d b_hh == column sums of dG) are accumulated inside the recurrence kernel
             fused = self.fused_drop and self.p_drop > 0 and training
+            flags = (1 if full else 0) | (2 if (self.last_only and k == self.nl - 1) else 0)
             if fused and k + 1 < self.nl:            # dOUT[k] is the gradient w.r.t. X[k+1] = dropout(OUT[k]): mask applied on load
                 call('subgnn_lstm_recur_bwd_drop', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]),
-                     ptr(self.dOUT[k]), self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g),
+                     ptr(self.dOUT[k]), self.n_seq, T, H, sf, sr, flags, a.base_addr(o['bias_ih'], g),
                      a.base_addr(o['bias_hh'], g), self.p_drop, seed, 8 + k + 1, step_dev, st)
             else:
                 call('subgnn_lstm_recur_bwd', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]), ptr(self.dOUT[k]),
-                     self.n_seq, T, H, sf, sr, 0 if not full else 1, a.base_addr(o['bias_ih'], g), a.base_addr(o['bias_hh'], g), st)
+                     self.n_seq, T, H, sf, sr, flags, a.base_addr(o['bias_ih'], g), a.base_addr(o['bias_hh'], g), st)
             dG = ptr(self.G[k])
             x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=False)
             w_ih, gw_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g)
@@ -640,6 +644,11 @@ class Engine:
             self._prep = torch.cuda.Stream(device=self.device)
         return self._prep
 
+    def _q_stream(self):
+        if getattr(self, '_qs', None) is None:
+            self._qs = torch.cuda.Stream(device=self.device)
+        return self._qs
+
     def _forward_launches(self, c, st, zero_grads=False):
         main = torch.cuda.current_stream()
         fork = self.lstm is not None and self.concurrent
@@ -655,18 +664,32 @@ class Engine:
             call('subgnn_fill_zero', ptr(c.fwd_zero), c.fwd_zero.numel(), st)
         if self.lstm is not None and not fork:
             self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), st)
-        pfork = fork and _flag('SUBGNN_PREP_BRANCH', False)
-        if pfork:                                 # tuning switch (off: measured +4 us/step): weight transposes on their own branch
+        # Neighbourhood branch.  Its long kernel (row_fwd phase 1: pooling + N chains) needs the transposed weights and the batch
+        # prep, NOT the position q (only phase 2 reads q).  SUBGNN_FWD_BRANCHES=1 starts the transposes with the step on their own
+        # branch and runs the position q beside row_fwd instead of before it.  Measured (tools/ab_bench.sh, PPI-BP shape, same
+        # box): 0.3751 -> 0.3831 ms/step — released earlier, row_fwd's CTAs land on the SMs together with the layer-1 projection
+        # of the LSTM chain (the critical path) instead of beside the half-empty top-layer recurrence — so it stays a switch.
+        bfork = fork and _flag('SUBGNN_FWD_BRANCHES', False)
+        pfork = bfork or (fork and _flag('SUBGNN_PREP_BRANCH', False))
+        if pfork:
             prep = self._prep_stream()
             with torch.cuda.stream(prep):
                 call('subgnn_model_prep_weights', c.dptr, prep.cuda_stream)
         call('subgnn_model_prep_batch', c.dptr, st)
         if not pfork:
             call('subgnn_model_prep_weights', c.dptr, st)
-        call('subgnn_model_q_fwd_part', c.dptr, 1, st)               # position anchors
+        if bfork:
+            qs = self._q_stream()
+            qs.wait_stream(main)
+            with torch.cuda.stream(qs):
+                call('subgnn_model_q_fwd_part', c.dptr, 1, qs.cuda_stream)   # position anchors
+        else:
+            call('subgnn_model_q_fwd_part', c.dptr, 1, st)           # position anchors
         if pfork:
             main.wait_stream(prep)
         call('subgnn_model_rows_fwd', c.dptr, 1, st)                 # pooling + neighbourhood channel
+        if bfork:
+            main.wait_stream(qs)
         if fork:
             main.wait_stream(side)
         call('subgnn_model_q_fwd_part', c.dptr, 2, st)               # structure anchors (LSTM output)

@@ -129,3 +129,29 @@ def test_fused_lstm_dropout_equals_separate_mask_kernels(tiny):
     ref = Engine(h, p, device='cuda', graph=g, seed=9)
     ref.init_parameters(4)
     assert abs(float(ref.train_step(idx, use_graph=False).item()) - float(Engine(dict(hp, lstm_dropout=0.35, lstm_n_layers=2), p, device='cuda', graph=g, seed=9).train_step(idx, use_graph=False).item())) >= 0.0
+
+
+@pytest.mark.parametrize('n_layers', [1, 2])
+def test_last_only_head_gradient_equals_zero_filled_rows(tiny, monkeypatch, n_layers):
+    """'last' aggregator: the head writes only the rows t = T-1 of the top layer's output gradient and the BPTT kernel takes the
+    others as zero without reading them (SUBGNN_HEAD_LAST_NO_FILL / SUBGNN_LSTM_DOUT_LAST_ONLY) — same steps as the zero-filled
+    buffer; also checks the step-graph variants of the forward branches (SUBGNN_FWD_BRANCHES) against each other."""
+    from subgnn_b200.engine import Engine
+    hp, g, p = tiny
+    h = dict(hp, lstm_aggregator='last', lstm_n_layers=n_layers, lstm_dropout=0.0)
+    idx = np.arange(hp['batch_size'])
+    states, losses = [], []
+    for last_only, branches in (('1', '1'), ('0', '0')):
+        monkeypatch.setenv('SUBGNN_LSTM_LAST_ONLY', last_only)
+        monkeypatch.setenv('SUBGNN_FWD_BRANCHES', branches)
+        eng = Engine(h, p, device='cuda', graph=g, seed=9)
+        eng.init_parameters(4)
+        assert eng.lstm.last_only == (last_only == '1')
+        eng.lstm.dOUT[-1].fill_(123.0)            # stale rows must never be read in the last-only mode (and are overwritten otherwise)
+        ls = [float(eng.train_step(idx + it, use_graph=(it > 0)).item()) for it in range(4)]
+        torch.cuda.synchronize()
+        losses.append(ls)
+        states.append({k: v.cpu().numpy().copy() for k, v in eng.arena.state_dict().items()})
+    np.testing.assert_allclose(losses[0], losses[1], rtol=1e-5)
+    for k in states[0]:
+        np.testing.assert_allclose(states[0][k], states[1][k], rtol=1e-4, atol=1e-6, err_msg=k)
