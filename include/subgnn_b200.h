@@ -90,6 +90,11 @@ int subgnn_degree_seq(const int* rowptr, const int* col, const int* rows, int n_
  * reproduces fastdtw(radius=1) (reference default), SUBGNN_DTW_EXACT the unconstrained DTW. fp64 inside. */
 int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
                      int max_len_a, int max_len_b, int mode, float* out, void* stream);
+/* the same over a subset of the A rows: pairs (rowsA[i], b) for i < n_rows (rowsA == NULL: rows 0 .. n_rows-1); out keeps its
+ * [nA][nB] layout and is written at the ORIGINAL row.  max_len_a bounds the lengths of the listed rows only: the host buckets
+ * the components by length so that the wavefront of SUBGNN_DTW_EXACT runs with as many lanes per pair as the rows it holds. */
+int subgnn_dtw_batch_rows(const int* seqA, const int* lenA, const int* rowsA, int n_rows, int strideA, const int* seqB, const int* lenB,
+                          int nB, int strideB, int max_len_a, int max_len_b, int mode, float* out, void* stream);
 
 
 /* prepare_dataset/precompute_graph_metrics.py:20-26 get_shortest_path for sources [src_begin, src_end): BFS hop counts

@@ -37,6 +37,7 @@ SIGNATURES = {
     'subgnn_sp_min_gather': [P, LL, P, P, I, P, P, I, P, P],
     'subgnn_degree_seq': [P, P, P, I, I, I, P, P, P],
     'subgnn_dtw_batch': [P, P, I, I, P, P, I, I, I, I, I, P, P],
+    'subgnn_dtw_batch_rows': [P, P, P, I, I, P, P, I, I, I, I, I, P, P],
     'subgnn_hop_table': [P, P, I, I, I, P, LL, P],
     'subgnn_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],
     'subgnn_tc_linear_fwd': [P, I, P, P, I, P, P, I, I, I, I, I, P],

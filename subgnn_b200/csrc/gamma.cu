@@ -157,7 +157,7 @@ __device__ __forceinline__ double dtw_cost(float a, float b) {      // gamma.py:
   return (mx + 1.0) / (mn + 1.0) - 1.0;
 }
 
-__global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __restrict__ lenA, int nA, int strideA,
+__global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __restrict__ lenA, const int* __restrict__ rowsA, int nA, int strideA,
                                  const int* __restrict__ seqB, const int* __restrict__ lenB, int nB, int strideB,
                                  int LA, int LB, int fast, float* __restrict__ out) {
   extern __shared__ __align__(16) int smem[];
@@ -172,9 +172,11 @@ __global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __rest
   const double INF = __longlong_as_double(0x7ff0000000000000LL);
   const long long total = (long long)nA * nB;
   for (long long p = blockIdx.x * (long long)blockDim.x + threadIdx.x; p < total; p += (long long)gridDim.x * blockDim.x) {
-    const int a = (int)(p / nB), b = (int)(p % nB);
+    const int ai = (int)(p / nB), b = (int)(p % nB);
+    const int a = rowsA ? rowsA[ai] : ai;                           // optional row subset (length buckets)
+    float* outp = out + (size_t)a * nB + b;
     const int n0 = lenA[a], m0 = lenB[b];
-    if (n0 == 0 || m0 == 0) { out[p] = 0.f; continue; }           // SubGNN.py:831
+    if (n0 == 0 || m0 == 0) { *outp = 0.f; continue; }            // SubGNN.py:831
     for (int i = 0; i < n0; ++i) xs[i] = (float)seqA[(size_t)a * strideA + i];
     for (int j = 0; j < m0; ++j) ys[j] = (float)seqB[(size_t)b * strideB + j];
     // coarsening levels (fastdtw __reduce_by_half); level l of x starts at xoff[l]
@@ -250,7 +252,7 @@ __global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __rest
         }
       }
     }
-    out[p] = (float)(1.0 / (dist + 1.0));                          // gamma.py:59, cast SubGNN.py:822
+    *outp = (float)(1.0 / (dist + 1.0));                           // gamma.py:59, cast SubGNN.py:822
   }
 }
 
@@ -262,7 +264,7 @@ __global__ void dtw_batch_kernel(const int* __restrict__ seqA, const int* __rest
 // the patch sequence is staged there).  Values are identical to the row-by-row evaluation: every cell is cost + min of the same
 // three fp64 numbers, and min(a+c, b+c, d+c) == min(a, b, d) + c in floating point (rounding is monotonic).
 template <int G, int R>
-__global__ void __launch_bounds__(128) dtw_exact_wave_kernel(const int* __restrict__ seqA, const int* __restrict__ lenA, int nA, int strideA,
+__global__ void __launch_bounds__(128) dtw_exact_wave_kernel(const int* __restrict__ seqA, const int* __restrict__ lenA, const int* __restrict__ rowsA, int nA, int strideA,
                                                              const int* __restrict__ seqB, const int* __restrict__ lenB, int nB, int strideB,
                                                              int LB, float* __restrict__ out) {
   extern __shared__ __align__(16) int smem[];
@@ -281,9 +283,10 @@ __global__ void __launch_bounds__(128) dtw_exact_wave_kernel(const int* __restri
     int n = 0, m = 0, a = 0, b = 0;
     if (valid) {
       a = (int)(p / nB); b = (int)(p % nB);
+      if (rowsA) a = rowsA[a];                              // optional row subset (length buckets)
       n = lenA[a]; m = lenB[b];
       if (n == 0 || m == 0) {                               // SubGNN.py:831
-        if (gl == 0) out[p] = 0.f;
+        if (gl == 0) out[(size_t)a * nB + b] = 0.f;
         n = 0; m = 0;
       }
     }
@@ -320,15 +323,15 @@ __global__ void __launch_bounds__(128) dtw_exact_wave_kernel(const int* __restri
       double d = col[0];
 #pragma unroll
       for (int r = 1; r < R; ++r) if (r == (n - 1) % R) d = col[r];
-      out[p] = (float)(1.0 / (d + 1.0));                     // gamma.py:59, cast SubGNN.py:822
+      out[(size_t)a * nB + b] = (float)(1.0 / (d + 1.0));    // gamma.py:59, cast SubGNN.py:822
     }
     __syncwarp();
   }
 }
 
 template <int G, int R>
-static int launch_dtw_wave(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
-                           int LB, float* out, cudaStream_t st) {
+static int launch_dtw_wave(const int* seqA, const int* lenA, const int* rowsA, int nA, int strideA, const int* seqB, const int* lenB, int nB,
+                           int strideB, int LB, float* out, cudaStream_t st) {
   const int threads = 128, groups = threads / G;
   const size_t smem = (size_t)groups * LB * sizeof(int);
   if (smem > 200 * 1024) return -1;
@@ -336,7 +339,7 @@ static int launch_dtw_wave(const int* seqA, const int* lenA, int nA, int strideA
   const long long total = (long long)nA * nB;
   const long long want = (total + groups - 1) / groups;
   const int grid = (int)(want < 148LL * 16 ? want : 148LL * 16);
-  dtw_exact_wave_kernel<G, R><<<grid, threads, smem, st>>>(seqA, lenA, nA, strideA, seqB, lenB, nB, strideB, LB, out);
+  dtw_exact_wave_kernel<G, R><<<grid, threads, smem, st>>>(seqA, lenA, rowsA, nA, strideA, seqB, lenB, nB, strideB, LB, out);
   return 0;
 }
 
@@ -372,8 +375,9 @@ int subgnn_degree_seq(const int* rowptr, const int* col, const int* rows, int n_
   return subgnn_check_launch("degree_seq_kernel");
 }
 
-int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
-                     int max_len_a, int max_len_b, int mode, float* out, void* stream) {
+int subgnn_dtw_batch_rows(const int* seqA, const int* lenA, const int* rowsA, int n_rows, int strideA, const int* seqB, const int* lenB,
+                          int nB, int strideB, int max_len_a, int max_len_b, int mode, float* out, void* stream) {
+  const int nA = n_rows;                       // pairs (rowsA[i], b), i < n_rows; out is indexed by the ORIGINAL row
   SG_REQUIRE(nA >= 0 && nB >= 0 && max_len_a >= 1 && max_len_b >= 1, "bad sizes");
   SG_REQUIRE(mode == SUBGNN_DTW_EXACT || mode == SUBGNN_DTW_FASTDTW_R1 || mode == SUBGNN_DTW_EXACT_THREAD, "unknown DTW mode");
   SG_REQUIRE(max_len_a <= strideA && max_len_b <= strideB && max_len_a < 32000 && max_len_b < 32000, "bad max lengths");
@@ -381,7 +385,7 @@ int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, cons
   if (mode == SUBGNN_DTW_EXACT && max_len_a <= 256) {         // lanes own the rows of the component sequence
     cudaStream_t st = (cudaStream_t)stream;
     int rc;
-#define SG_WAVE(G, R) rc = launch_dtw_wave<G, R>(seqA, lenA, nA, strideA, seqB, lenB, nB, strideB, max_len_b, out, st)
+#define SG_WAVE(G, R) rc = launch_dtw_wave<G, R>(seqA, lenA, rowsA, nA, strideA, seqB, lenB, nB, strideB, max_len_b, out, st)
     if (max_len_a <= 4) SG_WAVE(4, 1);
     else if (max_len_a <= 8) SG_WAVE(8, 1);
     else if (max_len_a <= 16) SG_WAVE(16, 1);
@@ -400,9 +404,14 @@ int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, cons
   const size_t smem = per_thread * threads;
   cudaFuncSetAttribute(dtw_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   const int grid = sg_grid_for((long long)nA * nB, threads, 1);
-  dtw_batch_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(seqA, lenA, nA, strideA, seqB, lenB, nB, strideB, max_len_a, max_len_b,
+  dtw_batch_kernel<<<grid, threads, smem, (cudaStream_t)stream>>>(seqA, lenA, rowsA, nA, strideA, seqB, lenB, nB, strideB, max_len_a, max_len_b,
                                                                   mode == SUBGNN_DTW_FASTDTW_R1, out);
   return subgnn_check_launch("dtw_batch_kernel");
+}
+
+int subgnn_dtw_batch(const int* seqA, const int* lenA, int nA, int strideA, const int* seqB, const int* lenB, int nB, int strideB,
+                     int max_len_a, int max_len_b, int mode, float* out, void* stream) {
+  return subgnn_dtw_batch_rows(seqA, lenA, nullptr, nA, strideA, seqB, lenB, nB, strideB, max_len_a, max_len_b, mode, out, stream);
 }
 
 }  // extern "C"

@@ -92,7 +92,16 @@ def degree_seq(g, rows, internal):
     return seq, ln
 
 
-def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_len_b=None):
+# upper length bounds of the row buckets of the exact DTW: singletons and pairs stay on the thread-per-pair mapping (a wavefront
+# group would carry one or two rows on four lanes), longer components run on the wavefront with G = bound lanes (R rows per lane
+# above 32), rows longer than 256 on the thread mapping again
+_DTW_EDGES = (2, 4, 8, 16, 32, 64, 128, 256)
+
+
+def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_len_b=None, bucketed=True):
+    """(nA, nB) similarities 1 / (1 + DTW) of every (row of A, row of B) pair; 0 for an empty sequence (SubGNN.py:831).
+    DTW_EXACT buckets the rows of A by length (index lists built with torch on the device) and launches one wavefront per
+    bucket; ``bucketed=False`` runs a single launch sized by the longest row."""
     nA, sA = seqA.shape
     nB, sB = seqB.shape
     if max_len_a is None:
@@ -100,8 +109,20 @@ def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_l
     if max_len_b is None:
         max_len_b = max(int(lenB.max().item()) if nB else 1, 1)
     out = torch.empty((nA, nB), dtype=torch.float32, device=seqA.device)
-    call('subgnn_dtw_batch', ptr(seqA), ptr(lenA), nA, sA, ptr(seqB), ptr(lenB), nB, sB, max_len_a, max_len_b, int(mode), ptr(out),
-         stream_ptr())
+    if mode != DTW_EXACT or not bucketed or nA == 0 or nB == 0:
+        call('subgnn_dtw_batch', ptr(seqA), ptr(lenA), nA, sA, ptr(seqB), ptr(lenB), nB, sB, max_len_a, max_len_b, int(mode), ptr(out),
+             stream_ptr())
+        return out
+    ln = lenA.to(torch.int64)
+    lo = -1                                                     # empty rows ride in the first bucket (the kernels write 0)
+    for hi in [b for b in _DTW_EDGES if b < max_len_a] + [max_len_a]:
+        m = DTW_EXACT if 2 < hi <= 256 else DTW_EXACT_THREAD
+        rows = torch.nonzero((ln > lo) & (ln <= hi)).reshape(-1).to(torch.int32)
+        lo = hi
+        if rows.numel() == 0:
+            continue
+        call('subgnn_dtw_batch_rows', ptr(seqA), ptr(lenA), ptr(rows), int(rows.numel()), sA, ptr(seqB), ptr(lenB), nB, sB, hi, max_len_b,
+             int(m), ptr(out), stream_ptr())
     return out
 
 

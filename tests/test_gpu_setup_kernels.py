@@ -198,9 +198,10 @@ def test_dtw_exact_wavefront_equals_thread_mapping(max_a):
     for j in range(nB):
         B[j, :lb[j]] = np.sort(rnd.randint(0, 400, size=lb[j]))
     dev = [torch.from_numpy(x).cuda() for x in (A, la, B, lb)]
-    wave = ops.dtw_batch(*dev, ops.DTW_EXACT, max_len_a=max_a, max_len_b=max_b).cpu().numpy()
+    wave = ops.dtw_batch(*dev, ops.DTW_EXACT, max_len_a=max_a, max_len_b=max_b).cpu().numpy()          # rows bucketed by length
+    wave_one = ops.dtw_batch(*dev, ops.DTW_EXACT, max_len_a=max_a, max_len_b=max_b, bucketed=False).cpu().numpy()   # one launch
     thread = ops.dtw_batch(*dev, ops.DTW_EXACT_THREAD, max_len_a=max_a, max_len_b=max_b).cpu().numpy()
-    assert np.array_equal(wave, thread)
+    assert np.array_equal(wave, thread) and np.array_equal(wave_one, thread)
     assert np.all(wave[la == 0] == 0) and np.all(wave[:, lb == 0] == 0)
     for i in rnd.choice(nA, 6, replace=False):
         for j in rnd.choice(nB, 6, replace=False):

@@ -139,10 +139,11 @@ def run(name, cpu_seconds, reps=5):
         'thread per pair, fp64 DP; FP64-issue / shared-memory bound, not HBM: mean lengths %.1f x %.1f' % (float(la_h[rows_valid].mean()), float(lb_h.mean())), cpu)
     # exact DTW on both mappings: DP cells/s (n*m per pair) — the sub-warp wavefront (registers + shuffles) against one thread per pair
     cells = float(la_h[rows_valid].astype(np.float64).sum()) * float(lb_h.astype(np.float64).sum())
-    for mode, key, note in ((ops.DTW_EXACT, 'dtw_batch_exact_wavefront', 'G lanes per pair (G from the longest component), DP columns in registers, '
-                             '__shfl_up_sync hand-off, patch sequence staged in smem'),
-                            (ops.DTW_EXACT_THREAD, 'dtw_batch_exact_thread', 'thread per pair, rolling fp64 rows in smem')):
-        t, sims_e = timed(lambda: ops.dtw_batch(sa, la, sb, lb, mode, max_len_a=Lcc, max_len_b=patches.shape[1]), reps, flush)
+    for mode, key, note, bk in ((ops.DTW_EXACT, 'dtw_batch_exact_wavefront', 'components bucketed by length (<= 2: thread per pair; else G = 4 ... 32 '
+                                 'lanes per pair), DP columns in registers, __shfl_up_sync hand-off, patch sequence staged in smem', True),
+                                (ops.DTW_EXACT, 'dtw_batch_exact_wavefront_one_launch', 'one launch, G from the longest component', False),
+                                (ops.DTW_EXACT_THREAD, 'dtw_batch_exact_thread', 'thread per pair, rolling fp64 rows in smem', False)):
+        t, sims_e = timed(lambda: ops.dtw_batch(sa, la, sb, lb, mode, max_len_a=Lcc, max_len_b=patches.shape[1], bucketed=bk), reps, flush)
         rec(key, t, pairs, '(component, patch) pairs', pairs * 4.0 * (float(la_h[rows_valid].mean()) + float(lb_h.mean()) + 1),
             note + '; %.3g DP cells/s; longest component %d' % (cells / t, int(la_h.max())))
     return res
