@@ -3,7 +3,7 @@
 // Same contract and data layout as the streaming kernels in lstm.cu (reference: SubGNN.py:60-88 nn.LSTM inside class LSTM,
 // called from anchor_patch_samplers.py:413-433); chosen by the host wrappers there whenever lstm_reg_supported(H).
 //
-// Why this shape (round-1 profile, profiles/r01_ncu_lstm_v5.txt): a thread-per-gate-column matvec reads every h value once per
+// Why this shape (round-1 profile of the streaming kernel, profiles/r01_ncu_lstm_recur_v3.txt): a thread-per-gate-column matvec reads every h value once per
 // FMA through a broadcast LDS.128 and is bound by the 128 B/clk shared-memory return path (fma pipe 23 % active).  Here each
 // thread owns a 4-sequence x 8-column register tile, so one loaded operand feeds 4-8 FMAs, and the FMAs are issued as packed
 // fma.rn.f32x2 (FFMA2, sm_100): 16 issues per k for 32 FMAs.
@@ -122,7 +122,7 @@ __device__ __forceinline__ void tile_fma(float2 (&acc)[4][4], const float4 x, co
 // ------------------------------------------------------------------------------------------------
 // Forward.  grid (n_tiles * CL, 2 directions), cluster (CL, 1, 1); block = KS * (tile/4) * (U/2) threads:
 // thread (ks, sgroup, p).  The k range is split over KS warps per register tile (the whole problem is only ~500 such tiles:
-// one warp per SM sub-partition cannot hide the FFMA2 / LDS latencies, profiles/r01_ncu_lstm_v6.txt), the partial tiles meet in
+// one warp per SM sub-partition cannot hide the FFMA2 / LDS latencies: measured with tools/lstm_bench.py), the partial tiles meet in
 // shared memory and each of the KS threads finishes 4/KS of the tile's sequences (activations, cell update, outputs).
 // Wp: permuted transposed weights written by lstm_prep_kernel: [dir][rank][k][half][p][4] with the 4 = (gate 2 half + {0,1}) x
 // (unit 2p + {0,1}): a thread's two float4 loads per k are contiguous across the warp (conflict free).

@@ -173,7 +173,7 @@ struct MNMajorStager {
 #define TC_EPI_LD 36      // padded row length (floats) of the per-warp transposition slab: conflict-free float4 in both directions
 // STAGES = 2 double-buffers the operand tiles: the threads split / store block kb+1 while the tensor core still works on block
 // kb (the single-buffered loop serialises load latency, store and MMA of every block: ~1.5 us per 32-wide block measured
-// in the step timeline, profiles/r01_timeline_ppi_bp.txt); STAGES = 1 keeps 3 CTAs per SM for the short reductions.
+// in the step timeline, profiles/r01_timeline_ppi_bp_v10.txt); STAGES = 1 keeps 3 CTAs per SM for the short reductions.
 template <int N_TILE, int STAGES, class LoadA, class LoadB, class StoreA, class StoreB, class Epi>
 __device__ __forceinline__ void tc_tile(int kr0, int kr1, LoadA load_a, LoadB load_b, StoreA store_a, StoreB store_b, Epi epi) {
   extern __shared__ unsigned char smem_raw[];

@@ -98,6 +98,15 @@ def degree_seq(g, rows, internal):
 _DTW_EDGES = (2, 4, 8, 16, 32, 64, 128, 256)
 
 
+def dtw_bucket_plan(max_len_a):
+    """[(lo, hi, mode)]: rows of A with lo < length <= hi run in one launch of ``mode`` sized for length hi."""
+    plan, lo = [], -1                                           # empty rows ride in the first bucket (the kernels write 0)
+    for hi in [b for b in _DTW_EDGES if b < max_len_a] + [max_len_a]:
+        plan.append((lo, hi, DTW_EXACT if 2 < hi <= 256 else DTW_EXACT_THREAD))
+        lo = hi
+    return plan
+
+
 def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_len_b=None, bucketed=True):
     """(nA, nB) similarities 1 / (1 + DTW) of every (row of A, row of B) pair; 0 for an empty sequence (SubGNN.py:831).
     DTW_EXACT buckets the rows of A by length (index lists built with torch on the device) and launches one wavefront per
@@ -114,11 +123,8 @@ def dtw_batch(seqA, lenA, seqB, lenB, mode=DTW_FASTDTW_R1, max_len_a=None, max_l
              stream_ptr())
         return out
     ln = lenA.to(torch.int64)
-    lo = -1                                                     # empty rows ride in the first bucket (the kernels write 0)
-    for hi in [b for b in _DTW_EDGES if b < max_len_a] + [max_len_a]:
-        m = DTW_EXACT if 2 < hi <= 256 else DTW_EXACT_THREAD
+    for lo, hi, m in dtw_bucket_plan(max_len_a):
         rows = torch.nonzero((ln > lo) & (ln <= hi)).reshape(-1).to(torch.int32)
-        lo = hi
         if rows.numel() == 0:
             continue
         call('subgnn_dtw_batch_rows', ptr(seqA), ptr(lenA), ptr(rows), int(rows.numel()), sA, ptr(seqB), ptr(lenB), nB, sB, hi, max_len_b,

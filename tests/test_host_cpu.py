@@ -97,3 +97,32 @@ def test_missing_library_fails_loudly(tmp_path, monkeypatch):
     ns = {'__file__': str(tmp_path / '_abi.py'), '__name__': 'x'}
     with pytest.raises(ImportError):
         exec(compile(src, 'x', 'exec'), ns)
+
+
+def test_dtw_bucket_plan_covers_every_length_once():
+    """host side of the exact DTW: length buckets are disjoint, cover 0 .. max_len, end at max_len, and route singletons / pairs
+    and rows beyond 256 to the thread-per-pair mapping, everything else to the wavefront."""
+    from subgnn_b200 import ops
+    for max_len in (1, 2, 3, 4, 5, 20, 32, 33, 150, 256, 257, 1000):
+        plan = ops.dtw_bucket_plan(max_len)
+        assert plan[0][0] == -1 and plan[-1][1] == max_len
+        assert all(a[1] == b[0] for a, b in zip(plan, plan[1:])) and all(lo < hi for lo, hi, _ in plan)
+        for lo, hi, mode in plan:
+            assert mode == (ops.DTW_EXACT if 2 < hi <= 256 else ops.DTW_EXACT_THREAD)
+            assert hi <= max_len
+
+
+def test_bench_stdout_carries_exactly_one_json_line():
+    """bench.py points fd 1 at stderr for the life of the process and writes the result to a private duplicate of stdout, so that
+    banners of native libraries (NCCL under torchrun) cannot land between the driver and the JSON line."""
+    import json
+    import subprocess
+    import sys
+    from pathlib import Path
+    root = Path(__file__).resolve().parents[1]
+    code = ("import os, sys; sys.path.insert(0, %r); import bench; bench._claim_stdout(); os.write(1, b'native banner\\n'); "
+            "print('python print'); bench.emit({'ok': 1})" % str(root))
+    r = subprocess.run([sys.executable, '-c', code], capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    assert r.stdout.strip().splitlines() == [json.dumps({'ok': 1})]
+    assert 'native banner' in r.stderr and 'python print' in r.stderr
