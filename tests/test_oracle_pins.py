@@ -101,6 +101,33 @@ def test_fastdtw_known_answers():
             assert fa == ex
 
 
+def test_exact_dtw_against_an_independent_formulation():
+    """og.dtw_exact (row-by-row DP, the oracle of SUBGNN_DTW_EXACT / _THREAD) against a memoised top-down recursion over the
+    definition D(i, j) = d(x_i, y_j) + min(D(i-1, j), D(i, j-1), D(i-1, j-1)) — a different evaluation order of the same sums."""
+    import functools
+    rnd = random.Random(11)
+    for _ in range(200):
+        x = sorted(rnd.randint(0, 40) for _ in range(rnd.randint(1, 18)))
+        y = sorted(rnd.randint(0, 400) for _ in range(rnd.randint(1, 30)))
+
+        @functools.lru_cache(maxsize=None)
+        def D(i, j):
+            c = og.calc_dist(x[i], y[j])
+            if i == 0 and j == 0:
+                return c
+            best = float('inf')
+            if i > 0:
+                best = min(best, D(i - 1, j))
+            if j > 0:
+                best = min(best, D(i, j - 1))
+            if i > 0 and j > 0:
+                best = min(best, D(i - 1, j - 1))
+            return c + best
+
+        assert og.dtw_exact(x, y)[0] == D(len(x) - 1, len(y) - 1)
+        assert og.calc_dtw(x, y, 'exact') == 1.0 / (1.0 + D(len(x) - 1, len(y) - 1))
+
+
 def canon_cc(cc):
     out = []
     for sub in cc:
