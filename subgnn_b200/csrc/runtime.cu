@@ -17,7 +17,9 @@ void subgnn_set_error(const char* fmt, ...) {
 // default classes launched with programmatic stream serialization (see sg_pdl_sync in common.cuh).  Measured on B200, ms/step
 // (ppi_bp / hpo_metab / em_user shapes, same box): mask 0: 0.445 / 0.860 / 0.712; 4 (recurrences): 0.442 / 0.843 / 0.727;
 // 14 (GEMMs + recurrences + row kernels): 0.431 / 0.800 / 0.739; 15 (everything): 0.426 / 0.879 / 0.827 — early-scheduled
-// small kernels take SM slots from the other graph branches at the two H = 128 shapes.
+// small kernels take SM slots from the other graph branches at the two H = 128 shapes.  Bit 4 (SG_PDL_CHAIN: the small kernels ON
+// the critical chain — readout MLP, structure q, LSTM head, optimizer) added later, same three shapes, mask 14 -> 30:
+// 0.3896 -> 0.3833 / 0.7546 -> 0.7473 / 0.659 -> 0.653.
 #define SUBGNN_PDL_DEFAULT_MASK 30
 
 static unsigned long long g_launches = 0;
