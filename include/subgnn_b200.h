@@ -33,6 +33,10 @@ int subgnn_abi_version(void);
 int subgnn_device_sm_count(void);
 /* number of kernels this library has launched (or recorded into a CUDA graph under capture) so far */
 unsigned long long subgnn_launch_count(void);
+/* test aid: the distinct kernel template instantiations launched so far, ';'-separated ("row_fwd<2>;lstm_fwd_tile<1,4,64>;..."),
+ * written into buf (cap bytes, NUL terminated); returns their number.  _reset clears the log. */
+int subgnn_variant_log(char* buf, int cap);
+void subgnn_variant_log_reset(void);
 
 /* ---- (1) anchor_patch_samplers.py ------------------------------------------------------------- */
 
@@ -149,9 +153,6 @@ int subgnn_lstm_recur_fwd_drop(float* G, const float* whh_t, float* OUT, float* 
 int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
                                int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed,
                                unsigned salt, const int* step_dev, void* stream);
-int subgnn_add_inplace(float* dst, const float* src, int n, void* stream);
-int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream);
-int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream);
 /* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out)), SubGNN.py:83-88).
    The head is linear, so the walks are summed first: fwd  AGG[g] = sum_w agg(OUT[g*group+w]),  EMB[g] = W AGG[g] + group * bias;
    bwd  dOUT rows <- W^T dEMB[g] (t = T-1 only for 'last'),  db += group * sum_g dEMB[g]   (dW = dEMB^T AGG: subgnn_linear_bwd_weight).
@@ -162,8 +163,6 @@ int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* 
                          int D, int sum_mode, void* stream);
 int subgnn_lstm_head_bwd(const float* dEMB, const float* W, float* dOUT, float* db, int n_groups, int group, int T, int H2, int D,
                          int sum_mode, void* stream);
-int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream);
-int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream);
 int subgnn_dropout(const float* x, float* y, long long n, float p, unsigned long long seed, unsigned salt, const int* step_dev,
                    void* stream);
 int subgnn_colsum(const float* dy, int ldy, float* db, int M, int N, const int* m_dev, void* stream);
@@ -234,10 +233,8 @@ typedef struct subgnn_model_desc {
 } subgnn_model_desc;
 
 /* batch bookkeeping + per-step weight transposes + q = w_p . x_anchor for every shared anchor list */
-int subgnn_model_prep(const subgnn_model_desc* d, void* stream);          /* == prep_batch + prep_weights */
 int subgnn_model_prep_batch(const subgnn_model_desc* d, void* stream);
 int subgnn_model_prep_weights(const subgnn_model_desc* d, void* stream);
-int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream);         /* == q_fwd_part(POS | STRUC) */
 #define SUBGNN_Q_POS 1     /* position-channel anchors (node embeddings) */
 #define SUBGNN_Q_STRUC 2   /* structure-channel anchors (LSTM output emb_s) */
 int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream);
@@ -245,17 +242,15 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
  * with it on another stream: SUBGNN_PHASE_N = pooling + N channel, SUBGNN_PHASE_PS = P / S property-aware outputs. */
 #define SUBGNN_PHASE_N 1
 #define SUBGNN_PHASE_PS 2
+/* rows_fwd + mlp_fwd together are SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers
+ * subgraph_mpn.py:133-241, masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training
+ * mlp_fwd also runs the MLP backward down to dZ. */
 int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream);
 int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training); H1 must be zero on entry (split-K target) */
+/* backward of all rows (autograd of the above): N-channel chains, property-aware outputs, pooling; scatters into dE / dq / Ndpre */
 int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream);
-/* SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers subgraph_mpn.py:133-241,
- * masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training also the
- * per-sample MLP backward (dZ). */
-int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream);
 /* per-sample MLP backward from externally supplied dlogits (autograd entry) */
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream);
-/* backward of all rows: N-channel chains, property-aware outputs, pooling; scatters into dE / dq / Ndpre */
-int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream);
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);
 /* weight gradients of the N-channel MPN projections and the MLP */
 int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream);

@@ -33,16 +33,21 @@ from .formats import SimilarityCache, load_embeddings, load_hop_table, read_edge
 
 class _LSTMFunction(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, module, x, *params):
-        runner, arena = module._runner_for(x.shape[0], x.shape[1])
+    def forward(ctx, module, keep, x, *params):
+        runner, arena = module._acquire(x.shape[0], x.shape[1])
         module._pack(arena, params)
         xc = x.contiguous().float()
         st = _abi.stream_ptr()
         call('subgnn_inc_step', ptr(module._step), st)
-        runner.forward(None, module.training, module._seed, ptr(module._step), st, dense_x=xc.view(-1, x.shape[2]))
-        ctx.module, ctx.runner, ctx.arena, ctx.training = module, runner, arena, module.training
-        ctx.x_shape = x.shape
-        return runner.EMB.clone()
+        runner.step_dev.copy_(module._step)                   # this call's dropout counter, read again by ITS backward
+        runner.forward(None, module.training, module._seed, ptr(runner.step_dev), st, dense_x=xc.view(-1, x.shape[2]))
+        out = runner.EMB.clone()
+        if keep:
+            ctx.module, ctx.runner, ctx.arena, ctx.training = module, runner, arena, module.training
+            ctx.x_shape = x.shape
+        else:                                                 # no backward will come (no_grad / nothing requires grad)
+            module._release(runner, arena)
+        return out
 
     @staticmethod
     def backward(ctx, dy):
@@ -51,8 +56,10 @@ class _LSTMFunction(torch.autograd.Function):
         call('subgnn_fill_zero', ptr(arena.grads), arena.size, st)
         runner.dEMB.copy_(dy.contiguous())
         dx = torch.empty(ctx.x_shape, dtype=torch.float32, device=dy.device)
-        runner.backward(None, None, ctx.training, m._seed, ptr(m._step), st, dense_dx=dx.view(-1, ctx.x_shape[2]))
-        return (None, dx) + tuple(arena.view(n, 'grads').clone() for n in m._arena_names)
+        runner.backward(None, None, ctx.training, m._seed, ptr(runner.step_dev), st, dense_dx=dx.view(-1, ctx.x_shape[2]))
+        grads = tuple(arena.view(n, 'grads').clone() for n in m._arena_names)
+        m._release(runner, arena)
+        return (None, None, dx) + grads
 
 
 class LSTM(nn.Module):
@@ -80,29 +87,36 @@ class LSTM(nn.Module):
     def _module_params(self):
         return [self.get_parameter(n[len('lstm.'):]) for n in self._arena_names]
 
-    def _runner_for(self, n_seq, T):
+    def _acquire(self, n_seq, T):
+        """one runner per OUTSTANDING forward: its buffers hold the activations saved for that call's backward (the reference
+        calls the shared LSTM 2 * n_layers times per step — internal / border side of every layer, anchor_patch_samplers.py:429 —
+        before loss.backward()).  Runners come from a free list per (n_seq, T) and return to it in backward."""
         from .engine import LstmRunner, ParamArena
-        # a fresh runner per call: its buffers hold the activations saved for this call's backward (the reference calls the
-        # shared LSTM several times per step — internal / border side of every layer — before loss.backward())
-        key = (n_seq, T, len(self._runners))
-        if key not in self._runners:
-            self._runners.clear()
-            dev = self.linear.weight.device
-            hp = {'node_embed_size': self.h, 'n_layers': 1, 'freeze_node_embeds': True, 'use_neighborhood': False, 'use_position': False,
-                  'use_structure': False, 'lstm_n_layers': self.num_layers, 'linear_hidden_dim_1': 1, 'linear_hidden_dim_2': 1, 'trainable_cc': False,
-                  'n_triangular_walks': 1, 'lstm_aggregator': self.aggregator, 'lstm_dropout': self.dropout}
-            arena = ParamArena(hp, 0, 1, 1, device=dev)
-            self._runners[key] = (LstmRunner(arena, hp, None, n_seq, dev, n_seq=n_seq, T=T), arena)
-            if self._step is None:
-                self._step = torch.zeros(1, dtype=torch.int32, device=dev)
-        return self._runners[key]
+        free = self._runners.setdefault((n_seq, T), [])
+        if free:
+            return free.pop()
+        dev = self.linear.weight.device
+        hp = {'node_embed_size': self.h, 'n_layers': 1, 'freeze_node_embeds': True, 'use_neighborhood': False, 'use_position': False,
+              'use_structure': False, 'lstm_n_layers': self.num_layers, 'linear_hidden_dim_1': 1, 'linear_hidden_dim_2': 1, 'trainable_cc': False,
+              'n_triangular_walks': 1, 'lstm_aggregator': self.aggregator, 'lstm_dropout': self.dropout}
+        arena = ParamArena(hp, 0, 1, 1, device=dev)
+        runner = LstmRunner(arena, hp, None, n_seq, dev, n_seq=n_seq, T=T)
+        runner.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
+        if self._step is None:
+            self._step = torch.zeros(1, dtype=torch.int32, device=dev)
+        return runner, arena
+
+    def _release(self, runner, arena):
+        self._runners[(runner.n_seq, runner.T)].append((runner, arena))
 
     def _pack(self, arena, params):
         for name, p in zip(self._arena_names, params):
             arena.view(name).copy_(p.detach())
 
     def forward(self, input):
-        return _LSTMFunction.apply(self, input, *self._module_params())
+        params = self._module_params()
+        keep = torch.is_grad_enabled() and (input.requires_grad or any(p.requires_grad for p in params))
+        return _LSTMFunction.apply(self, keep, input, *params)
 
 
 class _EngineFunction(torch.autograd.Function):
@@ -113,14 +127,19 @@ class _EngineFunction(torch.autograd.Function):
     def forward(ctx, module, split, indices, training, *params):
         eng = module.engine
         logits, _ = eng.forward(split, indices, training=training)
-        ctx.module, ctx.split, ctx.B = module, split, len(indices)
+        ctx.module, ctx.split, ctx.B, ctx.training = module, split, len(indices), training
+        ctx.generation = eng.context(split, len(indices), training).generation
         return logits.clone()
 
     @staticmethod
     def backward(ctx, dlogits):
         m = ctx.module
         eng = m.engine
-        eng.backward(ctx.split, ctx.B, training=True, external_dlogits=dlogits.contiguous())
+        c = eng.context(ctx.split, ctx.B, ctx.training)
+        if c.generation != ctx.generation:
+            raise RuntimeError('SubGNN backward after another forward of the same (split, batch size, mode): the step buffers hold '
+                               'the later forward\'s activations (call backward before the next forward)')
+        eng.backward(ctx.split, ctx.B, training=ctx.training, external_dlogits=dlogits.contiguous())
         grads = [eng.arena.view(name, 'grads').clone() for name in m._param_names]
         return (None, None, None, None) + tuple(grads)
 

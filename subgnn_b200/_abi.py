@@ -51,25 +51,16 @@ SIGNATURES = {
     'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'subgnn_lstm_recur_fwd_drop': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
     'subgnn_lstm_recur_bwd_drop': [P, P, P, P, P, I, I, I, I, I, I, P, P, F, U64, U32, P, P],
-    'subgnn_add_inplace': [P, P, I, P],
-    'subgnn_lstm_agg_fwd': [P, P, I, I, I, I, P],
-    'subgnn_lstm_agg_bwd': [P, P, I, I, I, I, P],
     'subgnn_lstm_head_fwd': [P, P, P, P, P, I, I, I, I, I, I, P],
     'subgnn_lstm_head_bwd': [P, P, P, P, I, I, I, I, I, I, P],
-    'subgnn_group_sum': [P, P, I, I, I, P],
-    'subgnn_group_bcast': [P, P, I, I, I, P],
     'subgnn_dropout': [P, P, LL, F, U64, U32, P, P],
-    'subgnn_model_prep': [P, P],
     'subgnn_model_prep_batch': [P, P],
     'subgnn_model_prep_weights': [P, P],
     'subgnn_model_q_fwd_part': [P, I, P],
     'subgnn_model_rows_fwd': [P, I, P],
     'subgnn_model_mlp_fwd': [P, P],
     'subgnn_model_rows_bwd': [P, I, P],
-    'subgnn_model_q_fwd': [P, P],
-    'subgnn_model_sub_fwd': [P, P],
     'subgnn_model_mlp_bwd': [P, P],
-    'subgnn_model_sub_bwd': [P, P],
     'subgnn_model_q_bwd': [P, P],
     'subgnn_model_wgrad': [P, P],
     'subgnn_mpn_fwd': [P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, P],
@@ -87,6 +78,8 @@ _OTHER = {
     'subgnn_model_desc_size': ([], I),
     'subgnn_launch_count': ([], U64),
     'subgnn_lstm_fused_dropout_supported': ([I], I),
+    'subgnn_variant_log': ([C.c_char_p, I], I),
+    'subgnn_variant_log_reset': ([], None),
 }
 
 
@@ -168,6 +161,16 @@ class ModelDesc(C.Structure):
 
 assert C.sizeof(ModelDesc) == lib.subgnn_model_desc_size(), \
     'subgnn_model_desc layout mismatch: ctypes %d vs C %d' % (C.sizeof(ModelDesc), lib.subgnn_model_desc_size())
+
+
+def variant_log(reset=False):
+    """set of kernel template instantiations launched so far (test aid, see include/subgnn_b200.h)."""
+    buf = C.create_string_buffer(4096)
+    lib.subgnn_variant_log(buf, 4096)
+    out = set(x for x in buf.value.decode().split(';') if x)
+    if reset:
+        lib.subgnn_variant_log_reset()
+    return out
 
 
 def exported_symbols():

@@ -15,12 +15,21 @@ from . import PAD_VALUE, ops
 from .graph import ragged_from_padded, resolve_graph
 
 _calls = defaultdict(int)
+# fixed call-site table (NOT hash(site): CPython salts str hashes per process, which made the module-level samplers differ from run
+# to run and between data-parallel ranks)
+_SITES = {'trw': 1, 'prw_in': 2, 'prw_bor': 3, 'ssap': 4, 'snap_in': 5, 'snap_out': 6, 'spap': 7, 'iapi': 8, 'ias': 9}
 
 
 def _seed(hparams, site):
-    """distinct Philox key per call site and call count (a re-sample must differ from the first sample)."""
+    """distinct Philox key per call site and call count (a re-sample must differ from the first sample); a function of
+    (hparams['seed'], site, number of earlier calls from that site in this process) only."""
     _calls[site] += 1
-    return (int(hparams.get('seed', 0)) * 1000003 + hash(site) % 9973) * 4099 + _calls[site]
+    return (int(hparams.get('seed', 0)) * 1000003 + _SITES[site] * 911) * 4099 + _calls[site]
+
+
+def reset_call_counters():
+    """start the per-site call counters again (a fresh process starts at zero: same seed => same samples)."""
+    _calls.clear()
 
 
 # ---- walks ---------------------------------------------------------------------------------------------

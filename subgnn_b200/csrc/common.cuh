@@ -10,6 +10,7 @@
 
 void subgnn_set_error(const char* fmt, ...);
 int subgnn_check_launch(const char* what);
+void subgnn_note_variant(const char* fmt, ...);
 
 #define SG_REQUIRE(cond, msg)                                  \
   do {                                                         \

@@ -241,52 +241,6 @@ lstm_recur_bwd_kernel(float* __restrict__ G, const float* __restrict__ Whh, cons
   }
 }
 
-// AGG[seq][2H] = OUT[seq][T-1][:] ('last', SubGNN.py:83) or sum_t OUT[seq][t][:] ('sum', :85)
-__global__ void lstm_agg_fwd_kernel(const float* __restrict__ OUT, float* __restrict__ AGG, int n_seq, int T, int H2, int sum_mode) {
-  const long long total = (long long)n_seq * H2;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int seq = (int)(e / H2), c = (int)(e % H2);
-    float v;
-    if (sum_mode) {
-      v = 0.f;
-      for (int t = 0; t < T; ++t) v += OUT[((size_t)seq * T + t) * H2 + c];
-    } else {
-      v = OUT[((size_t)seq * T + T - 1) * H2 + c];
-    }
-    AGG[e] = v;
-  }
-}
-
-// dOUT[seq][t][:] = dAGG[seq][:] for every t ('sum') or only t = T-1 ('last', zero elsewhere)
-__global__ void lstm_agg_bwd_kernel(const float* __restrict__ dAGG, float* __restrict__ dOUT, int n_seq, int T, int H2, int sum_mode) {
-  const long long total = (long long)n_seq * T * H2;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int c = (int)(e % H2);
-    const long long st = e / H2;
-    const int t = (int)(st % T), seq = (int)(st / T);
-    dOUT[e] = (sum_mode || t == T - 1) ? dAGG[(size_t)seq * H2 + c] : 0.f;
-  }
-}
-
-// EMB[g][d] = sum_{w<group} Y[g*group + w][d]       (anchor_patch_samplers.py:433)
-__global__ void group_sum_kernel(const float* __restrict__ Y, float* __restrict__ EMB, int n_groups, int group, int D) {
-  const long long total = (long long)n_groups * D;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int g = (int)(e / D), d = (int)(e % D);
-    float v = 0.f;
-    for (int w = 0; w < group; ++w) v += Y[((size_t)g * group + w) * D + d];
-    EMB[e] = v;
-  }
-}
-__global__ void group_bcast_kernel(const float* __restrict__ dEMB, float* __restrict__ dY, int n_groups, int group, int D) {
-  const long long total = (long long)n_groups * group * D;
-  for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
-    const int d = (int)(e % D);
-    const long long row = e / D;
-    dY[e] = dEMB[(row / group) * D + d];
-  }
-}
-
 // Walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out))).  The head
 // is linear, so the walks are summed first and the Linear runs once per patch.  One CTA per patch g:
 //   AGG[g][c] = sum_{w<group} agg(OUT[g*group + w])[c]          (agg = row T-1 for 'last', SubGNN.py:83; sum over t for 'sum', :85)
@@ -451,17 +405,7 @@ __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __r
   }
 }
 
-__global__ void add_inplace_kernel(float* __restrict__ dst, const float* __restrict__ src, int n) {
-  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) dst[i] += src[i];
-}
-
 extern "C" {
-
-int subgnn_add_inplace(float* dst, const float* src, int n, void* stream) {
-  if (n <= 0) return SUBGNN_OK;
-  add_inplace_kernel<<<sg_grid_for(n, 256, 2), 256, 0, (cudaStream_t)stream>>>(dst, src, n);
-  return subgnn_check_launch("add_inplace_kernel");
-}
 
 static int lstm_block(int H) { return ((4 * H + 31) / 32) * 32; }
 
@@ -548,30 +492,6 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
   else LSTM_BWD_LAUNCH(false, 1024);
 #undef LSTM_BWD_LAUNCH
   return subgnn_check_launch("lstm_recur_bwd_kernel");
-}
-
-int subgnn_lstm_agg_fwd(const float* OUT, float* AGG, int n_seq, int T, int H2, int sum_mode, void* stream) {
-  if (n_seq == 0) return SUBGNN_OK;
-  lstm_agg_fwd_kernel<<<sg_grid_for((long long)n_seq * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(OUT, AGG, n_seq, T, H2, sum_mode);
-  return subgnn_check_launch("lstm_agg_fwd_kernel");
-}
-
-int subgnn_lstm_agg_bwd(const float* dAGG, float* dOUT, int n_seq, int T, int H2, int sum_mode, void* stream) {
-  if (n_seq == 0) return SUBGNN_OK;
-  lstm_agg_bwd_kernel<<<sg_grid_for((long long)n_seq * T * H2, 256, 8), 256, 0, (cudaStream_t)stream>>>(dAGG, dOUT, n_seq, T, H2, sum_mode);
-  return subgnn_check_launch("lstm_agg_bwd_kernel");
-}
-
-int subgnn_group_sum(const float* Y, float* EMB, int n_groups, int group, int D, void* stream) {
-  if (n_groups == 0) return SUBGNN_OK;
-  group_sum_kernel<<<sg_grid_for((long long)n_groups * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(Y, EMB, n_groups, group, D);
-  return subgnn_check_launch("group_sum_kernel");
-}
-
-int subgnn_group_bcast(const float* dEMB, float* dY, int n_groups, int group, int D, void* stream) {
-  if (n_groups == 0) return SUBGNN_OK;
-  group_bcast_kernel<<<sg_grid_for((long long)n_groups * group * D, 256, 8), 256, 0, (cudaStream_t)stream>>>(dEMB, dY, n_groups, group, D);
-  return subgnn_check_launch("group_bcast_kernel");
 }
 
 int subgnn_lstm_head_fwd(const float* OUT, float* AGG, float* EMB, const float* W, const float* bias, int n_groups, int group, int T, int H2,

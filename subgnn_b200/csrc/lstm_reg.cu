@@ -528,6 +528,7 @@ int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int 
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  subgnn_note_variant("lstm_fwd_tile_kernel<%d,%d,%d>", CL, KS, HC);
   cudaLaunchKernelEx(&cfg, lstm_fwd_tile_kernel<CL, KS, HC>, G, wp, OUT, CS, n_seq, T, H, sf, sr, tile, drop);
   return subgnn_check_launch("lstm_fwd_tile_kernel");
 }
@@ -553,6 +554,7 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_RECUR);
   cfg.attrs = attr;
   cfg.numAttrs = 2;
+  subgnn_note_variant("lstm_bwd_tile_kernel<%d,%d,%d>", CL, KS, HC);
   cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS, HC>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile, drop);
   return subgnn_check_launch("lstm_bwd_tile_kernel");
 }

@@ -855,6 +855,7 @@ static int check_desc(const Desc* d) {
 #define DISPATCH_DPL(D, KERNEL, ...)                                   \
   do {                                                                 \
     const int dpl_ = ((D) + 31) / 32;                                  \
+    subgnn_note_variant(#KERNEL "<%d>", dpl_ <= 1 ? 1 : dpl_ <= 2 ? 2 : dpl_ <= 4 ? 4 : 8);   \
     if (dpl_ <= 1) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<1>, __VA_ARGS__); }          \
     else if (dpl_ <= 2) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<2>, __VA_ARGS__); }     \
     else if (dpl_ <= 4) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<4>, __VA_ARGS__); }     \
@@ -885,12 +886,6 @@ int subgnn_model_prep_weights(const subgnn_model_desc* d, void* stream) {
   return subgnn_check_launch("transpose_weights_kernel");
 }
 
-int subgnn_model_prep(const subgnn_model_desc* d, void* stream) {
-  int rc = subgnn_model_prep_batch(d, stream);
-  if (rc) return rc;
-  return subgnn_model_prep_weights(d, stream);
-}
-
 int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
@@ -905,8 +900,6 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
     sg_launch_pdl(q_fwd_kernel, dim3(sg_grid_for(total, 8, 8)), dim3(256), 0, (cudaStream_t)stream, *d, which);
   return subgnn_check_launch("q_fwd_kernel");
 }
-
-int subgnn_model_q_fwd(const subgnn_model_desc* d, void* stream) { return subgnn_model_q_fwd_part(d, SUBGNN_Q_POS | SUBGNN_Q_STRUC, stream); }
 
 int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) {
   int rc = check_desc(d);
@@ -952,12 +945,6 @@ int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   return rc;
 }
 
-int subgnn_model_sub_fwd(const subgnn_model_desc* d, void* stream) {
-  int rc = subgnn_model_rows_fwd(d, SUBGNN_PHASE_N | SUBGNN_PHASE_PS, stream);
-  if (rc) return rc;
-  return subgnn_model_mlp_fwd(d, stream);
-}
-
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
@@ -975,8 +962,6 @@ int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) 
   DISPATCH_DPL(d->D, row_bwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), bwd_smem(*d), (cudaStream_t)stream, *d, phases);
   return subgnn_check_launch("row_bwd_kernel");
 }
-
-int subgnn_model_sub_bwd(const subgnn_model_desc* d, void* stream) { return subgnn_model_rows_bwd(d, SUBGNN_PHASE_N | SUBGNN_PHASE_PS, stream); }
 
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);

@@ -24,6 +24,23 @@ void subgnn_set_error(const char* fmt, ...) {
 
 static unsigned long long g_launches = 0;
 
+// kernel-instantiation log: the dispatchers note which template instantiation they launched ("row_fwd<2>", "lstm_fwd_tile<1,4,64>",
+// "tc_gemm<fwd,128>" ...) so that the parity tests can assert that they exercised the instantiations the benchmark shapes run
+#define SG_VARIANT_MAX 64
+static char g_variants[SG_VARIANT_MAX][48];
+static int g_n_variants = 0;
+
+void subgnn_note_variant(const char* fmt, ...) {
+  char buf[48];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  for (int i = 0; i < g_n_variants; ++i)
+    if (strcmp(g_variants[i], buf) == 0) return;
+  if (g_n_variants < SG_VARIANT_MAX) strcpy(g_variants[g_n_variants++], buf);
+}
+
 int subgnn_check_launch(const char* what) {
   ++g_launches;   // one call per kernel launch (also while a CUDA graph is being captured)
   cudaError_t e = cudaGetLastError();
@@ -58,4 +75,18 @@ const char* subgnn_last_error(void) { return g_err; }
 int subgnn_abi_version(void) { return SUBGNN_ABI_VERSION; }
 int subgnn_device_sm_count(void) { return subgnn_sm_count(); }
 unsigned long long subgnn_launch_count(void) { return g_launches; }
+int subgnn_variant_log(char* buf, int cap) {
+  int n = 0;
+  if (cap > 0) buf[0] = 0;
+  for (int i = 0; i < g_n_variants; ++i) {
+    const int len = (int)strlen(g_variants[i]);
+    if (n + len + 2 > cap) break;
+    memcpy(buf + n, g_variants[i], len);
+    n += len;
+    buf[n++] = ';';
+    buf[n] = 0;
+  }
+  return g_n_variants;
+}
+void subgnn_variant_log_reset(void) { g_n_variants = 0; }
 }

@@ -393,6 +393,7 @@ static int tc_stages(int n_kb) { (void)n_kb; return tc_env("SUBGNN_TC_STAGES", 1
 
 #define TC_LAUNCH(KERNEL, NT, STAGES, grid, st, ...)                                                                          \
   do {                                                                                                                        \
+    subgnn_note_variant(#KERNEL "<%d,%d>", NT, STAGES);                                                                       \
     cudaFuncSetAttribute(KERNEL<NT, STAGES>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc_smem<NT, STAGES>());          \
     sg_launch_pdl<SG_PDL_GEMM>(KERNEL<NT, STAGES>, grid, dim3(TC_THREADS), tc_smem<NT, STAGES>(), st, __VA_ARGS__);             \
   } while (0)

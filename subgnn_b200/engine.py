@@ -489,6 +489,7 @@ class StepContext:
         self.desc = d
         self.dptr = C.addressof(d)
         self.graph = None
+        self.generation = 0          # forwards run on this context (an autograd backward checks it reads its own forward's buffers)
 
 
 class Engine:
@@ -760,6 +761,12 @@ class Engine:
         c = self.context(split, len(indices), training)
         self.set_batch(c, indices)
         st = _abi.stream_ptr()
+        if training:
+            # a training forward outside the fused step (SubGNN.training_step -> autograd): the dropout masks are keyed on
+            # (seed, step counter, element), so the counter advances here as it does in _grad_launches; the matching backward
+            # (same counter value) must run before the next training forward — guarded by the context generation
+            call('subgnn_inc_step', ptr(self.step_dev), st)
+        c.generation += 1
         self._forward_launches(c, st)
         return c.logits, c.loss
 

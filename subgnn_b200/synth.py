@@ -130,10 +130,16 @@ def make_subgraphs(name, n_nodes, rp, col, n_sub, rs):
     return subs
 
 
-def make_workload(name, seed=42, device='cuda', scale_subgraphs=1):
-    """-> (hparams, DeviceGraph, subgraphs{split}, labels{split}, embeddings)"""
+def make_workload(name, seed=42, device='cuda', scale_subgraphs=1, graph=None, n_sub=None):
+    """-> (hparams, DeviceGraph, subgraphs{split}, labels{split}, embeddings).
+    graph=('ba', n, m) / n_sub override the base graph and the subgraph count (reduced-size instances of a named shape for the
+    parity tests: every hyper-parameter, hence every kernel instantiation, stays the benchmark's)."""
     from .graph import DeviceGraph
-    w = WORKLOADS[name]
+    w = dict(WORKLOADS[name])
+    if graph is not None:
+        w['graph'] = graph
+    if n_sub is not None:
+        w['n_sub'] = n_sub
     hp = hparams(name)
     _, n, m = w['graph']
     edges = ba_edges(n, m, seed)

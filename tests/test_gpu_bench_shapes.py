@@ -1,0 +1,88 @@
+"""Parity of the fused engine at the BENCHMARKED shapes: reduced-size instances (<= 2 k-node base graph,
+a few hundred subgraphs) of all five BASELINE.json configurations with their REAL hyper-parameters
+(best_model_hyperparameters/*/ as inlined in subgnn_b200/synth.py: D, L, anchor counts, walks, LSTM depth, batch size), so that
+the kernel template instantiations the bench times are the ones compared with the CPU oracle:
+row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the tcgen05 projection GEMMs at M = n_seq * T.
+Dropout is 0 (its law is tested in test_gpu_dropout_law.py); tolerance fp32 rtol 1e-4 / atol 1e-5 (stated, as test_gpu_model.py).
+Reference path: SubGNN.py:225-348 forward / training_step, :1156-1164 Adam, Lightning clip_grad_norm_."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+# name -> (reduced base graph, n_sub, kernel instantiations that must have been launched)
+SHAPES = {
+    'density': (('ba', 1200, 5), 100, ['row_fwd_kernel<1>', 'row_bwd_kernel<1>', 'lstm_fwd_tile_kernel<1,4,32>', 'lstm_bwd_tile_kernel<1,4,32>']),
+    'cutratio': (('ba', 1200, 5), 200, ['lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>', 'tc_linear_fwd_kernel', 'tc_linear_bwd_weight_kernel']),
+    'ppi_bp': (('ba', 1500, 19), 60, ['row_fwd_kernel<2>', 'row_bwd_kernel<2>', 'lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>',
+                                      'tc_linear_fwd_kernel', 'tc_linear_bwd_input_kernel', 'tc_linear_bwd_weight_kernel']),
+    'hpo_metab': (('ba', 1500, 60), 100, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
+                                          'tc_linear_fwd_kernel', 'tc_linear_bwd_input_kernel', 'tc_linear_bwd_weight_kernel']),
+    'em_user': (('ba', 2000, 40), 48, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
+                                       'tc_linear_fwd_kernel', 'tc_linear_bwd_weight_kernel']),
+}
+
+
+def build(name):
+    from subgnn_b200 import prepare as prep
+    from subgnn_b200 import synth
+    graph, n_sub, _ = SHAPES[name]
+    hp, g, subs, labs, emb = synth.make_workload(name, seed=42, device='cuda', graph=graph, n_sub=n_sub)
+    hp = dict(hp, lin_dropout=0.0, lstm_dropout=0.0)
+    prepared = prep.prepare(hp, g, subs, labs, emb, seed=0, splits=('train',), num_classes=synth.WORKLOADS[name]['n_classes'])
+    return hp, g, prepared
+
+
+@pytest.mark.parametrize('name', list(SHAPES))
+def test_engine_step_matches_oracle_at_benchmark_shape(name):
+    from oracle.model import OracleSubGNN
+    from subgnn_b200 import _abi, synth
+    from subgnn_b200 import prepare as prep
+    from subgnn_b200.engine import Engine
+    hp, g, p = build(name)
+    ref = synth.hparams(name)
+    for k in ('node_embed_size', 'n_layers', 'batch_size', 'lstm_n_layers', 'n_anchor_patches_structure', 'n_triangular_walks', 'random_walk_len',
+              'n_anchor_patches_N_in', 'n_anchor_patches_N_out', 'n_anchor_patches_pos_in', 'n_anchor_patches_pos_out', 'cc_aggregator'):
+        assert hp[k] == ref[k], k                                   # the benchmark's hyper-parameters, not look-alikes
+    n = len(p['labels']['train'])
+    B = hp['batch_size']
+    assert n >= B
+    _abi.variant_log(reset=True)
+    eng = Engine(hp, p, device='cuda', graph=g, seed=5)
+    eng.init_parameters(3)
+    full = prep.prepared_subset(p, g, 'train', np.arange(n))
+    torch.manual_seed(0)
+    m = OracleSubGNN(hp, full)
+    m.load_state_dict({k: v.cpu() for k, v in eng.arena.state_dict().items()})
+    opt = torch.optim.Adam(m.parameters(), lr=hp['learning_rate'])
+    rs = np.random.RandomState(1)
+    names = dict(m.named_parameters())
+    for it in range(2):
+        idx = np.sort(rs.choice(n, size=B, replace=False))
+        loss_o, logits_o = m.training_step(m.make_batch('train', idx))
+        opt.zero_grad()
+        loss_o.backward()
+        gn_o = float(torch.nn.utils.clip_grad_norm_(m.parameters(), hp['grad_clip']))
+        opt.step()
+        loss = eng.train_step(idx, use_graph=(it > 0))              # eager launch order first, then the captured step graph
+        c = eng.context('train', B, True)
+        torch.cuda.synchronize()
+        np.testing.assert_allclose(c.logits.cpu().numpy(), logits_o.detach().numpy(), rtol=1e-4, atol=1e-5, err_msg='logits step %d' % it)
+        np.testing.assert_allclose(float(loss.item()), float(loss_o.detach()), rtol=1e-4, err_msg='loss step %d' % it)
+        gn = float(torch.sqrt(c.sumsq).item())
+        np.testing.assert_allclose(gn, gn_o, rtol=2e-4, err_msg='grad norm step %d' % it)
+        if it == 0:
+            coef = min(1.0, hp['grad_clip'] / (gn_o + 1e-6))
+            for k in eng.arena.entries:
+                if k in names and names[k].grad is not None:
+                    got = eng.arena.view(k, 'grads').cpu().numpy() * coef
+                    want = names[k].grad.numpy()
+                    tol = 2e-6 * max(1.0, float(np.abs(want).max()) / 1e-2)
+                    np.testing.assert_allclose(got, want, rtol=3e-4, atol=tol, err_msg='grad ' + k)
+    sd = m.state_dict()
+    for k in eng.arena.entries:
+        np.testing.assert_allclose(eng.arena.view(k).cpu().numpy(), sd[k].numpy(), rtol=1e-4, atol=1e-5, err_msg='weights after 2 steps: ' + k)
+    launched = _abi.variant_log()
+    for want in SHAPES[name][2]:
+        assert any(v.startswith(want) for v in launched), '%s not launched; saw %s' % (want, sorted(launched))
