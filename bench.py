@@ -41,6 +41,8 @@ def parse():
     ap.add_argument('--no-graph', action='store_true')
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--cpu-seconds', type=float, default=15.0)
+    ap.add_argument('--no-extra', dest='extra', action='store_false', help='skip the other BASELINE configs / strong / saturating legs')
+    ap.add_argument('--no-anomaly', dest='anomaly', action='store_false', help='skip the anomaly-detection-on CPU leg')
     return ap.parse_args()
 
 
@@ -199,11 +201,15 @@ ENTRY_KERNELS = {'subgnn_tc_linear_bwd_weight': ['tc_linear_bwd_weight_kernel'],
 
 
 def ncu_traffic(workload, entry):
-    """mean DRAM bytes per launch of the entry point's kernel from the committed ncu --set full capture of this workload, or None."""
-    f = ROOT / 'profiles' / ('r01_traffic_%s.json' % workload)
+    """mean DRAM bytes per launch of the entry point's kernel from the committed ncu --set full capture of this workload, or None.
+    The table is stamped with the digest of the CUDA sources it was captured on (tools/ncu_traffic.py); a table of other
+    kernels is refused (traffic = null) instead of being reported against kernels that have changed since."""
+    f = ROOT / 'profiles' / ('r02_traffic_%s.json' % workload)
     if not f.exists() or entry not in ENTRY_KERNELS:
         return None, None
     tab = json.loads(f.read_text())
+    if tab.get('csrc_digest') != csrc_digest():
+        return None, None
     ks = [tab['kernels'][k] for k in ENTRY_KERNELS[entry] if k in tab['kernels']]
     if not ks:
         return None, None
@@ -289,69 +295,90 @@ def emit(line):
         os.write(_RESULT_FD, data)
 
 
-def main():
-    args = parse()
-    _claim_stdout()
-    rank = int(os.environ.get('RANK', 0))
-    local_rank = int(os.environ.get('LOCAL_RANK', 0))
-    world = int(os.environ.get('WORLD_SIZE', 1))
+def config_for(workload, hp, g, n_train, world, B, use_graph=True):
+    """the workload description both arms print (the driver compares the two dicts)."""
+    return {'workload': (workload + '-shaped synthetic (SURVEY 8d), all channels N+P+S') if workload != 'cutratio' else 'cutratio-shaped synthetic, S only',
+            'batch_per_gpu': B, 'global_batch': B * world, 'n_layers': hp['n_layers'], 'node_embed_size': hp['node_embed_size'],
+            'graph_nodes': g.n_nodes, 'graph_edges': int(g.col.numel() // 2), 'train_subgraphs': n_train, 'parallelism': 'dp%d' % world,
+            'l2': 'flushed between timed iterations (256 MB write)', 'cuda_graph': bool(use_graph)}
+
+
+def csrc_digest():
+    """sha256 over the CUDA sources: stamps the ncu traffic tables (a table captured on other kernels is refused)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in sorted((ROOT / 'subgnn_b200' / 'csrc').glob('*.cu*')):
+        h.update(f.name.encode())
+        h.update(f.read_bytes())
+    return h.hexdigest()[:16]
+
+
+class Job:
+    """process-wide state shared by the measurement legs (rank / world / device / flush buffer / clock sampler)."""
+
+    def __init__(self, args):
+        import torch
+        self.args = args
+        self.rank = int(os.environ.get('RANK', 0))
+        self.local_rank = int(os.environ.get('LOCAL_RANK', 0))
+        self.world = int(os.environ.get('WORLD_SIZE', 1))
+        torch.cuda.set_device(self.local_rank)
+        self.dev = 'cuda:%d' % self.local_rank
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.init_process_group('nccl', device_id=torch.device(self.dev))
+            self.dist = dist
+        self.flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=self.dev)      # 256 MB > 126 MB L2
+        self.sampler = ClockSampler(self.local_rank)
+        self.sampler.start()
+
+    def barrier(self):
+        import torch
+        if self.dist is not None:
+            self.dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(self, x):
+        import torch
+        if self.dist is None:
+            return float(x)
+        tm = torch.tensor([x], device=self.dev, dtype=torch.float64)
+        self.dist.all_reduce(tm, op=self.dist.ReduceOp.MAX)
+        return float(tm.item())
+
+
+def measure(job, workload, K, W, batch_override=0, strong=False, detail=True, e2e_leg=True):
+    """One workload on this job's ranks: W warm-up steps, K timed steps (CUDA events per step on the launching stream, L2 flushed
+    in between, max over ranks), the e2e leg through SubGNN.training_step_fused with host batches, and — on rank 0, detail=True —
+    the instrumented per-entry-point pass for the roofline.  strong: batch_override is the GLOBAL batch, split over the ranks."""
     import torch
-
-    if args.impl == 'reference':
-        if rank != 0:
-            return 0
-        dev = 'cuda:0' if torch.cuda.is_available() else None
-        if dev is None:
-            emit({'impl': 'reference', 'unavailable': 'workload preparation needs the CUDA setup kernels; no GPU visible'})
-            return 0
-        torch.cuda.set_device(0)
-        hp, g, prepared, _ = build_workload(args.workload, dev, args.batch_size)
-        secs = min(120.0, max(5.0, 1.0 * args.steps)) if args.steps != 200 else 20.0
-        value, info = cpu_baseline(hp, g, prepared, secs, n_threads=os.cpu_count())
-        line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
-                'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
-                'data': 'synthetic', 'config': {'workload': args.workload, 'batch_per_gpu': hp['batch_size'], 'channels': 'N+P+S'},
-                'cpu_baseline': info, 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
-        emit(line)
-        return 0
-
-    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
-    torch.cuda.set_device(local_rank)
-    dev = 'cuda:%d' % local_rank
-    if world > 1:
-        import torch.distributed as dist
-        dist.init_process_group('nccl', device_id=torch.device(dev))
     from subgnn_b200 import _abi
     from subgnn_b200.engine import Engine
-
-    hp, g, prepared, prep_s = build_workload(args.workload, dev, args.batch_size)
+    from subgnn_b200.SubGNN import SubGNN
+    args, world, rank, dev = job.args, job.world, job.rank, job.dev
+    B_over = batch_override
+    if strong and batch_override:
+        assert batch_override % world == 0, 'strong scaling: the global batch must divide over the ranks'
+        B_over = batch_override // world
+    hp, g, prepared, prep_s = build_workload(workload, dev, B_over)
     B = hp['batch_size']
     eng = Engine(hp, prepared, device=dev, graph=g, seed=1234, world_size=world)
     eng.init_parameters(seed=7)
     n_train = len(prepared['labels']['train'])
-    K, W = args.steps, max(args.warmup, 3)
     use_graph = not args.no_graph
     batches = batches_for(n_train, B, W + K + 2, rank, world)
-
-    flush = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)      # 256 MB > 126 MB L2
-
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    flush, sampler = job.flush, job.sampler
     # ---- warm-up (includes graph capture) ----
     for i in range(W):
         eng.train_step(batches[i], use_graph=use_graph)
     if use_graph:
         eng.train_step(batches[W], use_graph=True)
-    barrier()
+    job.barrier()
     # ---- timed region: K steps, each bracketed by CUDA events on the launching stream, L2 flushed in between ----
     evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(K)]
     n0 = _abi.lib.subgnn_launch_count()
-    barrier()
+    job.barrier()
     sampler.mark_begin()
     wall0 = time.perf_counter()
     for i in range(K):
@@ -360,90 +387,79 @@ def main():
         evs[i][0].record()
         eng.train_step(idx, use_graph=use_graph)
         evs[i][1].record()
-    barrier()
+    job.barrier()
     wall = time.perf_counter() - wall0
     sampler.mark_end()
     step_ms = np.array([a.elapsed_time(b) for a, b in evs])
-    total_ms = float(step_ms.sum())
     launches = int(_abi.lib.subgnn_launch_count() - n0)
     if use_graph:
         launches = int(getattr(eng, 'launches_per_step', 0)) * K
-    if world > 1:
-        tm = torch.tensor([total_ms], device=dev, dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        total_ms = float(tm.item())
+    total_ms = job.max_over_ranks(float(step_ms.sum()))
     value = world * B * K / (total_ms * 1e-3)
     final_loss = float(eng.context('train', B, True).loss.item())
+    out = {'value': value, 'ms_per_step': total_ms / K, 'gpu_launches': launches, 'final_loss': final_loss, 'wall_s_timed_region': wall,
+           'config': config_for(workload, hp, g, n_train, world, B, use_graph), 'prepare_data_s': round(prep_s, 2),
+           'total_ms': total_ms}
 
     # ---- e2e: the user-facing call with host buffers; H2D of the step inputs + D2H of the loss inside the timed region ----
-    from subgnn_b200.SubGNN import SubGNN
-    model = SubGNN.from_engine(eng)
-    host_batches = [{'subgraph_idx': torch.from_numpy(b.astype(np.int64)).view(-1, 1).pin_memory()} for b in batches[W + 1:W + 1 + K]]
-    model.training_step_fused(host_batches[0], use_graph=use_graph)
-    barrier()
-    sampler.mark_begin()
-    t0 = time.perf_counter()
-    for hb in host_batches:
-        out = model.training_step_fused(hb, use_graph=use_graph, sync_loss=True)
-        _ = float(out['loss'])                                        # device -> host read of the step result
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    sampler.mark_end()
-    if world > 1:
-        tm = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
-        dist.all_reduce(tm, op=dist.ReduceOp.MAX)
-        e2e_s = float(tm.item())
-    e2e = {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 4,
-           'note': 'SubGNN.training_step_fused(host batch dict): pinned H2D of the subgraph indices, fused step graph ending in a D2H copy node of the loss, stream sync + host read every step; all tables are '
-                   'device-resident after prepare_data (the reference re-uploads the dense similarity slab every step)'}
+    e2e_s = 0.0
+    if e2e_leg:
+        model = SubGNN.from_engine(eng)
+        host_batches = [{'subgraph_idx': torch.from_numpy(b.astype(np.int64)).view(-1, 1).pin_memory()} for b in batches[W + 1:W + 1 + K]]
+        model.training_step_fused(host_batches[0], use_graph=use_graph)
+        job.barrier()
+        sampler.mark_begin()
+        t0 = time.perf_counter()
+        for hb in host_batches:
+            res = model.training_step_fused(hb, use_graph=use_graph, sync_loss=True)
+            _ = float(res['loss'])                                        # device -> host read of the step result
+        job.barrier()
+        e2e_s = job.max_over_ranks(time.perf_counter() - t0)
+        sampler.mark_end()
+        out['e2e'] = {'value': world * B * K / e2e_s, 'unit': UNIT, 'h2d_bytes_per_step': 4 * B, 'd2h_bytes_per_step': 4,
+                      'note': 'SubGNN.training_step_fused(host batch dict): pinned H2D of the subgraph indices, fused step graph ending in a D2H '
+                              'copy node of the loss, stream sync + host read every step (wall clock, so no L2 flush '
+                              'inside this loop: a flush would be timed as work); all tables are device-resident after prepare_data (the reference re-uploads the dense similarity '
+                              'slab every step)'}
+    out['loaded_s'] = (total_ms * 1e-3) + e2e_s
 
-    # the timed region of a launch-bound step can be shorter than nvidia-smi's polling period: keep the GPU under the
-    # same load (same step, same flush; untimed) until the poller has at least 5 samples under load
-    probe_steps = 0
-    sampler.mark_begin()
-    loaded_s = (total_ms * 1e-3) + e2e_s                      # identical on every rank (max-reduced): same number of extra rounds
-    rounds = 0 if loaded_s >= 0.8 else min(400, int(np.ceil((0.8 - loaded_s) / max(total_ms * 1e-3, 1e-4))))
-    for _ in range(rounds):
-        for i in range(K):
+    if detail and rank == 0:
+        # ---- instrumented pass: per-entry-point device time with CUDA events (eager launches, same batches, no exchange) ----
+        prof = {}
+
+        @contextlib.contextmanager
+        def hook(name):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            yield
+            b.record()
+            prof.setdefault(name, []).append((a, b))
+
+        n_prof = min(K, 10)
+        ws = eng.world_size
+        for i in range(n_prof):
             flush.zero_()
-            eng.train_step(batches[W + 1 + i], use_graph=use_graph)
-        probe_steps += K
-    barrier()
-    sampler.mark_end()
-    clocks = sampler.stop()
-    clocks['windows'] = 'timed region + e2e region' + (' + %d further untimed steps of the same loop (timed region shorter than the polling period)' % probe_steps if probe_steps else '')
-
-    if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return 0
-
-    # ---- instrumented pass: per-entry-point device time with CUDA events (eager launches, same batches) ----
-    prof = {}
-
-    @contextlib.contextmanager
-    def hook(name):
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        yield
-        b.record()
-        prof.setdefault(name, []).append((a, b))
-
-    n_prof = min(K, 10)
-    for i in range(n_prof):
-        flush.zero_()
+            torch.cuda.synchronize()
+            _abi._profile_hook = hook
+            eng.world_size = 1
+            try:
+                eng.train_step(batches[W + 1 + i], use_graph=False)
+            finally:
+                eng.world_size = ws
+                _abi._profile_hook = None
         torch.cuda.synchronize()
-        _abi._profile_hook = hook
-        eng.world_size_saved, eng.world_size = eng.world_size, 1
-        eng.train_step(batches[W + 1 + i], use_graph=False)
-        eng.world_size = eng.world_size_saved
-        _abi._profile_hook = None
-    torch.cuda.synchronize()
-    per_entry = {k: (sum(a.elapsed_time(b) for a, b in v) / n_prof, len(v) // n_prof) for k, v in prof.items()}
-    ctx = eng.context('train', B, True)
-    work, stats = algorithmic_work(eng, ctx)
+        per_entry = {k: (sum(a.elapsed_time(b) for a, b in v) / n_prof, len(v) // n_prof) for k, v in prof.items()}
+        ctx = eng.context('train', B, True)
+        work, stats = algorithmic_work(eng, ctx)
+        out['rows_last_batch'] = stats['rows']
+        out['breakdown_ms'] = {k: {'ms_per_step': round(v[0], 4), 'calls_per_step': v[1]} for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1][0])}
+        out['roofline'] = roofline_for(workload, per_entry, work)
+    out['_eng'] = (eng, hp, g, prepared, batches)
+    return out
+
+
+def roofline_for(workload, per_entry, work):
     peaks = measured_peaks()
-    breakdown = {k: {'ms_per_step': round(v[0], 4), 'calls_per_step': v[1]} for k, v in sorted(per_entry.items(), key=lambda kv: -kv[1][0])}
 
     def roof(name):
         if name not in work or name not in per_entry:
@@ -454,61 +470,175 @@ def main():
         amount_launch = amount / calls
         if bound == 'hbm':
             ach = amount_launch / per_launch_s / 1e9
-            return {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'],
-                    'traffic': None, 'algorithmic_bytes_per_launch': amount_launch, 'launches_per_step': calls,
-                    'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
-        # GEMM-shaped entries: the roofline bound follows from the arithmetic intensity against the ridge of the measured peaks
-        flops_launch, bytes_launch = amount_launch, work[name][2] / calls
-        ai, ridge = flops_launch / bytes_launch, peaks['tensor_sustained'] * 1e12 / (peaks['hbm'] * 1e9)
-        tf, gbs = flops_launch / per_launch_s / 1e12, bytes_launch / per_launch_s / 1e9
-        common = {'kernel': name, 'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
-                  'algorithmic_flops_per_launch': flops_launch, 'algorithmic_bytes_per_launch': bytes_launch,
-                  'arithmetic_intensity_flop_per_byte': ai, 'ridge_flop_per_byte': ridge, 'traffic': None,
-                  'achieved_tflops': tf, 'frac_of_tensor_peak': tf / peaks['tensor_sustained'], 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm']}
-        if bound == 'fp32':
-            common.update({'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': tf / FP32_FFMA_TFLOPS,
-                           'note': 'T dependent steps of an (n_seq x H)(H x 4H) fp32 FFMA product + 5H activations per sequence; latency bound: the '
-                                   'nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz) is reported beside the two contract peaks'})
+            r = {'kernel': name, 'bound': 'hbm', 'achieved': ach, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': ach / peaks['hbm'],
+                 'traffic': None, 'algorithmic_bytes_per_launch': amount_launch, 'launches_per_step': calls,
+                 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src']}
         else:
-            common['note'] = 'tcgen05 kind::tf32, 3xTF32 error compensation (3 MMAs per algorithmic product), accumulator in TMEM'
-        if ai < ridge:
-            common.update({'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm']})
-        else:
-            common.update({'bound': 'tensor', 'achieved': tf, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tensor_sustained']})
-        return common
-
-    _roof = roof
-
-    def roof(name):
-        r = _roof(name)
-        if r is not None:
-            r['traffic'], src = ncu_traffic(args.workload, name)
-            if src:
-                r['traffic_source'] = src + ': dram__bytes_read.sum + dram__bytes_write.sum per launch, cold caches (upper bound for the in-graph launch)'
+            # GEMM-shaped entries: the roofline bound follows from the arithmetic intensity against the ridge of the measured peaks
+            flops_launch, bytes_launch = amount_launch, work[name][2] / calls
+            ai, ridge = flops_launch / bytes_launch, peaks['tensor_sustained'] * 1e12 / (peaks['hbm'] * 1e9)
+            tf, gbs = flops_launch / per_launch_s / 1e12, bytes_launch / per_launch_s / 1e9
+            r = {'kernel': name, 'launches_per_step': calls, 'us_per_launch': per_launch_s * 1e6, 'peak_source': peaks['src'],
+                 'algorithmic_flops_per_launch': flops_launch, 'algorithmic_bytes_per_launch': bytes_launch,
+                 'arithmetic_intensity_flop_per_byte': ai, 'ridge_flop_per_byte': ridge, 'traffic': None,
+                 'achieved_tflops': tf, 'frac_of_tensor_peak': tf / peaks['tensor_sustained'], 'achieved_gbs': gbs, 'frac_of_hbm_peak': gbs / peaks['hbm']}
+            if bound == 'fp32':
+                r.update({'fp32_ffma_peak_tflops': FP32_FFMA_TFLOPS, 'frac_of_fp32_ffma_peak': tf / FP32_FFMA_TFLOPS,
+                          'note': 'T dependent steps of an (n_seq x H)(H x 4H) fp32 FFMA product + 5H activations per sequence; latency bound: the '
+                                  'nominal fp32 FFMA issue rate (148 SMs x 128 lanes x 2 x 1.965 GHz) is reported beside the two contract peaks'})
+            else:
+                r['note'] = 'tcgen05 kind::tf32, 3xTF32 error compensation (3 MMAs per algorithmic product), accumulator in TMEM'
+            if ai < ridge:
+                r.update({'bound': 'hbm', 'achieved': gbs, 'peak': peaks['hbm'], 'unit': 'GB/s', 'frac': gbs / peaks['hbm']})
+            else:
+                r.update({'bound': 'tensor', 'achieved': tf, 'peak': peaks['tensor_sustained'], 'unit': 'TFLOP/s', 'frac': tf / peaks['tensor_sustained']})
+        r['traffic'], src = ncu_traffic(workload, name)
+        if src:
+            r['traffic_source'] = src + ': dram__bytes_read.sum + dram__bytes_write.sum per launch, cold caches (upper bound for the in-graph launch)'
         return r
 
     ranked = sorted(per_entry, key=lambda k: -per_entry[k][0])
     roofline = next((r for r in (roof(k) for k in ranked) if r), None)
-    roofline['others'] = [r for r in (roof(k) for k in ('subgnn_model_rows_fwd', 'subgnn_model_rows_bwd', 'subgnn_tc_linear_fwd',
-                                                         'subgnn_tc_linear_bwd_weight', 'subgnn_lstm_recur_fwd', 'subgnn_adam_step')
-                                      if k in per_entry and k != roofline['kernel']) if r]
+    if roofline is not None:
+        roofline['others'] = [r for r in (roof(k) for k in ('subgnn_model_rows_fwd', 'subgnn_model_rows_bwd', 'subgnn_tc_linear_fwd',
+                                                             'subgnn_tc_linear_bwd_input', 'subgnn_tc_linear_bwd_weight', 'subgnn_lstm_recur_fwd',
+                                                             'subgnn_lstm_recur_bwd', 'subgnn_adam_step')
+                                          if k in per_entry and k != roofline['kernel']) if r]
+    return roofline
 
-    cpu = None
+
+def release(m):
+    """drop a leg's engine / tables before the next workload is built."""
+    import gc
+    import torch
+    m.pop('_eng', None)
+    gc.collect()
+    torch.cuda.empty_cache()
+
+
+EXTRA_WORKLOADS = ('density', 'cutratio', 'hpo_metab', 'em_user')
+
+
+def reference_arm(args):
+    """--impl reference: the CPU oracle port of the reference step (oracle/model.py) on rank 0's host cores, bounded sample of the
+    SAME workload and batch size; prints the same `config` dict as the b200 arm.  The workload tensors are prepared with the repo's
+    CUDA setup kernels (walks, DTW, hop table) — the timed loop is CPU only."""
+    import torch
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    if rank != 0:
+        return 0
+    dev = 'cuda:0' if torch.cuda.is_available() else None
+    if dev is None:
+        emit({'impl': 'reference', 'unavailable': 'workload preparation needs the CUDA setup kernels; no GPU visible'})
+        return 0
+    torch.cuda.set_device(0)
+    hp, g, prepared, _ = build_workload(args.workload, dev, args.batch_size)
+    n_train = len(prepared['labels']['train'])
+    secs = min(120.0, max(5.0, 1.0 * args.steps)) if args.steps != 200 else 20.0
+    value, info = cpu_baseline(hp, g, prepared, secs, n_threads=os.cpu_count())
+    line = {'impl': 'reference', 'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': info['ms_per_step'], 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
+            'data': 'synthetic', 'config': config_for(args.workload, hp, g, n_train, world, hp['batch_size'], not args.no_graph),
+            'cpu_baseline': info, 'e2e': {'value': value, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0}}
+    if args.anomaly:
+        _, info_a = cpu_baseline(hp, g, prepared, min(secs, 10.0), n_threads=os.cpu_count(), anomaly=True)
+        line['cpu_baseline_anomaly_on'] = info_a
+    emit(line)
+    return 0
+
+
+def main():
+    args = parse()
+    _claim_stdout()
+    import torch
+
+    if args.impl == 'reference':
+        return reference_arm(args)
+
+    assert torch.cuda.is_available(), 'bench.py needs a CUDA device (there is no CPU fallback)'
+    job = Job(args)
+    world, rank = job.world, job.rank
+    K, W = args.steps, max(args.warmup, 3)
+
+    main_leg = measure(job, args.workload, K, W, args.batch_size)
+    eng, hp, g, prepared, batches = main_leg['_eng']
+    B = hp['batch_size']
+    use_graph = not args.no_graph
+
+    # the timed region of a launch-bound step can be shorter than nvidia-smi's polling period: keep the GPU under the
+    # same load (same step, same flush; untimed) until the poller has at least 5 samples under load
+    probe_steps = 0
+    job.sampler.mark_begin()
+    loaded_s = main_leg['loaded_s']                         # identical on every rank (max-reduced): same number of extra rounds
+    rounds = 0 if loaded_s >= 0.8 else min(400, int(np.ceil((0.8 - loaded_s) / max(main_leg['total_ms'] * 1e-3, 1e-4))))
+    for _ in range(rounds):
+        for i in range(K):
+            job.flush.zero_()
+            eng.train_step(batches[W + 1 + i], use_graph=use_graph)
+        probe_steps += K
+    job.barrier()
+    job.sampler.mark_end()
+
+    cpu = cpu_anom = None
     if world == 1 and not args.no_cpu_baseline:
         _, cpu = cpu_baseline(hp, g, prepared, args.cpu_seconds)
+        if args.anomaly:
+            # the reference ships with torch.autograd.set_detect_anomaly(True) (train_config.py:206): reported beside anomaly-off
+            _, cpu_anom = cpu_baseline(hp, g, prepared, min(args.cpu_seconds, 8.0), anomaly=True)
+    release(main_leg)
+    del eng, prepared, batches
 
-    line = {'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': total_ms / K,
-            'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': args.workload + '-shaped synthetic (SURVEY 8d), all channels N+P+S' if args.workload != 'cutratio' else 'cutratio-shaped, S only',
-                       'batch_per_gpu': B, 'global_batch': B * world, 'n_layers': hp['n_layers'], 'node_embed_size': hp['node_embed_size'],
-                       'graph_nodes': g.n_nodes, 'graph_edges': int(g.col.numel() // 2), 'train_subgraphs': n_train, 'parallelism': 'dp%d' % world,
-                       'l2': 'flushed between timed iterations (256 MB write)', 'cuda_graph': use_graph, 'rows_last_batch': stats['rows'],
-                       'prepare_data_s': round(prep_s, 2)},
-            'roofline': roofline, 'cpu_baseline': cpu, 'e2e': e2e, 'gpu_launches': launches, 'clocks': clocks,
-            'breakdown_ms': breakdown, 'final_loss': final_loss, 'wall_s_timed_region': wall}
-    emit(line)
-    if world > 1:
-        dist.destroy_process_group()
+    # ---- the other BASELINE.json configurations, strong scaling and the saturating batch (same harness, fewer extras) ----
+    configs, strong, saturating = {}, None, None
+    if args.extra and args.workload == 'ppi_bp' and not args.batch_size:
+        Ke = max(10, min(K, 50))
+        for name in EXTRA_WORKLOADS:
+            m = measure(job, name, Ke, W, detail=True)
+            release(m)
+            configs[name] = {'value': m['value'], 'unit': UNIT, 'ms_per_step': m['ms_per_step'], 'steps': Ke, 'e2e': m['e2e']['value'],
+                             'batch_per_gpu': m['config']['batch_per_gpu'], 'config': m['config'], 'prepare_data_s': m['prepare_data_s'],
+                             'gpu_launches_per_step': m['gpu_launches'] // Ke}
+            if m.get('roofline'):
+                r = m['roofline']
+                configs[name]['roofline'] = {k: r.get(k) for k in ('kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'us_per_launch')}
+        if world > 1 and B % world == 0:
+            # strong scaling at the reference's global batch (SURVEY 8e): the batch of B subgraphs is split over the ranks
+            m = measure(job, args.workload, Ke, W, batch_override=B, strong=True, detail=False)
+            release(m)
+            strong = {'global_batch': B, 'batch_per_gpu': B // world, 'value': m['value'], 'ms_per_step': m['ms_per_step'], 'e2e': m['e2e']['value'],
+                      'unit': UNIT, 'scaling': 'strong'}
+        if world == 1:
+            # the whole train split as one batch: the LSTM chain is batch independent, so this is the throughput ceiling of the step
+            n_train = main_leg['config']['train_subgraphs']
+            m = measure(job, args.workload, Ke, W, batch_override=n_train, detail=True)
+            release(m)
+            saturating = {'batch': n_train, 'value': m['value'], 'ms_per_step': m['ms_per_step'], 'e2e': m['e2e']['value'], 'unit': UNIT}
+            if m.get('roofline'):
+                saturating['roofline'] = {k: m['roofline'].get(k) for k in ('kernel', 'bound', 'achieved', 'peak', 'unit', 'frac', 'us_per_launch')}
+                saturating['breakdown_ms'] = dict(list(m['breakdown_ms'].items())[:6])
+
+    clocks = job.sampler.stop()
+    clocks['windows'] = 'timed regions + e2e regions of every leg' + (' + %d further untimed steps of the same loop (timed region shorter than the polling period)' % probe_steps if probe_steps else '')
+
+    if rank == 0:
+        line = {'metric': METRIC, 'value': main_leg['value'], 'unit': UNIT, 'n_gpus': world, 'steps': K, 'warmup': W, 'ms_per_step': main_leg['ms_per_step'],
+                'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+                'config': main_leg['config'], 'roofline': main_leg.get('roofline'), 'cpu_baseline': cpu, 'e2e': main_leg['e2e'],
+                'gpu_launches': main_leg['gpu_launches'], 'clocks': clocks, 'breakdown_ms': main_leg.get('breakdown_ms'),
+                'final_loss': main_leg['final_loss'], 'wall_s_timed_region': main_leg['wall_s_timed_region'],
+                'workload_stats': {'rows_last_batch': main_leg.get('rows_last_batch'), 'prepare_data_s': main_leg['prepare_data_s']}}
+        if cpu_anom is not None:
+            line['cpu_baseline_anomaly_on'] = cpu_anom
+        if configs:
+            line['configs'] = configs
+        if strong:
+            line['strong'] = strong
+        if saturating:
+            line['saturating'] = saturating
+        emit(line)
+    if job.dist is not None:
+        job.dist.destroy_process_group()
     return 0
 
 

@@ -783,11 +783,33 @@ class Engine:
             import torch.distributed as dist
             dist.all_reduce(self.arena.grads)
 
+    def _capture_step(self, c):
+        """ONE CUDA graph for the whole step, data parallel included: the NCCL all-reduce of the gradient arena is captured between
+        the backward pass and the optimizer (NCCL collectives are stream-capturable), so a replay is a single launch on every rank
+        and the exchange is ordered by graph edges instead of by the host.  SUBGNN_DP_SPLIT_GRAPH=1 keeps the round-1 form (two
+        graphs around an eagerly enqueued all-reduce) for A/B runs."""
+        split = self.world_size > 1 and _flag('SUBGNN_DP_SPLIT_GRAPH', False)
+        if split:
+            g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g1):
+                self._grad_launches(c, _abi.stream_ptr())
+            with torch.cuda.graph(g2):
+                self._optimizer_launches(c, _abi.stream_ptr())
+                c.loss_host.copy_(c.loss, non_blocking=True)
+            return (g1, g2)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            self._grad_launches(c, _abi.stream_ptr())
+            self.allreduce_grads()
+            self._optimizer_launches(c, _abi.stream_ptr())
+            c.loss_host.copy_(c.loss, non_blocking=True)
+        return (g,)
+
     def train_step(self, indices, use_graph=False):
         """one optimisation step on the train split: forward, loss, backward, [allreduce,] clip, Adam (in place).
-        With use_graph the launches are captured once and replayed: ONE CUDA graph for the whole step on a single GPU, two
-        halves around the NCCL allreduce when data parallel.  The graph ends with a D2H copy node of the loss into pinned
-        host memory (read it with ``loss_value``); per-step host work is one pinned copy of the indices + the graph launch."""
+        With use_graph the launches are captured once and replayed as ONE CUDA graph (the NCCL all-reduce included when data
+        parallel).  The graph ends with a D2H copy node of the loss into pinned host memory (read it with ``loss_value``);
+        per-step host work is one pinned copy of the indices + the graph launch."""
         c = self._last_ctx = self.context('train', indices.numel() if isinstance(indices, torch.Tensor) else len(indices), True)
         self.set_batch(c, indices)
         st = _abi.stream_ptr()
@@ -798,30 +820,16 @@ class Engine:
             c.loss_host.copy_(c.loss, non_blocking=True)
             return c.loss
         if c.graph is None:
-            self._grad_launches(c, st)                         # warm-up (sets function attributes) — a real step
+            self._grad_launches(c, st)                         # warm-up (sets function attributes, NCCL communicator) — a real step
             self.allreduce_grads()
             self._optimizer_launches(c, st)
             c.loss_host.copy_(c.loss, non_blocking=True)
             torch.cuda.synchronize()
             n0 = _abi.lib.subgnn_launch_count()
-            if self.world_size > 1:
-                g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g1):
-                    self._grad_launches(c, _abi.stream_ptr())
-                with torch.cuda.graph(g2):
-                    self._optimizer_launches(c, _abi.stream_ptr())
-                    c.loss_host.copy_(c.loss, non_blocking=True)
-                c.graph = (g1, g2)
-            else:
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self._grad_launches(c, _abi.stream_ptr())
-                    self._optimizer_launches(c, _abi.stream_ptr())
-                    c.loss_host.copy_(c.loss, non_blocking=True)
-                c.graph = (g,)
+            c.graph = self._capture_step(c)
             self.launches_per_step = int(_abi.lib.subgnn_launch_count() - n0)
             return c.loss
-        if self.world_size > 1:
+        if len(c.graph) == 2:
             c.graph[0].replay()
             self.allreduce_grads()
             c.graph[1].replay()

@@ -2,13 +2,18 @@
 """Per-kernel DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum, bytes per launch, mean over the launches of one
 captured step) and duration from an `ncu --set full` report -> JSON for profiles/ (read by bench.py's roofline.traffic).
 
-    python tools/ncu_traffic.py gpurun_out/full.ncu-rep > profiles/r01_traffic_<workload>.json"""
+    python tools/ncu_traffic.py gpurun_out/full.ncu-rep > profiles/r02_traffic_<workload>.json
+
+The table is stamped with bench.csrc_digest() (sha256 of subgnn_b200/csrc): bench.py refuses a table captured on other kernels."""
 import collections
 import csv
 import json
 import re
 import subprocess
 import sys
+from pathlib import Path
+
+sys.path.insert(0, str(Path(__file__).resolve().parents[1]))
 
 UNIT = {'byte': 1.0, 'Kbyte': 1e3, 'Mbyte': 1e6, 'Gbyte': 1e9}
 TIME = {'ns': 1e-3, 'us': 1.0, 'ms': 1e3, 'second': 1e6, 's': 1e6}
@@ -28,7 +33,8 @@ def main(path):
         a['us'] += float(r[iT]) * TIME[units[iT]]
     res = {k: {'launches_per_step': v['launches'], 'dram_bytes_per_launch': v['dram_bytes'] / v['launches'], 'us_per_launch': v['us'] / v['launches']}
            for k, v in agg.items()}
-    print(json.dumps({'source': path.split('/')[-1], 'note': 'ncu --set full --clock-control none, one eager step, caches flushed before every kernel '
+    import bench
+    print(json.dumps({'source': path.split('/')[-1], 'csrc_digest': bench.csrc_digest(), 'note': 'ncu --set full --clock-control none, one eager step, caches flushed before every kernel '
                       '(cold): an upper bound on the traffic of the same kernel inside the step graph, where producers leave their outputs in L2',
                       'kernels': res}, indent=1))
 
