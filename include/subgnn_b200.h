@@ -131,6 +131,35 @@ int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw
 int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ldx, const int* gather_ids, float* dw, int lddw, float* db,
                                 int M, int N, int K, void* stream);
 
+/* Grouped form (tcgemm_ws.cu): up to 6 dense products in ONE persistent, warp-specialised launch (TMA-fed 3-stage operand ring,
+ * converter warps for the 3xTF32 low parts, double-buffered TMEM accumulators).  The three entry points above route their dense
+ * (gather_ids == NULL) calls here; the step engine groups the gate-gradient consumers of an LSTM layer (input gradient + three
+ * weight gradients) into one launch.  op selects the product:
+ *   SUBGNN_GEMM_FWD               out[M][N]      = a[M][K] . b[N][K]^T + bias [, relu]             (a = x, b = W)
+ *   SUBGNN_GEMM_BWD_INPUT         out[row(m)][K] (+)= a[M][N] . b[N][K]     row(m) = scatter_ids ? scatter_ids[m] : m  (a = dy, b = W)
+ *   SUBGNN_GEMM_BWD_WEIGHT        out[N][K]     += a[M][N]^T . b[M][K]                             (a = dy, b = x)
+ *   SUBGNN_GEMM_BWD_WEIGHT_SHIFT  out[N][K]     += sum_m a[m][N]^T . b[m + shift][K] over the rows with (m % period) != (shift < 0 ? 0 :
+ *                                 period - 1): the recurrent-weight gradient dW_hh = sum_t dG_t^T h_(t-1) of nn.LSTM (SubGNN.py:73)
+ *                                 for sequences of `period` steps stored row after row (shift = -1 forward, +1 reverse direction).
+ * max_ctas > 0 caps the grid (a companion launch leaves the other SMs to the kernel on the critical chain). */
+#define SUBGNN_GEMM_FWD 0
+#define SUBGNN_GEMM_BWD_INPUT 1
+#define SUBGNN_GEMM_BWD_WEIGHT 2
+#define SUBGNN_GEMM_BWD_WEIGHT_SHIFT 3
+typedef struct subgnn_gemm_desc {
+  const float* a;
+  const float* b;
+  float* out;
+  const float* bias;
+  const int* scatter_ids;
+  int op, lda, ldb, ldo, M, N, K, relu, accumulate, shift, period;
+} subgnn_gemm_desc;
+int subgnn_gemm_desc_size(void);
+int subgnn_tc_ws_available(void);   /* 1 when the driver exports cuTensorMapEncodeTiled (TMA descriptors) */
+int subgnn_tc_gemm_group(const subgnn_gemm_desc* problems, int n_problems, int max_ctas, void* stream);
+/* out[m][:] = table[ids[m]][:] (anchor_patch_samplers.py:409: embedding lookup of the walk nodes, once per step) */
+int subgnn_gather_rows(const float* table, const int* ids, float* out, int M, int D, void* stream);
+
 /* ---- walk-encoder LSTM (lstm.cu): SubGNN.py:60-88, anchor_patch_samplers.py:413-433 ------------------ */
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,

@@ -192,6 +192,10 @@ class SubGNN(nn.Module):
         for name in self._param_names:
             p = nn.Parameter(engine.arena.view(name), requires_grad=True)
             self._register_by_path(name, p)
+        if not engine.arena.embed_trainable:
+            # the reference's state_dict carries the frozen table too (nn.Embedding.from_pretrained(freeze=True), SubGNN.py:568):
+            # checkpoints stay loadable on either side; the tensor is the engine's own table (load_state_dict writes through)
+            self._register_by_path('node_embeddings.weight', nn.Parameter(engine.E_frozen, requires_grad=False))
 
     def _register_by_path(self, path, param):
         mod = self

@@ -45,6 +45,8 @@ SIGNATURES = {
     'subgnn_tc_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P],
     'subgnn_linear_bwd_input': [P, I, P, I, P, I, P, I, I, I, I, P],
     'subgnn_linear_bwd_weight': [P, I, P, I, P, P, I, P, I, I, I, P, P],
+    'subgnn_tc_gemm_group': [P, I, I, P],
+    'subgnn_gather_rows': [P, P, P, I, I, P],
     'subgnn_colsum': [P, I, P, I, I, P, P],
     'subgnn_lstm_prep': [P, P, P, P, P, I, P],
     'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
@@ -76,6 +78,8 @@ _OTHER = {
     'subgnn_abi_version': ([], I),
     'subgnn_device_sm_count': ([], I),
     'subgnn_model_desc_size': ([], I),
+    'subgnn_gemm_desc_size': ([], I),
+    'subgnn_tc_ws_available': ([], I),
     'subgnn_launch_count': ([], U64),
     'subgnn_lstm_fused_dropout_supported': ([I], I),
     'subgnn_variant_log': ([C.c_char_p, I], I),
@@ -130,11 +134,11 @@ def call(name, *args):
         raise SubgnnError('%s failed (%d): %s' % (name, rc, lib.subgnn_last_error().decode()))
 
 
-def _parse_desc_fields():
-    """Builds the ctypes mirror of ``subgnn_model_desc`` from include/subgnn_b200.h so the two cannot drift."""
+def _parse_desc_fields(struct='subgnn_model_desc'):
+    """Builds the ctypes mirror of a descriptor struct from include/subgnn_b200.h so the two cannot drift."""
     import re
     hdr = (Path(__file__).resolve().parent.parent / 'include' / 'subgnn_b200.h').read_text()
-    body = hdr.split('typedef struct subgnn_model_desc {')[1].split('} subgnn_model_desc;')[0]
+    body = hdr.split('typedef struct %s {' % struct)[1].split('} %s;' % struct)[0]
     body = re.sub(r'/\*.*?\*/', '', body, flags=re.S)
     fields = []
     for stmt in body.split(';'):
@@ -157,6 +161,28 @@ def _parse_desc_fields():
 
 class ModelDesc(C.Structure):
     _fields_ = _parse_desc_fields()
+
+
+class GemmDesc(C.Structure):
+    _fields_ = _parse_desc_fields('subgnn_gemm_desc')
+
+
+GEMM_FWD, GEMM_BWD_INPUT, GEMM_BWD_WEIGHT, GEMM_BWD_WEIGHT_SHIFT = 0, 1, 2, 3      # include/subgnn_b200.h
+assert C.sizeof(GemmDesc) == lib.subgnn_gemm_desc_size(), 'subgnn_gemm_desc layout mismatch'
+
+
+def gemm_desc(op, a, lda, b, ldb, out, ldo, M, N, K, bias=None, scatter_ids=None, relu=0, accumulate=0, shift=0, period=0):
+    """one problem of subgnn_tc_gemm_group; a / b / out / bias / scatter_ids are raw device addresses (int) or None."""
+    d = GemmDesc()
+    d.a, d.b, d.out, d.bias, d.scatter_ids = a, b, out, bias, scatter_ids
+    d.op, d.lda, d.ldb, d.ldo, d.M, d.N, d.K = op, lda, ldb, ldo, M, N, K
+    d.relu, d.accumulate, d.shift, d.period = relu, accumulate, shift, period
+    return d
+
+
+def gemm_group(descs, stream, max_ctas=0):
+    arr = (GemmDesc * len(descs))(*descs)
+    call('subgnn_tc_gemm_group', C.addressof(arr), len(descs), max_ctas, stream)
 
 
 assert C.sizeof(ModelDesc) == lib.subgnn_model_desc_size(), \

@@ -156,7 +156,8 @@ def _to_device(x, device):
 
 class Trainer:
     def __init__(self, max_epochs=1000, min_epochs=1, gpus=0, num_sanity_val_steps=0, progress_bar_refresh_rate=1, gradient_clip_val=0.0,
-                 logger=True, checkpoint_callback=True, early_stop_callback=None, profiler=None, auto_lr_find=False, fused=None, **unused):
+                 logger=True, checkpoint_callback=True, early_stop_callback=None, profiler=None, auto_lr_find=False, fused=None,
+                 resume_from_checkpoint=None, **unused):
         self.max_epochs, self.min_epochs, self.gpus = max_epochs, min_epochs, gpus
         self.gradient_clip_val = float(gradient_clip_val or 0.0)
         self.progress_bar_refresh_rate = progress_bar_refresh_rate
@@ -168,6 +169,7 @@ class Trainer:
             print('[subgnn_b200.compat] auto_lr_find is accepted and ignored (0.7.1 runs its LR finder only on request of trainer.lr_find)')
         self.fused = fused if fused is not None else os.environ.get('SUBGNN_B200_AUTOGRAD_STEP', '0') != '1'
         self.current_epoch, self.global_step = 0, 0
+        self.resume_from_checkpoint = resume_from_checkpoint
         self.callback_metrics = {}
         self.optimizers = []
         self.model = None
@@ -185,7 +187,9 @@ class Trainer:
     def save_checkpoint(self, path):
         m = self.model
         ckpt = {'epoch': self.current_epoch + 1, 'global_step': self.global_step, 'state_dict': {k: v.detach().cpu() for k, v in m.state_dict().items()},
-                'optimizer_states': [o.state_dict() for o in self.optimizers] if not self._fused_active else [],
+                # fused mode: the engine's own Adam moments and step count, in torch.optim.Adam's state_dict layout
+                'optimizer_states': ([o.state_dict() for o in self.optimizers] if not self._fused_active
+                                     else [m.engine.optimizer_state_dict()]),
                 'checkpoint_callback_best': getattr(self.checkpoint_callback, 'best', None), 'hparams': dict(getattr(m, 'hparams', {}) or {})}
         torch.save(ckpt, path)
 
@@ -210,8 +214,19 @@ class Trainer:
         if self._fused_active and getattr(model, 'engine', None) is not None:
             model.engine.grad_clip = self.gradient_clip_val  # Trainer(gradient_clip_val=...) is what Lightning clips with
         train_loader, val_loader = model.train_dataloader(), model.val_dataloader()
+        first_epoch = 0
+        if self.resume_from_checkpoint:            # Lightning 0.7.1 restore: weights, optimizer state, epoch / step counters
+            ckpt = torch.load(self.resume_from_checkpoint, map_location='cpu', weights_only=False)
+            model.load_state_dict(ckpt['state_dict'], strict=False)
+            if ckpt.get('optimizer_states'):
+                if self._fused_active:
+                    model.engine.load_optimizer_state_dict(ckpt['optimizer_states'][0])
+                else:
+                    osd = {k: v for k, v in ckpt['optimizer_states'][0].items() if k in ('state', 'param_groups')}
+                    opt.load_state_dict(osd)
+            first_epoch, self.global_step = int(ckpt.get('epoch', 0)), int(ckpt.get('global_step', 0))
         stop = False
-        for epoch in range(self.max_epochs):
+        for epoch in range(first_epoch, self.max_epochs):
             self.current_epoch = epoch
             t0 = time.time()
             model.train()

@@ -508,28 +508,30 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
 //   mlp_rest_kernel  CTA per sample: bias / relu / dropout, lin2, lin3, loss, d logits, dH2, dH1       (W2 staged in smem)
 //   mlp_dz_kernel    CTA per 64-column slice of hid: dZ[b][i] = sum_j dH1[b][j] W1[j][i]
 #define MLP_SLICE 64
+#define MLP_BT 128      // samples per CTA of the two sliced kernels (grid.y tiles larger batches)
 __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
   extern __shared__ float sm[];
-  float* zs = sm;                               // [B][MLP_SLICE]
-  float* ws = sm + (size_t)d.B * MLP_SLICE;     // [MLP_SLICE][h1]
+  const int b0 = blockIdx.y * MLP_BT, bn = min(MLP_BT, d.B - b0);
+  float* zs = sm;                               // [bn][MLP_SLICE]
+  float* ws = sm + (size_t)min(d.B, MLP_BT) * MLP_SLICE;     // [MLP_SLICE][h1]
   const int k0 = blockIdx.x * MLP_SLICE, kn = min(MLP_SLICE, d.hid - k0);
   // the weight slice was transposed several launches ago (complete by transitivity of the dependency waits): staged before
   // this kernel's own wait, while the row kernel that finishes Z is still running
   const float* wt = d.lin_wt[0] + (size_t)k0 * d.h1;
   sg_stage<16>(ws, kn * d.h1, [&](int e) { return __ldg(wt + e); });
   sg_pdl_sync();
-  sg_stage<8>(zs, d.B * MLP_SLICE, [&](int e) {
+  sg_stage<8>(zs, bn * MLP_SLICE, [&](int e) {
     const int b = e / MLP_SLICE, kk = e % MLP_SLICE;
-    return kk < kn ? d.Z[(size_t)b * d.hid + k0 + kk] : 0.f;
+    return kk < kn ? d.Z[(size_t)(b0 + b) * d.hid + k0 + kk] : 0.f;
   });
   __syncthreads();
-  for (int o = threadIdx.x; o < d.B * d.h1; o += blockDim.x) {
+  for (int o = threadIdx.x; o < bn * d.h1; o += blockDim.x) {
     const int b = o / d.h1, j = o % d.h1;
     const float* zr = zs + (size_t)b * MLP_SLICE;
     float acc = 0.f;
 #pragma unroll 8
     for (int kk = 0; kk < kn; ++kk) acc = fmaf(zr[kk], ws[kk * d.h1 + j], acc);
-    atomicAdd(d.H1 + o, acc);
+    atomicAdd(d.H1 + (size_t)b0 * d.h1 + o, acc);
   }
 }
 
@@ -629,8 +631,9 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
 
 __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
   extern __shared__ float sm[];
-  float* g1s = sm;                               // [B][h1]
-  float* ws = sm + (size_t)d.B * d.h1;           // [h1][MLP_SLICE]
+  const int b0 = blockIdx.y * MLP_BT, bn = min(MLP_BT, d.B - b0);
+  float* g1s = sm;                               // [bn][h1]
+  float* ws = sm + (size_t)min(d.B, MLP_BT) * d.h1;           // [h1][MLP_SLICE]
   const int i0 = blockIdx.x * MLP_SLICE, in = min(MLP_SLICE, d.hid - i0);
   // the W1 slice is a PARAMETER (last written by the previous step's Adam, a full stream dependency ago): staged before the
   // programmatic-dependency wait, i.e. while mlp_rest_kernel is still running
@@ -640,16 +643,16 @@ __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
     return ii < in ? __ldg(w0 + (size_t)j * d.hid + i0 + ii) : 0.f;
   });
   sg_pdl_sync();
-  sg_stage<8>(g1s, d.B * d.h1, [&](int e) { return d.dH1[e]; });
+  sg_stage<8>(g1s, bn * d.h1, [&](int e) { return d.dH1[(size_t)b0 * d.h1 + e]; });
   __syncthreads();
-  for (int o = threadIdx.x; o < d.B * MLP_SLICE; o += blockDim.x) {
+  for (int o = threadIdx.x; o < bn * MLP_SLICE; o += blockDim.x) {
     const int b = o / MLP_SLICE, ii = o % MLP_SLICE;
     if (ii >= in) continue;
     const float* gr = g1s + (size_t)b * d.h1;
     float acc = 0.f;
 #pragma unroll 8
     for (int j = 0; j < d.h1; ++j) acc = fmaf(gr[j], ws[j * MLP_SLICE + ii], acc);
-    d.dZ[(size_t)b * d.hid + i0 + ii] = acc;
+    d.dZ[(size_t)(b0 + b) * d.hid + i0 + ii] = acc;
   }
 }
 
@@ -925,21 +928,22 @@ int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   if (rc) return rc;
   cudaStream_t st = (cudaStream_t)stream;
   const int slices = sg_div_up(d->hid, MLP_SLICE);
-  const size_t s1 = (size_t)(d->B * MLP_SLICE + MLP_SLICE * d->h1) * sizeof(float);
+  const int bt = d->B < MLP_BT ? d->B : MLP_BT, b_tiles = sg_div_up(d->B, MLP_BT);
+  const size_t s1 = (size_t)(bt * MLP_SLICE + MLP_SLICE * d->h1) * sizeof(float);
   const size_t s2 = (size_t)(2 * d->h1 * d->h2 + d->h1 + 2 * d->h2 + 2 * d->n_classes + 8) * sizeof(float);
-  const size_t s3 = (size_t)(d->B * d->h1 + d->h1 * MLP_SLICE) * sizeof(float);
+  const size_t s3 = (size_t)(bt * d->h1 + d->h1 * MLP_SLICE) * sizeof(float);
   if (s1 > 200 * 1024 || s2 > 200 * 1024 || s3 > 200 * 1024) { subgnn_set_error("MLP dimensions too large for shared memory"); return SUBGNN_ERR_ARG; }
   if (s1 > 48 * 1024) cudaFuncSetAttribute(mlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (s2 > 48 * 1024) cudaFuncSetAttribute(mlp_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
   if (s3 > 48 * 1024) cudaFuncSetAttribute(mlp_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
-  sg_launch_pdl<SG_PDL_CHAIN>(mlp_lin1_kernel, dim3(slices), dim3(256), s1, st, *d);
+  sg_launch_pdl<SG_PDL_CHAIN>(mlp_lin1_kernel, dim3(slices, b_tiles), dim3(256), s1, st, *d);
   rc = subgnn_check_launch("mlp_lin1_kernel");
   if (rc) return rc;
   sg_launch_pdl<SG_PDL_CHAIN>(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
   rc = subgnn_check_launch("mlp_rest_kernel");
   if (rc) return rc;
   if (d->training && d->dZ) {
-    sg_launch_pdl<SG_PDL_CHAIN>(mlp_dz_kernel, dim3(slices), dim3(256), s3, st, *d);
+    sg_launch_pdl<SG_PDL_CHAIN>(mlp_dz_kernel, dim3(slices, b_tiles), dim3(256), s3, st, *d);
     rc = subgnn_check_launch("mlp_dz_kernel");
   }
   return rc;

@@ -378,6 +378,14 @@ tc_linear_bwd_weight_kernel(const float* __restrict__ dy, int ldy, const float* 
       });
 }
 
+bool tc_ws_usable(const void* a, int lda, const void* b, int ldb);      // tcgemm_ws.cu: TMA-fed warp-specialised kernel
+static subgnn_gemm_desc ws_desc(int op, const float* a, int lda, const float* b, int ldb, float* out, int ldo, int M, int N, int K) {
+  subgnn_gemm_desc d;
+  d.a = a; d.b = b; d.out = out; d.bias = nullptr; d.scatter_ids = nullptr;
+  d.op = op; d.lda = lda; d.ldb = ldb; d.ldo = ldo; d.M = M; d.N = N; d.K = K; d.relu = 0; d.accumulate = 0; d.shift = 0; d.period = 0;
+  return d;
+}
+
 static bool tc_aligned(const void* p, int ld) { return (ld % 4) == 0 && (((size_t)p) & 15) == 0; }
 template <int NT, int STAGES> static size_t tc_smem() { return (size_t)STAGES * (2 * TC_M * 128 + 2 * NT * 128) + 1024; }
 
@@ -417,6 +425,11 @@ int subgnn_tc_linear_fwd(const float* x, int ldx, const int* gather_ids, const f
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(x, ldx) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
+  if (!gather_ids && tc_ws_usable(x, ldx, w, ldw)) {
+    subgnn_gemm_desc d = ws_desc(SUBGNN_GEMM_FWD, x, ldx, w, ldw, y, ldy, M, N, K);
+    d.bias = bias; d.relu = relu;
+    return subgnn_tc_gemm_group(&d, 1, 0, stream);
+  }
   // (stand-alone a 64-wide tile is 1 us faster at M = 10000, N = 256 — tools/gemm_sweep.py — but inside the step graph, next to
   // the row kernels, the 128-wide launch with half the CTAs wins by 4 us per step: tools/ab_bench.sh)
   int nt = tc_env("SUBGNN_TC_NT_FWD", N <= 64 ? 64 : 128);
@@ -433,6 +446,11 @@ int subgnn_tc_linear_bwd_input(const float* dy, int ldy, const float* w, int ldw
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(w, ldw), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
+  if (tc_ws_usable(dy, ldy, w, ldw)) {
+    subgnn_gemm_desc d = ws_desc(SUBGNN_GEMM_BWD_INPUT, dy, ldy, w, ldw, dx, lddx, M, N, K);
+    d.scatter_ids = scatter_ids; d.accumulate = accumulate;
+    return subgnn_tc_gemm_group(&d, 1, 0, stream);
+  }
   // output tile width: the widest that still gives every SM a CTA.  (Stand-alone, the scatter GEMM of layer 0 is faster with a
   // 64-wide tile and 4 reduction splits, 16.9 against 26.9 us; inside the step graph, where it shares the GPU with three
   // weight-gradient GEMMs, the narrow tile with 2 splits is 4 us per step better: tools/gemm_sweep.py, tools/ab_bench.sh)
@@ -465,6 +483,12 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
   SG_REQUIRE(M >= 0 && N >= 1 && K >= 1, "bad sizes");
   SG_REQUIRE(tc_aligned(dy, ldy) && tc_aligned(x, ldx), "tensor-core path needs 16-byte aligned rows");
   if (M == 0) return SUBGNN_OK;
+  if (!gather_ids && tc_ws_usable(dy, ldy, x, ldx)) {
+    subgnn_gemm_desc d = ws_desc(SUBGNN_GEMM_BWD_WEIGHT, dy, ldy, x, ldx, dw, lddw, M, N, K);
+    int rc = subgnn_tc_gemm_group(&d, 1, 0, stream);
+    if (!rc && db) rc = subgnn_colsum(dy, ldy, db, M, N, nullptr, stream);
+    return rc;
+  }
   int nt = tc_env("SUBGNN_TC_NT_BWW", K <= 64 ? 64 : 128);
   if (nt != 32 && nt != 64) nt = 128;
   const int tiles = sg_div_up(K, nt) * sg_div_up(N, TC_M);

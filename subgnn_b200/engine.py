@@ -240,6 +240,13 @@ class LstmRunner:
         self.dense_x = None
         # tensor-core (tcgen05, 3xTF32) projections need 16-byte aligned rows; otherwise the FFMA tiles are used
         self.use_tc = (self.D % 4 == 0) and hp.get('b200_tensor_core_gemm', True)
+        # TMA-fed warp-specialised grouped GEMM (tcgemm_ws.cu): dense operands only, so the walk-node rows of the embedding table are
+        # gathered ONCE per step into X0 (they feed the layer-0 projection and its weight gradient); the gate-gradient consumers
+        # of a layer (input gradient + weight gradients) go out as grouped launches.  SUBGNN_TC_LEGACY=1 / SUBGNN_GEMM_GROUPED=0
+        # keep the round-1 per-GEMM launches for A/B runs.
+        self.ws = self.use_tc and bool(_abi.lib.subgnn_tc_ws_available()) and not _flag('SUBGNN_TC_LEGACY', False) and hp.get('b200_ws_gemm', True)
+        self.grouped = int(os.environ.get('SUBGNN_GEMM_GROUPED', hp.get('b200_gemm_grouped', 1))) if self.ws else 0
+        self.X0 = z(M, self.D) if (self.ws and walks is not None) else None
         self.fwd_fn = 'subgnn_tc_linear_fwd' if self.use_tc else 'subgnn_linear_fwd'
         self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
         # inter-layer dropout fused into the recurrence kernels (mask written / applied in place of two element-wise launches per layer)
@@ -271,13 +278,22 @@ class LstmRunner:
             o = a.lstm_off[k]
             call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
                  ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
+        if self.X0 is not None and dense_x is None:
+            call('subgnn_gather_rows', E_ptr, ptr(self.ids_flat), ptr(self.X0), M, D, st)     # anchor_patch_samplers.py:409, once per step
         for k in range(self.nl):
             o = a.lstm_off[k]
             fused = self.fused_drop and self.p_drop > 0 and training
             x_ptr, ldx, ids, din = self._layer_input(k, E_ptr, training, seed, step_dev, st, make=not fused)
             sf, sr = self.steps(k)
             w_ih, G = a.base_addr(o['weight_ih']), ptr(self.G[k])
-            if sr == T:
+            if self.ws and ids is None:
+                descs = [_abi.gemm_desc(_abi.GEMM_FWD, x_ptr, ldx, w_ih, din, G, 8 * H, M, 8 * H if sr == T else 4 * H, din, bias=ptr(self.bsum[k]))]
+                if sr != T:      # 'last' aggregator, top layer: reverse-direction gates of the rows t = T-1 only (SubGNN.py:83), same launch
+                    xl, ldxl, _ = self._last_rows(k, x_ptr, ldx, None)
+                    descs.append(_abi.gemm_desc(_abi.GEMM_FWD, xl, ldxl, w_ih + 4 * (4 * H * din), din, G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H,
+                                                self.n_seq, 4 * H, din, bias=self.bsum[k].data_ptr() + 4 * 4 * H))
+                _abi.gemm_group(descs, st)
+            elif sr == T:
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 8 * H, din, 0, st)
             else:
                 # 'last' aggregator, top layer: the reverse direction is only ever read at t = T-1 (SubGNN.py:83), so its
@@ -307,6 +323,8 @@ class LstmRunner:
         """(x pointer, leading dim, gather ids, K) of layer k's input rows (all n_seq*T of them)."""
         H, D, M = self.H, self.D, self.n_seq * self.T
         if k == 0:
+            if self.X0 is not None and self.dense_x is None:
+                return ptr(self.X0), D, None, D
             return E_ptr, D, (ptr(self.ids_flat) if self.dense_x is None else None), D
         x = self.OUT[k - 1]
         if self.p_drop > 0 and training:
@@ -358,6 +376,11 @@ class LstmRunner:
             w_ih, gw_ih = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], g)
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
+            if self.ws and ids is None:
+                self._backward_gemms_ws(k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux)
+                if k > 0 and self.p_drop > 0 and training and not fused:
+                    call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
+                continue
             # ---- weight gradients: off the critical chain ----
             for a_ in aux:
                 a_.wait_stream(cur)
@@ -395,6 +418,62 @@ class LstmRunner:
                 call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
         for a_ in aux:
             cur.wait_stream(a_)
+
+
+    def _backward_gemms_ws(self, k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux):
+        """the consumers of layer k's gate gradients on the TMA-fed grouped kernel (tcgemm_ws.cu): input gradient (the chain) and the
+        three weight gradients.  grouped == 2: ONE launch per layer; grouped == 1: one launch for the LAST processed layer (nothing
+        of the chain follows it: the tail of the backward pass), otherwise the input gradient on the chain stream and the weight
+        gradients as one companion launch on an auxiliary stream, capped to the SMs the chain launch leaves free; grouped == 0:
+        one launch per product."""
+        a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
+        o = a.lstm_off[k]
+        gd = _abi.gemm_desc
+        w_ih, gw_ih, gw_hh = a.base_addr(o['weight_ih']), a.base_addr(o['weight_ih'], 'grads'), a.base_addr(o['weight_hh'], 'grads')
+        for a_ in aux:                                         # every auxiliary stream joins the capture / the step's dependency chain
+            a_.wait_stream(cur)
+        bw = [gd(_abi.GEMM_BWD_WEIGHT, dG, 8 * H, x_ptr, ldx, gw_ih, din, M, n_out, din)]
+        if not full:
+            xl, ldxl, _ = self._last_rows(k, x_ptr, ldx, None)
+            bw.append(gd(_abi.GEMM_BWD_WEIGHT, dG_last, T * 8 * H, xl, ldxl, gw_ih + 4 * (4 * H * din), din, self.n_seq, 4 * H, din))
+        for d_ in range(2 if full else 1):                     # reverse direction took one step from h = 0: no W_hh gradient
+            bw.append(gd(_abi.GEMM_BWD_WEIGHT_SHIFT, dG + 4 * (d_ * 4 * H), 8 * H, self.OUT[k].data_ptr() + 4 * (d_ * H), 2 * H,
+                         gw_hh + 4 * (d_ * 4 * H * H), H, M, 4 * H, H, shift=-1 if d_ == 0 else 1, period=T))
+        bi, bi_after = [], []
+        if k > 0:
+            dx_ptr, lddx, scat = ptr(self.dOUT[k - 1]), 2 * H, None
+        elif dense:
+            dx_ptr, lddx, scat = (ptr(dense_dx) if dense_dx is not None else None), D, None
+        else:
+            dx_ptr, lddx, scat = dE_ptr, D, ptr(self.ids_flat)
+        if dx_ptr:
+            bi.append(gd(_abi.GEMM_BWD_INPUT, dG, 8 * H, w_ih, din, dx_ptr, lddx, M, n_out, din, scatter_ids=scat, accumulate=1 if scat else 0))
+            if not full:
+                w_rev = w_ih + 4 * (4 * H * din)
+                if scat:
+                    bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr, lddx, self.n_seq, 4 * H, din,
+                                 scatter_ids=ptr(self.ids_last), accumulate=1))
+                else:          # read-add-store onto rows the main product writes: after it, not beside it
+                    bi_after.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx, self.n_seq,
+                                       4 * H, din, accumulate=1))
+        mode = self.grouped
+        if mode == 2 or (mode == 1 and (k == 0 or not bi)):
+            _abi.gemm_group(bi + bw, st)
+        elif mode == 1:
+            tiles = ((M + 127) // 128) * ((din + 127) // 128)
+            sms = _abi.lib.subgnn_device_sm_count()
+            with torch.cuda.stream(aux[0]):
+                _abi.gemm_group(bw, aux[0].cuda_stream, max_ctas=max(32, sms - min(sms, tiles)))
+            _abi.gemm_group(bi, st)
+        else:
+            for i, d_ in enumerate(bw):
+                s_ = aux[i % len(aux)]
+                with torch.cuda.stream(s_):
+                    _abi.gemm_group([d_], s_.cuda_stream)
+            for d_ in bi:
+                _abi.gemm_group([d_], st)
+        for d_ in bi_after:
+            _abi.gemm_group([d_], st)
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -836,6 +915,35 @@ class Engine:
         else:
             c.graph[0].replay()
         return c.loss
+
+    # ---- optimizer state (checkpoints) -----------------------------------------------------------------
+    def optimizer_state_dict(self):
+        """Adam state of the fused step in torch.optim.Adam's own state_dict layout over the arena entries in registration order
+        (== SubGNN.parameters() order), so a checkpoint written in fused mode restores into either optimizer."""
+        t = int(self.step_dev.item())
+        state = {}
+        for i, name in enumerate(self.arena.entries):
+            state[i] = {'step': torch.tensor(float(t)), 'exp_avg': self.arena.view(name, 'm').detach().cpu().clone(),
+                        'exp_avg_sq': self.arena.view(name, 'v').detach().cpu().clone()}
+        group = {'lr': self.lr, 'betas': (0.9, 0.999), 'eps': 1e-8, 'weight_decay': 0, 'amsgrad': False, 'params': list(range(len(self.arena.entries)))}
+        return {'state': state, 'param_groups': [group], 'subgnn_b200_step': t, 'names': list(self.arena.entries)}
+
+    def load_optimizer_state_dict(self, sd):
+        names = sd.get('names') or list(self.arena.entries)
+        t = sd.get('subgnn_b200_step')
+        for i, name in enumerate(names):
+            st = sd['state'].get(i)
+            if st is None or name not in self.arena.entries:
+                continue
+            self.arena.view(name, 'm').copy_(torch.as_tensor(st['exp_avg']).to(self.device))
+            self.arena.view(name, 'v').copy_(torch.as_tensor(st['exp_avg_sq']).to(self.device))
+            if t is None:
+                t = int(float(st['step']))
+        self.step_dev.fill_(int(t or 0))
+        if sd.get('param_groups'):
+            self.lr = float(sd['param_groups'][0].get('lr', self.lr))
+            for c in self.ctx.values():
+                c.graph = None                     # the learning rate is a launch argument baked into a captured step
 
     def loss_value(self, B=None):
         """loss of the last enqueued train step as a Python float: waits for the stream, reads the pinned copy."""

@@ -68,7 +68,7 @@ def test_readout_dropout_law(wide):
         live2 = pre2 > 1e-5
         keep2 = h2 != 0
         assert not np.any(keep2 & (pre2 < -1e-5))
-        np.testing.assert_allclose(h2[keep2 & live2], (pre2 / (1 - pd))[keep2 & live2], rtol=1e-4)
+        np.testing.assert_allclose(h2[keep2 & live2], (pre2 / (1 - pd))[keep2 & live2], rtol=1e-4, atol=1e-6)
         rate2 = keep2[live2].mean()
         assert abs(rate2 - (1 - pd)) < _binom_tol(pd, live2.sum()), rate2
         masks1.append((keep1, live1))

@@ -182,6 +182,7 @@ def test_train_config_style_driver_on_the_stand_ins(tmp_path, fused):
         assert 1 <= len(ckpts) <= 2
         ck = torch.load(os.path.join(log_dir, ckpts[0]))
         assert set(ck['state_dict']) == set(model.state_dict())
+        assert ck['optimizer_states'] and len(ck['optimizer_states'][0]['state']) > 0          # Adam moments travel in both step modes
         # train.py:307-316 restore pattern, then the test pass (train.py:411-417)
         fresh = sys.modules['SubGNN'].SubGNN(dict(model.hparams), *PATHS)
         model_dict = fresh.state_dict()
@@ -213,3 +214,39 @@ def test_resample_anchor_patches_each_epoch(tmp_path):
     assert np.array_equal(sims_before, m.engine.prepared['I_S_sim']['train'])
     assert not torch.equal(w_before, m.state_dict()['lin.weight']) and int(m.engine.step_dev.item()) == 3 * len(m.train_dataloader())
     assert losses[-1] < losses[0] and len(m.metric_scores) == 3
+
+
+def test_fused_checkpoint_restores_adam_state_and_step_counter(tmp_path):
+    """ADVICE r1: a checkpoint written in fused mode carries the engine's Adam moments and step count (torch.optim.Adam layout);
+    restoring them continues training exactly, restoring the weights alone does not; frozen embeddings appear in the state_dict
+    like the reference's nn.Embedding.from_pretrained(freeze=True) (SubGNN.py:568)."""
+    root = _copy_task(tmp_path)
+    m = _model(root, lin_dropout=0.2)
+    torch.manual_seed(0)
+    batches = list(m.train_dataloader())
+    for b in batches:
+        m.training_step_fused(b)
+    torch.cuda.synchronize()
+    sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+    osd = m.engine.optimizer_state_dict()
+    assert set(osd['state'][0]) >= {'step', 'exp_avg', 'exp_avg_sq'} and float(osd['state'][0]['step']) == len(batches)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-3)
+    opt.load_state_dict({'state': osd['state'], 'param_groups': osd['param_groups']})       # loads into torch's own Adam as is
+    for b in batches:
+        m.training_step_fused(b)
+    conts = {}
+    for name, restore in (('warm', True), ('cold', False)):
+        f = _model(root, lin_dropout=0.2)
+        f.load_state_dict(sd)
+        if restore:
+            f.engine.load_optimizer_state_dict(osd)
+        for b in batches:
+            f.training_step_fused(b)
+        torch.cuda.synchronize()
+        conts[name] = {k: v.detach().cpu().numpy() for k, v in f.state_dict().items()}
+    want = {k: v.detach().cpu().numpy() for k, v in m.state_dict().items()}
+    for k in want:
+        np.testing.assert_allclose(conts['warm'][k], want[k], rtol=1e-5, atol=1e-7, err_msg=k)
+    assert max(float(np.abs(conts['cold'][k] - want[k]).max()) for k in want) > 1e-4
+    mf = _model(root, freeze_node_embeds=True)
+    assert 'node_embeddings.weight' in mf.state_dict() and not dict(mf.named_parameters())['node_embeddings.weight'].requires_grad

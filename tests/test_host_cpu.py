@@ -126,3 +126,50 @@ def test_bench_stdout_carries_exactly_one_json_line():
     assert r.returncode == 0, r.stderr
     assert r.stdout.strip().splitlines() == [json.dumps({'ok': 1})]
     assert 'native banner' in r.stderr and 'python print' in r.stderr
+
+
+@pytest.mark.parametrize('kind', ['density', 'cutratio'])
+def test_property_dataset_generator_follows_the_reference_recipe(kind):
+    """DENSITY / CUTRATIO data sets restated from prepare_dataset/prepare_dataset.py (:288-327 BFS, :469-516 planting,
+    :552-617 edge editing toward the drawn target, :619-633 largest-component relabelling, :641-728 equal-count label bins,
+    :756-779 80/10/10 split).  Reduced size; checks the properties the recipe guarantees."""
+    import networkx as nx
+    from subgnn_b200 import synth
+    n, n_sub, k = 1500, 90, 20
+    edges, subs, labs, values = synth.generate_property_dataset(kind, n=n, m=5, n_subgraphs=n_sub, n_subgraph_nodes=k, seed=42)
+    G = nx.Graph()
+    G.add_edges_from(edges.tolist())
+    n_nodes = G.number_of_nodes()
+    assert nx.is_connected(G) and sorted(G.nodes()) == list(range(n_nodes))            # largest component, consecutive ids
+    assert [len(subs[s]) for s in ('train', 'val', 'test')] == [72, 9, 9]
+    all_subs = [s for sp in ('train', 'val', 'test') for s in subs[sp]]
+    all_labs = np.concatenate([labs[sp] for sp in ('train', 'val', 'test')])
+    assert all(1 <= u <= n_nodes for s in all_subs for u in s) and all(len(set(s)) == len(s) <= k for s in all_subs)
+    assert set(all_labs.tolist()) == {0, 1, 2}
+    vals = []
+    for s in all_subs:
+        sg = G.subgraph([u - 1 for u in s])
+        if kind == 'density':
+            vals.append(nx.density(sg))
+        else:
+            vals.append(len(list(nx.edge_boundary(G, sg.nodes))) / (len(s) * (n_nodes - len(s))))
+    vals = np.asarray(vals)
+    # labels are the equal-count bins of the achieved values: monotone in the value
+    order = np.argsort(vals, kind='stable')
+    assert np.all(np.diff(all_labs[order]) >= 0)
+    assert np.bincount(all_labs, minlength=3).min() >= n_sub // 6
+    if kind == 'density':
+        # every subgraph was edited to within epsilon of one of the three targets (always reachable in <= 100 edits at 20 nodes)
+        near = np.min(np.abs(vals[:, None] - np.asarray(synth.DENSITY_RANGE)[None, :]), axis=1)
+        assert np.mean(near < synth.DENSITY_EPSILON + 0.03) > 0.8
+        cc = [nx.number_connected_components(G.subgraph([u - 1 for u in s])) for s in all_subs]
+        assert 1.5 < np.mean(cc) < 6.0                                                  # F16: edge removal fragments the BFS subgraphs
+    else:
+        # planted complete graphs stay (nearly) complete inside — cut-ratio editing touches boundary edges only, and a boundary edge
+        # of one subgraph is an inner edge of another only where two planted node sets overlap — and the boundary moved toward the
+        # targets: <= 100 edits per subgraph, so the ratio sits between the untouched level and the highest target
+        assert np.mean([nx.density(G.subgraph([u - 1 for u in s])) for s in all_subs if len(s) == k]) > 0.9
+        assert vals.min() > 0.0 and vals.max() <= max(synth.CUT_RATIO_RANGE) + synth.CUT_RATIO_EPSILON
+    # deterministic in the seed
+    e2, s2, l2, v2 = synth.generate_property_dataset(kind, n=n, m=5, n_subgraphs=n_sub, n_subgraph_nodes=k, seed=42)
+    assert np.array_equal(edges, e2) and s2 == subs and np.array_equal(values, v2)
