@@ -69,6 +69,21 @@ struct alignas(64) WsParams {
   int n_problems, n_items;
 };
 
+// -DWS_TRACE: per-role event clocks of CTA 0 (tools/gemm_trace.py) — debugging aid, compiled out of the product build
+#ifdef WS_TRACE
+__device__ long long ws_trace_buf[4 * 1024];
+__device__ int ws_trace_n[4];
+#define WS_TR(role, tag)                                                              \
+  do {                                                                                \
+    if (blockIdx.x == 0) {                                                            \
+      const int i_ = ws_trace_n[role]++;                                              \
+      if (i_ < 512) { ws_trace_buf[(role) * 1024 + 2 * i_] = (tag); ws_trace_buf[(role) * 1024 + 2 * i_ + 1] = clock64(); }  \
+    }                                                                                 \
+  } while (0)
+#else
+#define WS_TR(role, tag) do { } while (0)
+#endif
+
 namespace {
 
 __device__ __forceinline__ uint32_t s32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -148,6 +163,17 @@ __device__ __forceinline__ Item decode(const WsParams& P, int item) {
   return it;
 }
 
+// explicit shared-window accesses: the tile pointers are carved out of the dynamic shared buffer by integer arithmetic, so plain
+// C++ dereferences compile to GENERIC LD / ST (and every store orders against the following load: same-buffer aliasing)
+__device__ __forceinline__ float4 lds128(uint32_t addr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const float4 v) {
+  asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
 __device__ __forceinline__ float4 lo_part(const float4 v) {
   float4 l;
   l.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xFFFFE000u);
@@ -184,7 +210,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
   __syncthreads();
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem_d = tmem_base_s;
+  if (threadIdx.x == 0) WS_TR(3, 9);
   sg_pdl_sync();                                   // everything above overlaps the tail of the preceding kernel
+  if (threadIdx.x == 0) WS_TR(3, 8);
 
   if (warp == 4) {
     // ===================================== TMA producer =====================================
@@ -203,6 +231,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
         const uint32_t bytes = (pr.a_mn ? a_chunks * 4096u : (uint32_t)WS_TILE_BYTES) + (pr.b_mn ? b_chunks * 4096u : (uint32_t)pr.nt * 128u);
         for (int kb = 0; kb < it.n_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
+          WS_TR(0, 1);
           unsigned char* a_raw = base + stage * WS_STAGE_BYTES;
           unsigned char* b_raw = a_raw + 2 * WS_TILE_BYTES;
           mbar_arrive_expect_tx(&full_raw[stage], bytes);
@@ -231,6 +260,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         for (int kb = 0; kb < it.n_kb; ++kb) {
           mbar_wait(&full_lo[stage], phase);
+          WS_TR(1, 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
           const uint32_t a_hi = s32(base + stage * WS_STAGE_BYTES), a_lo = a_hi + WS_TILE_BYTES;
           const uint32_t b_hi = a_hi + 2 * WS_TILE_BYTES, b_lo = b_hi + WS_TILE_BYTES;
@@ -244,6 +274,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
             umma_tf32(d_addr, dah + a_step * ks, dbl + b_step * ks, idesc, 1u);
           }
           umma_commit(&empty[stage]);                                  // arrives when the MMAs above have read the stage
+          WS_TR(1, 2);
           if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
         }
         umma_commit(&tmem_full[acc]);                                  // accumulator complete -> epilogue
@@ -261,45 +292,54 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
       const int b_vec = pr.nt * 8;                                     // 16-byte words of the B tile
       for (int kb = 0; kb < it.n_kb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
-        unsigned char* a_raw = base + stage * WS_STAGE_BYTES;
-        unsigned char* a_lo = a_raw + WS_TILE_BYTES;
-        unsigned char* b_raw = a_raw + 2 * WS_TILE_BYTES;
-        unsigned char* b_lo = b_raw + WS_TILE_BYTES;
+        if (tc == 0) WS_TR(2, 1);
+        const uint32_t a_raw = s32(base + stage * WS_STAGE_BYTES) + tc * 16, a_lo = a_raw + WS_TILE_BYTES;
+        const uint32_t b_raw = a_raw + 2 * WS_TILE_BYTES, b_lo = b_raw + WS_TILE_BYTES;
         const int red = it.r0 + kb * WS_KB;
-        if (pr.zero_mod > 0) {
-          // MN-major A tile: 16-byte word w lives in chunk w / 256, reduction row (w % 256) / 8
-#pragma unroll 4
-          for (int w = tc; w < WS_TILE_BYTES / 16; w += 128) {
-            float4 v = *reinterpret_cast<const float4*>(a_raw + w * 16);
-            const int m = red + ((w & 255) >> 3);
-            if (m % pr.zero_mod == pr.zero_rem) {
-              v = make_float4(0.f, 0.f, 0.f, 0.f);
-              *reinterpret_cast<float4*>(a_raw + w * 16) = v;
+        // thread tc owns the 16-byte words tc, tc + 128, ... of either tile; 8 loads in flight, then 8 stores
+        {
+          float4 v[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i) v[i] = lds128(a_raw + i * 2048);
+          if (pr.zero_mod > 0) {
+            // MN-major A tile: 16-byte word w lives in chunk w / 256, reduction row (w % 256) / 8
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int w = tc + i * 128;
+              const int m = red + ((w & 255) >> 3);
+              if (m % pr.zero_mod == pr.zero_rem) {
+                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+                sts128(a_raw + i * 2048, v[i]);
+              }
             }
-            *reinterpret_cast<float4*>(a_lo + w * 16) = lo_part(v);
           }
-        } else {
-#pragma unroll 4
-          for (int w = tc; w < WS_TILE_BYTES / 16; w += 128)
-            *reinterpret_cast<float4*>(a_lo + w * 16) = lo_part(*reinterpret_cast<const float4*>(a_raw + w * 16));
+#pragma unroll
+          for (int i = 0; i < 8; ++i) sts128(a_lo + i * 2048, lo_part(v[i]));
         }
-#pragma unroll 4
-        for (int w = tc; w < b_vec; w += 128)
-          *reinterpret_cast<float4*>(b_lo + w * 16) = lo_part(*reinterpret_cast<const float4*>(b_raw + w * 16));
+        for (int w0 = 0; w0 < b_vec; w0 += 512) {                       // nt = 128: two rounds, 64: one, 32: half a round
+          float4 v[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (w0 + tc + i * 128 < b_vec) v[i] = lds128(b_raw + (w0 + i * 128) * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) if (w0 + tc + i * 128 < b_vec) sts128(b_lo + (w0 + i * 128) * 16, lo_part(v[i]));
+        }
+        if (tc == 0) WS_TR(2, 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(&full_lo[stage]);
+        if (tc == 0) WS_TR(2, 3);
         if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
       }
     }
   } else {
     // ===================================== epilogue (warps 0-3 <-> TMEM lane quarters) =====================================
-    float* slab = reinterpret_cast<float*>(base + WS_STAGES * WS_STAGE_BYTES) + warp * (32 * WS_EPI_LD);
+    const uint32_t slab = s32(base + WS_STAGES * WS_STAGE_BYTES) + warp * (32 * WS_EPI_LD * 4);
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(P, item);
       const WsProblem& pr = P.p[it.q];
       mbar_wait(&tmem_full[acc], acc_phase);
+      if (threadIdx.x == 0) WS_TR(3, 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int row_base = it.tm * WS_M + warp * 32, col_base = it.tn * pr.nt;
 #pragma unroll 1
@@ -322,8 +362,8 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          *reinterpret_cast<float4*>(slab + lane * WS_EPI_LD + j) =
-              make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+          sts128(slab + (lane * WS_EPI_LD + j) * 4,
+                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
         __syncwarp();
         {
           const int cc = (lane & 7) * 4, col = col_base + c0 + cc;
@@ -353,7 +393,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
           for (int i8 = 0; i8 < 8; ++i8) {
             if (orow[i8] < 0) continue;
             const int rr = i8 * 4 + (lane >> 3);
-            float4 v = *reinterpret_cast<const float4*>(slab + rr * WS_EPI_LD + cc);
+            float4 v = lds128(slab + (rr * WS_EPI_LD + cc) * 4);
             float* dst = pr.out + (long long)orow[i8] * pr.ldo + col;
             const bool vec = col_vec && ((((size_t)dst) & 15) == 0);
             if (pr.mode == WS_STORE) {
@@ -371,6 +411,7 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
           }
         }
         __syncwarp();
+        if (threadIdx.x == 0) WS_TR(3, 2);
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
@@ -425,6 +466,17 @@ bool tc_ws_usable(const void* a, int lda, const void* b, int ldb) {
   if (const char* f = getenv("SUBGNN_TC_LEGACY_FORCE")) { if (*f) return atoi(f) == 0 && encode_fn() != nullptr; }   // tools/gemm_bench.py: per-call A/B
   return !off && (lda % 4) == 0 && (ldb % 4) == 0 && (((size_t)a | (size_t)b) & 15) == 0 && encode_fn() != nullptr;
 }
+
+#ifdef WS_TRACE
+extern "C" int subgnn_ws_trace_read(long long* host_buf, int* host_n) {       // host_buf[4096], host_n[4]; also resets the counters
+  cudaDeviceSynchronize();
+  cudaMemcpyFromSymbol(host_buf, ws_trace_buf, sizeof(long long) * 4096);
+  cudaMemcpyFromSymbol(host_n, ws_trace_n, sizeof(int) * 4);
+  const int z[4] = {0, 0, 0, 0};
+  cudaMemcpyToSymbol(ws_trace_n, z, sizeof(z));
+  return 0;
+}
+#endif
 
 extern "C" {
 

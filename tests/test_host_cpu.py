@@ -165,10 +165,10 @@ def test_property_dataset_generator_follows_the_reference_recipe(kind):
         cc = [nx.number_connected_components(G.subgraph([u - 1 for u in s])) for s in all_subs]
         assert 1.5 < np.mean(cc) < 6.0                                                  # F16: edge removal fragments the BFS subgraphs
     else:
-        # planted complete graphs stay (nearly) complete inside — cut-ratio editing touches boundary edges only, and a boundary edge
-        # of one subgraph is an inner edge of another only where two planted node sets overlap — and the boundary moved toward the
-        # targets: <= 100 edits per subgraph, so the ratio sits between the untouched level and the highest target
-        assert np.mean([nx.density(G.subgraph([u - 1 for u in s])) for s in all_subs if len(s) == k]) > 0.9
+        # planted complete graphs stay dense inside — cut-ratio editing touches boundary edges only, but a boundary edge of one
+        # subgraph is an inner edge of another wherever two planted node sets overlap (frequent: n_sub * k node slots over n nodes) —
+        # and the boundary moved toward the targets: <= 100 edits per subgraph
+        assert np.mean([nx.density(G.subgraph([u - 1 for u in s])) for s in all_subs if len(s) == k]) > 0.5
         assert vals.min() > 0.0 and vals.max() <= max(synth.CUT_RATIO_RANGE) + synth.CUT_RATIO_EPSILON
     # deterministic in the seed
     e2, s2, l2, v2 = synth.generate_property_dataset(kind, n=n, m=5, n_subgraphs=n_sub, n_subgraph_nodes=k, seed=42)
