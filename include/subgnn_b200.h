@@ -249,6 +249,7 @@ typedef struct subgnn_model_desc {
   float* H1; float* H2;      /* [B][h1], [B][h2] post-relu post-dropout */
   float* logits;             /* [B][K] */
   float* loss_b;             /* [B] per-sample loss terms (already divided by B [and K]) */
+  float* loss_sum;           /* [1] zeroed by the caller; subgnn_model_readout adds the per-sample terms (the step's loss) */
   float* dlogits; float* dH2; float* dH1; float* dZ;
   unsigned long long seed;   /* dropout key */
   int n_sub, n_cc, n_nodes;
@@ -259,6 +260,8 @@ typedef struct subgnn_model_desc {
   int B, R_cap;
   unsigned step;             /* dropout salt (optimizer step counter) */
   float lin_dropout;
+  int mlp_fused;             /* subgnn_model_readout also accumulates the MLP weight / bias gradients (from its own d logits): the fused
+                                training step; subgnn_model_wgrad then skips them */
 } subgnn_model_desc;
 
 /* batch bookkeeping + per-step weight transposes + q = w_p . x_anchor for every shared anchor list */
@@ -278,6 +281,13 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream);
 int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training); H1 must be zero on entry (split-K target) */
 /* backward of all rows (autograd of the above): N-channel chains, property-aware outputs, pooling; scatters into dE / dq / Ndpre */
 int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream);
+/* The readout section as ONE launch of 8-CTA clusters (SubGNN.py:303-310 masked-sum output -> lin -> lin2 -> lin3, loss :338-342
+ * and, when training, the backward down to dZ and — with d->mlp_fused — the MLP weight / bias gradients): every CTA of a cluster
+ * owns a slice of the hid columns of Z / W1 (kept in shared memory for forward, dZ and dW1), partial first-layer sums are
+ * exchanged through distributed shared memory; a cluster serves 8 samples (one per CTA behind the first layer).  Same outputs and dropout masks as
+ * subgnn_model_mlp_fwd (+ the MLP part of subgnn_model_wgrad); needs d->loss_sum zeroed.  _supported: shapes the kernel takes. */
+int subgnn_model_readout_supported(const subgnn_model_desc* d);
+int subgnn_model_readout(const subgnn_model_desc* d, void* stream);
 /* per-sample MLP backward from externally supplied dlogits (autograd entry) */
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream);
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);

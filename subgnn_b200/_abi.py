@@ -61,6 +61,7 @@ SIGNATURES = {
     'subgnn_model_q_fwd_part': [P, I, P],
     'subgnn_model_rows_fwd': [P, I, P],
     'subgnn_model_mlp_fwd': [P, P],
+    'subgnn_model_readout': [P, P],
     'subgnn_model_rows_bwd': [P, I, P],
     'subgnn_model_mlp_bwd': [P, P],
     'subgnn_model_q_bwd': [P, P],
@@ -79,6 +80,7 @@ _OTHER = {
     'subgnn_device_sm_count': ([], I),
     'subgnn_model_desc_size': ([], I),
     'subgnn_gemm_desc_size': ([], I),
+    'subgnn_model_readout_supported': ([P], I),
     'subgnn_tc_ws_available': ([], I),
     'subgnn_launch_count': ([], U64),
     'subgnn_lstm_fused_dropout_supported': ([I], I),

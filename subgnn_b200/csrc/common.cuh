@@ -126,6 +126,22 @@ __device__ __forceinline__ void sg_stage(float* dst, int n, Src src) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// thread-block clusters: rank, barrier, store into a peer CTA's shared memory (distributed shared memory)
+__device__ __forceinline__ unsigned sg_cluster_rank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void sg_cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void sg_st_cluster(const float* local_addr, unsigned rank, float v) {
+  uint32_t remote;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(remote) : "r"((uint32_t)__cvta_generic_to_shared(local_addr)), "r"(rank));
+  asm volatile("st.shared::cluster.f32 [%0], %1;" :: "r"(remote), "f"(v) : "memory");
+}
+
+// ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

@@ -656,6 +656,286 @@ __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------
+// Readout section as one cluster kernel (SubGNN.py:303-310, :338-342 and their backward).  Cluster = RO_CL CTAs = RO_BT samples
+// (one sample per CTA behind the first layer); a batch of B samples runs on B / RO_BT clusters = B CTAs:
+//   every CTA owns a slice of S = ceil(hid / RO_CL) columns of Z and of W1 (staged ONCE, used by the forward product, by dZ and
+//   by dW1).
+//   1  partial[b][j] = sum_{i in slice} Z[b][i] W1[j][i]                 -> sent to the owner CTA of sample b (DSMEM)
+//   2  owner: H1 = drop(relu(sum of the RO_CL partials + b1)), H2, logits, loss, d logits, dH2, dH1
+//      dH1 row broadcast to every CTA of the cluster (DSMEM); mlp_fused: dW2, dW3, db1-3 from the owner's sample
+//   3  dZ[b][slice] = dH1[b] . W1[:, slice];   mlp_fused: dW1[:, slice] += dH1^T Z[:, slice]
+// (first version: 32 samples per cluster, i.e. 8 CTAs at the reference batch of 32 — 45 us against 30 us for the three
+// batch-level kernels: too few SMs for the 0.45 MB of W1; one sample per CTA puts B CTAs on the section)
+#define RO_CL 8
+#define RO_BT 8
+#define RO_THREADS 256
+#define RO_IQ 4            // phase 1: the slice is cut in RO_IQ quarters over thread groups
+
+struct RoSmem {
+  float *w1t, *zs, *w2t, *w2n, *recv, *gall, *part, *h1s, *h2s, *g2s, *g1s, *lgs, *dls, *bs, *w3s;
+  int S, ld1;
+};
+__host__ __device__ inline int ro_slice(int hid) { return ((hid + RO_CL - 1) / RO_CL + 3) / 4 * 4; }
+__host__ __device__ inline size_t ro_smem_floats(int hid, int h1, int h2, int K) {
+  const int S = ro_slice(hid);
+  return (size_t)S * (h1 + 1) + (size_t)RO_BT * S + 2 * (size_t)h1 * h2 + (size_t)RO_CL * h1 + (size_t)h1 * RO_BT + (size_t)RO_IQ * RO_BT * h1 +
+         (size_t)(2 * h1 + 2 * h2 + 2 * K) + (size_t)(h1 + h2 + K + K * h2) + 32;
+}
+__device__ __forceinline__ RoSmem ro_carve(float* sm, const Desc& d) {
+  RoSmem r;
+  r.S = ro_slice(d.hid);
+  r.ld1 = d.h1 + 1;
+  r.zs = sm;                                              // [RO_BT][S]      (16-byte aligned rows: S % 4 == 0)
+  r.gall = r.zs + (size_t)RO_BT * r.S;                    // [h1][RO_BT]     dH1 of the cluster's samples, sample index contiguous
+  r.w2t = r.gall + (size_t)d.h1 * RO_BT;                  // [h1][h2]
+  r.w2n = r.w2t + (size_t)d.h1 * d.h2;                    // [h2][h1]
+  r.recv = r.w2n + (size_t)d.h1 * d.h2;                   // [RO_CL][h1]     partial first-layer sums of MY sample from every CTA
+  r.part = r.recv + (size_t)RO_CL * d.h1;                 // [RO_IQ][RO_BT][h1]
+  r.h1s = r.part + (size_t)RO_IQ * RO_BT * d.h1;          // [h1]
+  r.g1s = r.h1s + d.h1;                                   // [h1]
+  r.h2s = r.g1s + d.h1;                                   // [h2]
+  r.g2s = r.h2s + d.h2;                                   // [h2]
+  r.lgs = r.g2s + d.h2;                                   // [K]
+  r.dls = r.lgs + d.n_classes;                            // [K]
+  r.bs = r.dls + d.n_classes;                             // [h1 + h2 + K]   the three bias vectors
+  r.w3s = r.bs + d.h1 + d.h2 + d.n_classes;               // [K][h2]         lin3 weights
+  r.w1t = r.w3s + (size_t)d.n_classes * d.h2;             // [S][h1 + 1]     W1^T slice, rows padded by one float (conflict-free both ways)
+  return r;
+}
+
+__global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
+  extern __shared__ __align__(16) float sm[];
+  const RoSmem R = ro_carve(sm, d);
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const unsigned rank = sg_cluster_rank();
+  const int cl = blockIdx.x / RO_CL;
+  const int b0 = cl * RO_BT, bn = min(RO_BT, d.B - b0);
+  const int S = R.S, ld1 = R.ld1, h1 = d.h1, h2 = d.h2, K = d.n_classes;
+  const int i0 = (int)rank * S, Sr = max(0, min(S, d.hid - i0));      // my columns [i0, i0 + Sr)
+  const bool bwd = d.training && d.dZ;
+  // ---- weights: staged before the dependency wait (parameters / derived copies whose producers never trigger early) ----
+  {
+    const float* wt = d.lin_wt[0] + (size_t)i0 * h1;                  // W1^T rows i0 .. : contiguous, 16-byte aligned when h1 % 4 == 0
+    const bool v4 = (h1 % 4) == 0 && ((((size_t)wt) & 15) == 0);
+    if (v4) {
+      const int n4 = S * h1 / 4, nv = Sr * h1 / 4;
+      for (int e0 = tid; e0 < n4; e0 += 8 * RO_THREADS) {
+        float4 r8[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { const int e = e0 + u * RO_THREADS; r8[u] = (e < nv) ? __ldg(reinterpret_cast<const float4*>(wt) + e) : make_float4(0.f, 0.f, 0.f, 0.f); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) {
+          const int e = e0 + u * RO_THREADS;
+          if (e < n4) {
+            float* dst = R.w1t + ((4 * e) / h1) * ld1 + ((4 * e) % h1);
+            dst[0] = r8[u].x; dst[1] = r8[u].y; dst[2] = r8[u].z; dst[3] = r8[u].w;
+          }
+        }
+      }
+    } else {
+      for (int e = tid; e < S * h1; e += RO_THREADS) R.w1t[(e / h1) * ld1 + (e % h1)] = (e < Sr * h1) ? __ldg(wt + e) : 0.f;
+    }
+    const float* src_t = d.lin_wt[1];
+    const float* src_n = d.lin_w[1];
+    const int nw = h1 * h2;
+    sg_stage<8>(R.w2t, bwd ? 2 * nw : nw, [&](int e) { return e < nw ? __ldg(src_t + e) : __ldg(src_n + e - nw); });
+    // everything the chain behind the first layer reads from global memory — biases, lin3 weights, the label — is fetched here,
+    // before the wait: that chain is ~8 dependent phases and each L2 round trip inside it costs ~1 us of the step's critical path
+    sg_stage<8>(R.bs, h1 + h2 + K + K * h2, [&](int e) {
+      if (e < h1) return __ldg(d.lin_b[0] + e);
+      if (e < h1 + h2) return __ldg(d.lin_b[1] + e - h1);
+      if (e < h1 + h2 + K) return __ldg(d.lin_b[2] + e - h1 - h2);
+      return __ldg(d.lin_w[2] + e - h1 - h2 - K);
+    });
+  }
+  // (batch_idx is written by the step's H2D copy before any kernel of the step; labels are static)
+  const int my_b = blockIdx.x / RO_CL * RO_BT + (int)rank;
+  int my_label = 0;
+  if (tid == 0 && my_b < d.B && !d.multilabel && d.labels) my_label = d.labels[d.batch_idx[my_b]];
+  sg_pdl_sync();
+  // ---- Z slice ----
+  {
+    const bool v4 = (d.hid % 4) == 0 && ((((size_t)d.Z) & 15) == 0);    // i0 and S are multiples of 4
+    if (v4) {
+      const int S4 = S / 4;
+      for (int e = tid; e < RO_BT * S4; e += RO_THREADS) {
+        const int b = e / S4, i = (e % S4) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (b < bn && i < Sr) {
+          const float* src = d.Z + (size_t)(b0 + b) * d.hid + i0 + i;
+          if (i + 3 < Sr) v = *reinterpret_cast<const float4*>(src);
+          else { v.x = src[0]; if (i + 1 < Sr) v.y = src[1]; if (i + 2 < Sr) v.z = src[2]; }
+        }
+        *reinterpret_cast<float4*>(R.zs + (size_t)b * S + i) = v;
+      }
+    } else {
+      for (int e = tid; e < RO_BT * S; e += RO_THREADS) {
+        const int b = e / S, i = e % S;
+        R.zs[e] = (b < bn && i < Sr) ? d.Z[(size_t)(b0 + b) * d.hid + i0 + i] : 0.f;
+      }
+    }
+  }
+  __syncthreads();
+  // ---- 1: partial first-layer sums of my slice: work item = (unit j, quarter q of the slice), all RO_BT samples ----
+  {
+    const int S4q = ((S / 4 + RO_IQ - 1) / RO_IQ) * 4;                 // columns per quarter (multiple of 4)
+    for (int it = tid; it < h1 * RO_IQ; it += RO_THREADS) {
+      const int j = it % h1, q = it / h1;
+      const int ia = q * S4q, ib = min(S, ia + S4q);
+      float acc[RO_BT];
+#pragma unroll
+      for (int u = 0; u < RO_BT; ++u) acc[u] = 0.f;
+      for (int i = ia; i < ib; i += 4) {
+        const float w0 = R.w1t[(i + 0) * ld1 + j], w1 = R.w1t[(i + 1) * ld1 + j], w2 = R.w1t[(i + 2) * ld1 + j], w3 = R.w1t[(i + 3) * ld1 + j];
+#pragma unroll
+        for (int u = 0; u < RO_BT; ++u) {
+          const float4 z = *reinterpret_cast<const float4*>(R.zs + (size_t)u * S + i);
+          acc[u] = fmaf(z.x, w0, fmaf(z.y, w1, fmaf(z.z, w2, fmaf(z.w, w3, acc[u]))));
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < RO_BT; ++u) R.part[((size_t)q * RO_BT + u) * h1 + j] = acc[u];
+    }
+    __syncthreads();
+    for (int o = tid; o < RO_BT * h1; o += RO_THREADS) {               // quarter sums -> the owner CTA of sample b = o / h1
+      const int b = o / h1, j = o % h1;
+      float v = 0.f;
+#pragma unroll
+      for (int q = 0; q < RO_IQ; ++q) v += R.part[((size_t)q * RO_BT + b) * h1 + j];
+      sg_st_cluster(R.recv + (size_t)rank * h1 + j, (unsigned)b, v);
+    }
+  }
+  sg_cluster_sync();
+  // ---- 2: my sample behind the first layer ----
+  const int b = b0 + (int)rank;                                        // the sample I own
+  const bool live = b < d.B;
+  for (int j = tid; j < h1; j += RO_THREADS) {
+    float acc = 0.f;
+#pragma unroll
+    for (int r = 0; r < RO_CL; ++r) acc += R.recv[(size_t)r * h1 + j];
+    acc = fmaxf(acc + R.bs[j], 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * h1 + j, d.lin_dropout);
+    R.h1s[j] = acc;
+    if (live) d.H1[(size_t)b * h1 + j] = acc;
+  }
+  __syncthreads();
+  for (int j = tid; j < h2; j += RO_THREADS) {
+    float acc = R.bs[h1 + j];
+#pragma unroll 8
+    for (int i = 0; i < h1; ++i) acc = fmaf(R.h1s[i], R.w2t[i * h2 + j], acc);
+    acc = fmaxf(acc, 0.f);
+    if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * h2 + j, d.lin_dropout);
+    R.h2s[j] = acc;
+    if (live) d.H2[(size_t)b * h2 + j] = acc;
+  }
+  __syncthreads();
+  for (int c = warp; c < K; c += RO_THREADS / 32) {                     // lin3: warp per class
+    float acc = 0.f;
+    for (int i = lane; i < h2; i += 32) acc = fmaf(R.h2s[i], R.w3s[c * h2 + i], acc);
+    acc = warp_sum(acc);
+    if (lane == 0) {
+      acc += R.bs[h1 + h2 + c];
+      R.lgs[c] = acc;
+      if (live) d.logits[(size_t)b * K + c] = acc;
+    }
+  }
+  __syncthreads();
+  if (tid == 0) {
+    float loss = 0.f;
+    if (live) {
+      const float* lg = R.lgs;
+      const int sub = d.multilabel ? d.batch_idx[b] : 0;
+      if (!d.multilabel) {
+        float mx = lg[0];
+        for (int c = 1; c < K; ++c) mx = fmaxf(mx, lg[c]);
+        float se = 0.f;
+        for (int c = 0; c < K; ++c) se += expf(lg[c] - mx);
+        const float lse = mx + logf(se);
+        const int y = my_label;
+        loss = (lse - lg[y]) / (float)d.B;
+        for (int c = 0; c < K; ++c) R.dls[c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)d.B;
+      } else {
+        const float inv = 1.f / ((float)d.B * (float)K);
+        for (int c = 0; c < K; ++c) {
+          const float x = lg[c], y = d.labels_multi[(size_t)sub * K + c];
+          loss += (fmaxf(x, 0.f) - x * y + log1pf(expf(-fabsf(x)))) * inv;
+          R.dls[c] = (1.f / (1.f + expf(-x)) - y) * inv;
+        }
+      }
+      if (d.dlogits) for (int c = 0; c < K; ++c) d.dlogits[(size_t)b * K + c] = R.dls[c];
+      d.loss_b[b] = loss;
+      if (d.loss_sum) atomicAdd(d.loss_sum, loss);
+    } else {
+      for (int c = 0; c < K; ++c) R.dls[c] = 0.f;
+    }
+  }
+  if (!bwd) return;                                                     // (uniform over the cluster: no CTA waits at barrier 2)
+  __syncthreads();
+  for (int j = tid; j < h2; j += RO_THREADS) {
+    float acc = 0.f;
+    for (int c = 0; c < K; ++c) acc = fmaf(R.dls[c], R.w3s[c * h2 + j], acc);
+    const float sc = sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * h2 + j, d.lin_dropout);
+    acc = (live && R.h2s[j] > 0.f) ? acc * sc : 0.f;
+    if (live) d.dH2[(size_t)b * h2 + j] = acc;
+    R.g2s[j] = acc;
+  }
+  __syncthreads();
+  for (int i = tid; i < h1; i += RO_THREADS) {
+    float acc = 0.f;
+#pragma unroll 8
+    for (int j = 0; j < h2; ++j) acc = fmaf(R.g2s[j], R.w2n[j * h1 + i], acc);
+    const float sc = sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * h1 + i, d.lin_dropout);
+    acc = (live && R.h1s[i] > 0.f) ? acc * sc : 0.f;
+    if (live) d.dH1[(size_t)b * h1 + i] = acc;
+    R.g1s[i] = acc;
+#pragma unroll
+    for (unsigned r = 0; r < RO_CL; ++r) sg_st_cluster(R.gall + (size_t)i * RO_BT + rank, r, acc);
+  }
+  __syncthreads();
+  if (d.mlp_fused && d.lin_gw[0] && live) {                             // small gradients from my sample (atomics over the B CTAs)
+    for (int o = tid; o < h2 * h1; o += RO_THREADS) {                   // dW2[j][i] += g2[j] h1[i]
+      const float v = R.g2s[o / h1] * R.h1s[o % h1];
+      if (v != 0.f) atomicAdd(d.lin_gw[1] + o, v);
+    }
+    for (int o = tid; o < K * h2; o += RO_THREADS) {                    // dW3[c][j] += dl[c] h2[j]
+      const float v = R.dls[o / h2] * R.h2s[o % h2];
+      if (v != 0.f) atomicAdd(d.lin_gw[2] + o, v);
+    }
+    for (int o = tid; o < h1 + h2 + K; o += RO_THREADS) {               // bias gradients
+      if (o < h1) { if (R.g1s[o] != 0.f) atomicAdd(d.lin_gb[0] + o, R.g1s[o]); }
+      else if (o < h1 + h2) { if (R.g2s[o - h1] != 0.f) atomicAdd(d.lin_gb[1] + o - h1, R.g2s[o - h1]); }
+      else if (R.dls[o - h1 - h2] != 0.f) atomicAdd(d.lin_gb[2] + o - h1 - h2, R.dls[o - h1 - h2]);
+    }
+  }
+  sg_cluster_sync();                                                    // gall complete in every CTA
+  // ---- 3: dZ and dW1 of my slice: thread = column i of the slice ----
+  const bool wgrad = d.mlp_fused && d.lin_gw[0];
+  for (int i = tid; i < Sr; i += RO_THREADS) {
+    float acc[RO_BT], zr[RO_BT];
+#pragma unroll
+    for (int u = 0; u < RO_BT; ++u) { acc[u] = 0.f; zr[u] = R.zs[(size_t)u * S + i]; }
+    float* gw = wgrad ? d.lin_gw[0] + i0 + i : nullptr;
+    for (int j = 0; j < h1; ++j) {
+      const float w = R.w1t[i * ld1 + j];
+      const float4* g4 = reinterpret_cast<const float4*>(R.gall + (size_t)j * RO_BT);
+      float dw = 0.f;
+#pragma unroll
+      for (int q = 0; q < RO_BT / 4; ++q) {
+        const float4 g = g4[q];
+        acc[4 * q + 0] = fmaf(g.x, w, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(g.y, w, acc[4 * q + 1]);
+        acc[4 * q + 2] = fmaf(g.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(g.w, w, acc[4 * q + 3]);
+        dw = fmaf(g.x, zr[4 * q + 0], fmaf(g.y, zr[4 * q + 1], fmaf(g.z, zr[4 * q + 2], fmaf(g.w, zr[4 * q + 3], dw))));
+      }
+      if (wgrad && dw != 0.f) atomicAdd(gw + (size_t)j * d.hid, dw);
+    }
+#pragma unroll
+    for (int u = 0; u < RO_BT; ++u)
+      if (u < bn) d.dZ[(size_t)(b0 + u) * d.hid + i0 + i] = acc[u];
+  }
+}
+
 template <int DPL>
 __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases) {
   sg_pdl_sync();
@@ -949,6 +1229,35 @@ int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
   return rc;
 }
 
+int subgnn_model_readout_supported(const subgnn_model_desc* d) {
+  if (!d || d->h1 < 1 || d->h2 < 1 || d->h1 > 256 || d->h2 > 256 || d->n_classes < 1 || d->n_classes > 64 || d->hid < RO_CL) return 0;
+  if (ro_slice(d->hid) > 4 * RO_THREADS) return 0;
+  return ro_smem_floats(d->hid, d->h1, d->h2, d->n_classes) * sizeof(float) <= 200 * 1024 ? 1 : 0;
+}
+
+int subgnn_model_readout(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  SG_REQUIRE(subgnn_model_readout_supported(d), "shape outside the cluster readout kernel (use subgnn_model_mlp_fwd)");
+  const size_t smem = ro_smem_floats(d->hid, d->h1, d->h2, d->n_classes) * sizeof(float);
+  cudaFuncSetAttribute(readout_cluster_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(RO_CL * sg_div_up(d->B, RO_BT), 1, 1);      // B CTAs (rounded up to whole clusters)
+  cfg.blockDim = dim3(RO_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[2];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = RO_CL; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[1].val.programmaticStreamSerializationAllowed = subgnn_pdl_enabled(SG_PDL_CHAIN);
+  cfg.attrs = attr;
+  cfg.numAttrs = 2;
+  subgnn_note_variant("readout_cluster_kernel");
+  cudaLaunchKernelEx(&cfg, readout_cluster_kernel, *d);
+  return subgnn_check_launch("readout_cluster_kernel");
+}
+
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
@@ -996,7 +1305,7 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
     rc = subgnn_check_launch("n_wgrad_kernel");
     if (rc) return rc;
   }
-  if (d->lin_gw[0]) {
+  if (d->lin_gw[0] && !d->mlp_fused) {
     // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)
     rc = subgnn_linear_bwd_weight(d->dH1, d->h1, d->Z, d->hid, nullptr, d->lin_gw[0], d->hid, d->lin_gb[0], d->B, d->h1, d->hid, nullptr, stream);
     if (rc) return rc;

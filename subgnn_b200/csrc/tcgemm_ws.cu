@@ -183,6 +183,32 @@ __device__ __forceinline__ float4 lo_part(const float4 v) {
   return l;
 }
 
+// column tails / unaligned destinations: element-wise (rare: shapes whose width is not a multiple of 4, odd pitches)
+__device__ __noinline__ void ws_epilogue_tail(uint32_t slab_rd, int row0, int out_rows, const int* ids, float* out, const float* bias, int ldo,
+                                              int col, int out_cols, int mode, int relu) {
+  for (int i8 = 0; i8 < 8; ++i8) {
+    const int row = row0 + i8 * 4;
+    if (row >= out_rows) continue;
+    long long orow = row;
+    if (mode == WS_SCATTER) {
+      orow = ids[row];
+      if (orow == 0) continue;
+    }
+    const float4 v4 = lds128(slab_rd + i8 * (4 * WS_EPI_LD * 4));
+    const float t[4] = {v4.x, v4.y, v4.z, v4.w};
+    float* dst = out + orow * ldo + col;
+    for (int j = 0; j < 4 && col + j < out_cols; ++j) {
+      float v = t[j];
+      if (mode == WS_STORE) {
+        if (bias) v += bias[col + j];
+        if (relu) v = fmaxf(v, 0.f);
+        dst[j] = v;
+      } else if (mode == WS_ACCUM) dst[j] += v;
+      else atomicAdd(dst + j, v);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_constant__ WsParams P) {
   extern __shared__ unsigned char ws_smem_raw[];
   unsigned char* base = reinterpret_cast<unsigned char*>(((uintptr_t)ws_smem_raw + 1023) & ~(uintptr_t)1023);
@@ -214,6 +240,9 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
   sg_pdl_sync();                                   // everything above overlaps the tail of the preceding kernel
   if (threadIdx.x == 0) WS_TR(3, 8);
 
+  // Every role copies the fields of its problem into registers ONCE per work item: the problem table lives in the kernel parameter
+  // bank and is indexed by a run-time problem id, so every `P.p[q].x` is a constant-bank load with a register offset — re-issued
+  // after each asm volatile (the first build spent ~1400 instructions per 32-column epilogue block that way).
   if (warp == 4) {
     // ===================================== TMA producer =====================================
     if (lane == 0) {
@@ -222,26 +251,29 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(P, item);
         const WsProblem& pr = P.p[it.q];
-        const int a_row0 = it.tm * WS_M, b_row0 = it.tn * pr.nt;
+        const CUtensorMap* tmA = &pr.tmA;
+        const CUtensorMap* tmB = &pr.tmB;
+        const int a_mn = pr.a_mn, b_mn = pr.b_mn, nt = pr.nt, b_shift = pr.b_shift, n_kb = it.n_kb, r0 = it.r0;
+        const int a_row0 = it.tm * WS_M, b_row0 = it.tn * nt;
         // only boxes that intersect the tensor are fetched (a fully out-of-range 32-wide chunk of an MN-major operand feeds
         // output rows / columns beyond the matrix, which the epilogue never stores)
         int a_chunks = 1, b_chunks = 1;
-        if (pr.a_mn) a_chunks = min(WS_M / 32, (pr.out_rows - a_row0 + 31) / 32);
-        if (pr.b_mn) b_chunks = min(pr.nt / 32, (pr.out_cols - b_row0 + 31) / 32);
-        const uint32_t bytes = (pr.a_mn ? a_chunks * 4096u : (uint32_t)WS_TILE_BYTES) + (pr.b_mn ? b_chunks * 4096u : (uint32_t)pr.nt * 128u);
-        for (int kb = 0; kb < it.n_kb; ++kb) {
+        if (a_mn) a_chunks = min(WS_M / 32, (pr.out_rows - a_row0 + 31) / 32);
+        if (b_mn) b_chunks = min(nt / 32, (pr.out_cols - b_row0 + 31) / 32);
+        const uint32_t bytes = (a_mn ? a_chunks * 4096u : (uint32_t)WS_TILE_BYTES) + (b_mn ? b_chunks * 4096u : (uint32_t)nt * 128u);
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&empty[stage], phase ^ 1u);
           WS_TR(0, 1);
           unsigned char* a_raw = base + stage * WS_STAGE_BYTES;
           unsigned char* b_raw = a_raw + 2 * WS_TILE_BYTES;
           mbar_arrive_expect_tx(&full_raw[stage], bytes);
-          const int red = it.r0 + kb * WS_KB;
-          if (!pr.a_mn) tma_load_2d(&pr.tmA, &full_raw[stage], a_raw, red, a_row0);
+          const int red = r0 + kb * WS_KB;
+          if (!a_mn) tma_load_2d(tmA, &full_raw[stage], a_raw, red, a_row0);
           else
-            for (int c = 0; c < a_chunks; ++c) tma_load_2d(&pr.tmA, &full_raw[stage], a_raw + c * 4096, a_row0 + 32 * c, red);
-          if (!pr.b_mn) tma_load_2d(&pr.tmB, &full_raw[stage], b_raw, red, b_row0);
+            for (int c = 0; c < a_chunks; ++c) tma_load_2d(tmA, &full_raw[stage], a_raw + c * 4096, a_row0 + 32 * c, red);
+          if (!b_mn) tma_load_2d(tmB, &full_raw[stage], b_raw, red, b_row0);
           else
-            for (int c = 0; c < b_chunks; ++c) tma_load_2d(&pr.tmB, &full_raw[stage], b_raw + c * 4096, b_row0 + 32 * c, red + pr.b_shift);
+            for (int c = 0; c < b_chunks; ++c) tma_load_2d(tmB, &full_raw[stage], b_raw + c * 4096, b_row0 + 32 * c, red + b_shift);
           if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
         }
       }
@@ -251,22 +283,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
     if (lane == 0) {
       int stage = 0, acc = 0;
       uint32_t phase = 0, acc_phase = 0;
+      const uint32_t smem0 = s32(base);
       for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
         const Item it = decode(P, item);
         const WsProblem& pr = P.p[it.q];
-        const uint32_t idesc = idesc_tf32(pr.nt, pr.a_mn, pr.b_mn);
+        const int a_mn = pr.a_mn, b_mn = pr.b_mn, n_kb = it.n_kb;
+        const uint32_t idesc = idesc_tf32(pr.nt, a_mn, b_mn);
+        // descriptor = constant part | start address; the address field advances by whole 16-byte units
+        const uint64_t a_const = (a_mn ? desc_mn_major(0) : desc_k_major(0)), b_const = (b_mn ? desc_mn_major(0) : desc_k_major(0));
+        const uint32_t a_step = a_mn ? 64u : 2u, b_step = b_mn ? 64u : 2u;     // K = 8 per MMA: +1024 B (MN-major) or +32 B (K-major)
         const uint32_t d_addr = tmem_d + (uint32_t)(acc * WS_NT_MAX);
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1u);                  // the epilogue has drained this accumulator
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        for (int kb = 0; kb < it.n_kb; ++kb) {
+        for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(&full_lo[stage], phase);
           WS_TR(1, 1);
           asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-          const uint32_t a_hi = s32(base + stage * WS_STAGE_BYTES), a_lo = a_hi + WS_TILE_BYTES;
-          const uint32_t b_hi = a_hi + 2 * WS_TILE_BYTES, b_lo = b_hi + WS_TILE_BYTES;
-          const uint64_t dah = pr.a_mn ? desc_mn_major(a_hi) : desc_k_major(a_hi), dal = pr.a_mn ? desc_mn_major(a_lo) : desc_k_major(a_lo);
-          const uint64_t dbh = pr.b_mn ? desc_mn_major(b_hi) : desc_k_major(b_hi), dbl = pr.b_mn ? desc_mn_major(b_lo) : desc_k_major(b_lo);
-          const uint64_t a_step = pr.a_mn ? 64 : 2, b_step = pr.b_mn ? 64 : 2;     // K = 8 per MMA: +1024 B (MN-major) or +32 B (K-major)
+          const uint32_t a16 = (smem0 + stage * WS_STAGE_BYTES) >> 4;           // tiles are 1024-byte aligned, < 256 KB: fits the 14-bit field
+          const uint64_t dah = a_const | a16, dal = a_const | (a16 + (WS_TILE_BYTES >> 4));
+          const uint64_t dbh = b_const | (a16 + 2 * (WS_TILE_BYTES >> 4)), dbl = b_const | (a16 + 3 * (WS_TILE_BYTES >> 4));
 #pragma unroll
           for (int ks = 0; ks < WS_KB / 8; ++ks) {
             umma_tf32(d_addr, dah + a_step * ks, dbh + b_step * ks, idesc, (kb > 0 || ks > 0) ? 1u : 0u);
@@ -286,43 +321,40 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
     const int tc = threadIdx.x - 6 * 32;                               // 0 .. 127
     int stage = 0;
     uint32_t phase = 0;
+    const uint32_t smem0 = s32(base) + tc * 16;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(P, item);
       const WsProblem& pr = P.p[it.q];
       const int b_vec = pr.nt * 8;                                     // 16-byte words of the B tile
-      for (int kb = 0; kb < it.n_kb; ++kb) {
+      const int zero_mod = pr.zero_mod, zero_rem = pr.zero_rem, n_kb = it.n_kb, r0 = it.r0;
+      for (int kb = 0; kb < n_kb; ++kb) {
         mbar_wait(&full_raw[stage], phase);
         if (tc == 0) WS_TR(2, 1);
-        const uint32_t a_raw = s32(base + stage * WS_STAGE_BYTES) + tc * 16, a_lo = a_raw + WS_TILE_BYTES;
+        const uint32_t a_raw = smem0 + stage * WS_STAGE_BYTES, a_lo = a_raw + WS_TILE_BYTES;
         const uint32_t b_raw = a_raw + 2 * WS_TILE_BYTES, b_lo = b_raw + WS_TILE_BYTES;
-        const int red = it.r0 + kb * WS_KB;
-        // thread tc owns the 16-byte words tc, tc + 128, ... of either tile; 8 loads in flight, then 8 stores
-        {
-          float4 v[8];
+        // thread tc owns the 16-byte words tc, tc + 128, ... of either tile; all loads in flight first, then the stores
+        float4 va[8], vb[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = lds128(a_raw + i * 2048);
-          if (pr.zero_mod > 0) {
-            // MN-major A tile: 16-byte word w lives in chunk w / 256, reduction row (w % 256) / 8
+        for (int i = 0; i < 8; ++i) va[i] = lds128(a_raw + i * 2048);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const int w = tc + i * 128;
-              const int m = red + ((w & 255) >> 3);
-              if (m % pr.zero_mod == pr.zero_rem) {
-                v[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-                sts128(a_raw + i * 2048, v[i]);
-              }
+        for (int i = 0; i < 8; ++i) vb[i] = (tc + i * 128 < b_vec) ? lds128(b_raw + i * 2048) : make_float4(0.f, 0.f, 0.f, 0.f);
+        if (zero_mod > 0) {
+          // MN-major A tile: 16-byte word w lives in chunk w / 256, reduction row (w % 256) / 8
+          const int red = r0 + kb * WS_KB;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int w = tc + i * 128;
+            const int m = red + ((w & 255) >> 3);
+            if (m % zero_mod == zero_rem) {
+              va[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+              sts128(a_raw + i * 2048, va[i]);
             }
           }
-#pragma unroll
-          for (int i = 0; i < 8; ++i) sts128(a_lo + i * 2048, lo_part(v[i]));
         }
-        for (int w0 = 0; w0 < b_vec; w0 += 512) {                       // nt = 128: two rounds, 64: one, 32: half a round
-          float4 v[4];
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (w0 + tc + i * 128 < b_vec) v[i] = lds128(b_raw + (w0 + i * 128) * 16);
+        for (int i = 0; i < 8; ++i) sts128(a_lo + i * 2048, lo_part(va[i]));
 #pragma unroll
-          for (int i = 0; i < 4; ++i) if (w0 + tc + i * 128 < b_vec) sts128(b_lo + (w0 + i * 128) * 16, lo_part(v[i]));
-        }
+        for (int i = 0; i < 8; ++i) if (tc + i * 128 < b_vec) sts128(b_lo + i * 2048, lo_part(vb[i]));
         if (tc == 0) WS_TR(2, 2);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to the tensor core
         mbar_arrive(&full_lo[stage]);
@@ -333,17 +365,25 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
   } else {
     // ===================================== epilogue (warps 0-3 <-> TMEM lane quarters) =====================================
     const uint32_t slab = s32(base + WS_STAGES * WS_STAGE_BYTES) + warp * (32 * WS_EPI_LD * 4);
+    const uint32_t slab_wr = slab + lane * (WS_EPI_LD * 4);                      // my row of the transposition slab
+    const int rsub = lane >> 3, cc = (lane & 7) * 4;
+    const uint32_t slab_rd = slab + (rsub * WS_EPI_LD + cc) * 4;                 // + i8 * 4 rows
     int acc = 0;
     uint32_t acc_phase = 0;
     for (int item = blockIdx.x; item < P.n_items; item += gridDim.x) {
       const Item it = decode(P, item);
       const WsProblem& pr = P.p[it.q];
+      float* const out = pr.out;
+      const float* const bias = pr.bias;
+      const int* const ids = pr.scatter_ids;
+      const int ldo = pr.ldo, out_rows = pr.out_rows, out_cols = pr.out_cols, nt = pr.nt, mode = pr.mode, relu = pr.relu;
+      const int row0 = it.tm * WS_M + warp * 32 + rsub, col_base = it.tn * nt + cc;
+      const bool aligned = ((((size_t)out) & 15) == 0) && ((ldo & 3) == 0) && (!bias || ((((size_t)bias) & 15) == 0));
       mbar_wait(&tmem_full[acc], acc_phase);
       if (threadIdx.x == 0) WS_TR(3, 1);
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-      const int row_base = it.tm * WS_M + warp * 32, col_base = it.tn * pr.nt;
 #pragma unroll 1
-      for (int c0 = 0; c0 < pr.nt; c0 += 32) {
+      for (int c0 = 0; c0 < nt; c0 += 32) {
         uint32_t r[32];
         const uint32_t taddr = tmem_d + ((uint32_t)(warp * 32) << 16) + (uint32_t)(acc * WS_NT_MAX + c0);
         asm volatile(
@@ -355,60 +395,61 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
               "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
               "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
             : "r"(taddr));
+        const int col = col_base + c0;
+        const bool fast = aligned && (col + 3 < out_cols);
+        float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);                   // bias: one fetch per column block, in flight with the TMEM read
+        if (mode == WS_STORE && bias && fast) bq = __ldg(reinterpret_cast<const float4*>(bias + col));
+        int orow[8];
+        if (mode == WS_SCATTER) {                                      // row targets: 8 independent loads, PAD row (id 0) skipped
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) {
+            const int row = row0 + i8 * 4;
+            const int o = (row < out_rows) ? __ldg(ids + row) : 0;
+            orow[i8] = o == 0 ? -1 : o;
+          }
+        } else {
+#pragma unroll
+          for (int i8 = 0; i8 < 8; ++i8) { const int row = row0 + i8 * 4; orow[i8] = (row < out_rows) ? row : -1; }
+        }
         asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-        if (c0 + 32 >= pr.nt) {                                        // last column block read: the accumulator may be overwritten
+        if (c0 + 32 >= nt) {                                           // last column block read: the accumulator may be overwritten
           asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
           mbar_arrive(&tmem_empty[acc]);
         }
 #pragma unroll
         for (int j = 0; j < 32; j += 4)
-          sts128(slab + (lane * WS_EPI_LD + j) * 4,
-                 make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
+          sts128(slab_wr + j * 4, make_float4(__uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3])));
         __syncwarp();
-        {
-          const int cc = (lane & 7) * 4, col = col_base + c0 + cc;
-          const bool col_ok = col < pr.out_cols, col_vec = col + 3 < pr.out_cols;
-          float4 bq = make_float4(0.f, 0.f, 0.f, 0.f);                 // one bias fetch per column block, not per row
-          if (pr.mode == WS_STORE && pr.bias && col_ok) {
-            if (col_vec && ((((size_t)(pr.bias + col)) & 15) == 0)) bq = __ldg(reinterpret_cast<const float4*>(pr.bias + col));
-            else {
-              bq.x = pr.bias[col];
-              if (col + 1 < pr.out_cols) bq.y = pr.bias[col + 1];
-              if (col + 2 < pr.out_cols) bq.z = pr.bias[col + 2];
-              if (col + 3 < pr.out_cols) bq.w = pr.bias[col + 3];
-            }
-          }
-          int orow[8];
+        if (fast) {
+          float* const dst0 = out + col;
+          if (mode == WS_STORE) {
 #pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {                             // row targets first (scatter ids: 8 independent loads)
-            const int row = row_base + i8 * 4 + (lane >> 3);
-            int o = (row < pr.out_rows && col_ok) ? row : -1;
-            if (o >= 0 && pr.mode == WS_SCATTER) {
-              o = pr.scatter_ids[row];
-              if (o == 0) o = -1;                                      // PAD row of the embedding table
-            }
-            orow[i8] = o;
-          }
-#pragma unroll
-          for (int i8 = 0; i8 < 8; ++i8) {
-            if (orow[i8] < 0) continue;
-            const int rr = i8 * 4 + (lane >> 3);
-            float4 v = lds128(slab + (rr * WS_EPI_LD + cc) * 4);
-            float* dst = pr.out + (long long)orow[i8] * pr.ldo + col;
-            const bool vec = col_vec && ((((size_t)dst) & 15) == 0);
-            if (pr.mode == WS_STORE) {
+            for (int i8 = 0; i8 < 8; ++i8) {
+              float4 v = lds128(slab_rd + i8 * (4 * WS_EPI_LD * 4));
               v.x += bq.x; v.y += bq.y; v.z += bq.z; v.w += bq.w;
-              if (pr.relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-              if (vec) *reinterpret_cast<float4*>(dst) = v;
-              else { const float t[4] = {v.x, v.y, v.z, v.w}; for (int j = 0; j < 4 && col + j < pr.out_cols; ++j) dst[j] = t[j]; }
-            } else if (pr.mode == WS_ACCUM) {
-              if (vec) { float4 o = *reinterpret_cast<const float4*>(dst); o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w; *reinterpret_cast<float4*>(dst) = o; }
-              else { const float t[4] = {v.x, v.y, v.z, v.w}; for (int j = 0; j < 4 && col + j < pr.out_cols; ++j) dst[j] += t[j]; }
-            } else {
-              if (vec) atomicAdd(reinterpret_cast<float4*>(dst), v);   // red.global.add.v4.f32
-              else { const float t[4] = {v.x, v.y, v.z, v.w}; for (int j = 0; j < 4 && col + j < pr.out_cols; ++j) atomicAdd(dst + j, t[j]); }
+              if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+              if (orow[i8] >= 0) *reinterpret_cast<float4*>(dst0 + (size_t)orow[i8] * ldo) = v;
+            }
+          } else if (mode == WS_ACCUM) {
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const float4 v = lds128(slab_rd + i8 * (4 * WS_EPI_LD * 4));
+              if (orow[i8] >= 0) {
+                float4* d4 = reinterpret_cast<float4*>(dst0 + (size_t)orow[i8] * ldo);
+                float4 o = *d4;
+                o.x += v.x; o.y += v.y; o.z += v.z; o.w += v.w;
+                *d4 = o;
+              }
+            }
+          } else {
+#pragma unroll
+            for (int i8 = 0; i8 < 8; ++i8) {
+              const float4 v = lds128(slab_rd + i8 * (4 * WS_EPI_LD * 4));
+              if (orow[i8] >= 0) atomicAdd(reinterpret_cast<float4*>(dst0 + (size_t)orow[i8] * ldo), v);   // red.global.add.v4.f32
             }
           }
+        } else if (col < out_cols) {
+          ws_epilogue_tail(slab_rd, row0, out_rows, ids, out, bias, ldo, col, out_cols, mode, relu);
         }
         __syncwarp();
         if (threadIdx.x == 0) WS_TR(3, 2);

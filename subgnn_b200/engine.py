@@ -500,7 +500,7 @@ class StepContext:
         A_pi, A_pb, A_s = eng.A['pi'], eng.A['pb'], eng.A['s']
         # gradient-side scratch that must start at zero every step lives in ONE buffer (single fill)
         n_dq = L * (B * A_pi + A_pb + 2 * A_s)
-        self.zero_scratch = z(_align(n_dq) + 8 + _align(B * hid) + _align(B * h1))
+        self.zero_scratch = z(_align(n_dq) + 8 + _align(B * hid) + _align(B * h1) + 4)
         self.dq_pi = self.zero_scratch[:L * B * A_pi]
         self.dq_pb = self.zero_scratch[L * B * A_pi:L * B * A_pi + L * A_pb]
         self.dq_s = self.zero_scratch[L * (B * A_pi + A_pb):n_dq]
@@ -518,7 +518,7 @@ class StepContext:
         self.H1 = self.fwd_zero[_align(B * hid):_align(B * hid) + B * h1].view(B, h1)
         self.H2, self.logits, self.loss_b = z(B, h2), z(B, K), z(B)
         self.dlogits, self.dH2, self.dH1, self.dZ = z(B, K), z(B, h2), z(B, h1), z(B, hid)
-        self.loss = z(1)
+        self.loss = self.fwd_zero[_align(B * hid) + _align(B * h1):_align(B * hid) + _align(B * h1) + 1]   # zeroed with Z / H1: the readout kernel adds into it
         d = ModelDesc()
         t = tables
         P = lambda x: ptr(x) if x is not None else None
@@ -555,6 +555,8 @@ class StepContext:
         d.dq_pi, d.dq_pb, d.dq_s = (self.dq_pi.data_ptr(), self.dq_pb.data_ptr(), self.dq_s.data_ptr())
         d.X0, d.Nh, d.Nagg, d.Ndpre = ptr(self.X0), ptr(self.Nh), ptr(self.Nagg), ptr(self.Ndpre)
         d.Z, d.H1, d.H2, d.logits, d.loss_b = ptr(self.Z), ptr(self.H1), ptr(self.H2), ptr(self.logits), ptr(self.loss_b)
+        d.loss_sum = self.loss.data_ptr()
+        d.mlp_fused = 0
         d.dlogits, d.dH2, d.dH1, d.dZ = ptr(self.dlogits), ptr(self.dH2), ptr(self.dH1), ptr(self.dZ)
         d.seed = eng.seed
         d.n_sub, d.n_cc, d.n_nodes = t.n_sub, t.n_cc, eng.n_nodes
@@ -567,6 +569,9 @@ class StepContext:
         d.B, d.R_cap, d.step, d.lin_dropout = B, self.R_cap, 0, float(hp['lin_dropout'])
         self.desc = d
         self.dptr = C.addressof(d)
+        # readout section as one cluster kernel (model.cu readout_cluster_kernel) where the shape allows; SUBGNN_READOUT_CLUSTER=0
+        # keeps the three batch-level MLP kernels + the loss reduction for A/B runs
+        self.readout_cluster = _flag('SUBGNN_READOUT_CLUSTER', hp.get('b200_readout_cluster', True)) and bool(_abi.lib.subgnn_model_readout_supported(self.dptr))
         self.graph = None
         self.generation = 0          # forwards run on this context (an autograd backward checks it reads its own forward's buffers)
 
@@ -774,8 +779,11 @@ class Engine:
             main.wait_stream(side)
         call('subgnn_model_q_fwd_part', c.dptr, 2, st)               # structure anchors (LSTM output)
         call('subgnn_model_rows_fwd', c.dptr, 2, st)                 # P / S property-aware outputs
-        call('subgnn_model_mlp_fwd', c.dptr, st)
-        call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
+        if c.readout_cluster:
+            call('subgnn_model_readout', c.dptr, st)                 # lin -> lin2 -> lin3 -> loss (-> dZ [, MLP gradients]) in one launch
+        else:
+            call('subgnn_model_mlp_fwd', c.dptr, st)
+            call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
 
     def _backward_launches(self, c, st, external_dlogits=False):
         main = torch.cuda.current_stream()
@@ -953,8 +961,14 @@ class Engine:
 
     def _grad_launches(self, c, st):
         call('subgnn_inc_step', ptr(self.step_dev), st)
-        self._forward_launches(c, st, zero_grads=True)
-        self._backward_launches(c, st)
+        # fused step: the readout kernel's own d logits are THE gradient, so it also produces the MLP weight / bias gradients
+        # (the descriptor is copied by value at every launch: the flag is per call)
+        c.desc.mlp_fused = 1 if (c.readout_cluster and _flag('SUBGNN_READOUT_FUSED_WGRAD', self.hp.get('b200_readout_fused_wgrad', False))) else 0
+        try:
+            self._forward_launches(c, st, zero_grads=True)
+            self._backward_launches(c, st)
+        finally:
+            c.desc.mlp_fused = 0
 
     def _step_launches(self, c, st):
         self._grad_launches(c, st)

@@ -2,7 +2,8 @@
 a few hundred subgraphs) of all five BASELINE.json configurations with their REAL hyper-parameters
 (best_model_hyperparameters/*/ as inlined in subgnn_b200/synth.py: D, L, anchor counts, walks, LSTM depth, batch size), so that
 the kernel template instantiations the bench times are the ones compared with the CPU oracle:
-row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the tcgen05 projection GEMMs at M = n_seq * T.
+row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the TMA-fed grouped tcgen05 GEMM (tc_gemm_ws_kernel) at M = n_seq * T, the
+cluster readout kernel.
 Dropout is 0 (its law is tested in test_gpu_dropout_law.py); tolerance fp32 rtol 1e-4 / atol 1e-5 (stated, as test_gpu_model.py).
 Reference path: SubGNN.py:225-348 forward / training_step, :1156-1164 Adam, Lightning clip_grad_norm_."""
 import numpy as np
@@ -13,14 +14,14 @@ pytestmark = pytest.mark.gpu
 
 # name -> (reduced base graph, n_sub, kernel instantiations that must have been launched)
 SHAPES = {
-    'density': (('ba', 1200, 5), 100, ['row_fwd_kernel<1>', 'row_bwd_kernel<1>', 'lstm_fwd_tile_kernel<1,4,32>', 'lstm_bwd_tile_kernel<1,4,32>']),
-    'cutratio': (('ba', 1200, 5), 200, ['lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>', 'tc_linear_fwd_kernel', 'tc_linear_bwd_weight_kernel']),
+    'density': (('ba', 1200, 5), 100, ['row_fwd_kernel<1>', 'row_bwd_kernel<1>', 'lstm_fwd_tile_kernel<1,4,32>', 'lstm_bwd_tile_kernel<1,4,32>', 'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
+    'cutratio': (('ba', 1200, 5), 200, ['lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>', 'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
     'ppi_bp': (('ba', 1500, 19), 60, ['row_fwd_kernel<2>', 'row_bwd_kernel<2>', 'lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>',
-                                      'tc_linear_fwd_kernel', 'tc_linear_bwd_input_kernel', 'tc_linear_bwd_weight_kernel']),
+                                      'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
     'hpo_metab': (('ba', 1500, 60), 100, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
-                                          'tc_linear_fwd_kernel', 'tc_linear_bwd_input_kernel', 'tc_linear_bwd_weight_kernel']),
+                                          'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
     'em_user': (('ba', 2000, 40), 48, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
-                                       'tc_linear_fwd_kernel', 'tc_linear_bwd_weight_kernel']),
+                                       'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
 }
 
 

@@ -94,7 +94,8 @@ def test_dense_calls_run_on_the_tma_kernel():
     _call('subgnn_tc_linear_fwd', x, 64, None, w, 64, None, y, 512, 300, 512, 64, 0)
     torch.cuda.synchronize()
     assert 'tc_gemm_ws_kernel<1>' in _abi.variant_log()
-    np.testing.assert_allclose(y.cpu().numpy(), x.cpu().double().numpy() @ w.cpu().double().numpy().T, rtol=0, atol=5e-5)
+    want = x.cpu().double().numpy() @ w.cpu().double().numpy().T
+    assert np.abs(y.cpu().numpy() - want).max() / np.abs(want).max() < 4e-6
 
 
 @pytest.mark.parametrize('n_seq,T,H', [(37, 10, 64), (1000, 10, 64), (50, 23, 128), (9, 5, 32), (3, 1, 32)])
