@@ -668,10 +668,27 @@ __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
 //   3  dZ[b][slice] = dH1[b] . W1[:, slice];   mlp_fused: dW1[:, slice] += dH1^T Z[:, slice]
 // (first version: 32 samples per cluster, i.e. 8 CTAs at the reference batch of 32 — 45 us against 30 us for the three
 // batch-level kernels: too few SMs for the 0.45 MB of W1; one sample per CTA puts B CTAs on the section)
+#ifdef WS_TRACE
+__device__ long long ro_trace_buf[64];
+#define RO_TR(i) do { if (blockIdx.x == 0 && threadIdx.x == 0) ro_trace_buf[i] = clock64(); } while (0)
+extern "C" int subgnn_ro_trace_read(long long* host_buf) { cudaDeviceSynchronize(); return (int)cudaMemcpyFromSymbol(host_buf, ro_trace_buf, sizeof(long long) * 64); }
+#else
+#define RO_TR(i) do { } while (0)
+#endif
 #define RO_CL 8
 #define RO_BT 8
 #define RO_THREADS 256
 #define RO_IQ 4            // phase 1: the slice is cut in RO_IQ quarters over thread groups
+
+// 1-D TMA bulk copy global -> shared completing on an mbarrier (one issuing thread); chunks of <= 32 KB
+__device__ __forceinline__ void ro_bulk_copy(float* dst, const float* src, uint32_t bytes, uint64_t* bar) {
+  for (uint32_t off = 0; off < bytes; off += 32768u) {
+    const uint32_t n = bytes - off < 32768u ? bytes - off : 32768u;
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"((uint32_t)__cvta_generic_to_shared(reinterpret_cast<const char*>(dst) + off)), "l"(reinterpret_cast<const char*>(src) + off), "r"(n),
+                    "r"((uint32_t)__cvta_generic_to_shared(bar)) : "memory");
+  }
+}
 
 struct RoSmem {
   float *w1t, *zs, *w2t, *w2n, *recv, *gall, *part, *h1s, *h2s, *g2s, *g1s, *lgs, *dls, *bs, *w3s;
@@ -680,18 +697,21 @@ struct RoSmem {
 __host__ __device__ inline int ro_slice(int hid) { return ((hid + RO_CL - 1) / RO_CL + 3) / 4 * 4; }
 __host__ __device__ inline size_t ro_smem_floats(int hid, int h1, int h2, int K) {
   const int S = ro_slice(hid);
-  return (size_t)S * (h1 + 1) + (size_t)RO_BT * S + 2 * (size_t)h1 * h2 + (size_t)RO_CL * h1 + (size_t)h1 * RO_BT + (size_t)RO_IQ * RO_BT * h1 +
+  const size_t w2 = ((size_t)h1 * h2 + 3) / 4 * 4;
+  return (size_t)S * h1 + 2 * w2 + (size_t)RO_BT * S + (size_t)h1 * RO_BT + (size_t)RO_CL * h1 + (size_t)RO_IQ * RO_BT * h1 +
          (size_t)(2 * h1 + 2 * h2 + 2 * K) + (size_t)(h1 + h2 + K + K * h2) + 32;
 }
 __device__ __forceinline__ RoSmem ro_carve(float* sm, const Desc& d) {
   RoSmem r;
   r.S = ro_slice(d.hid);
-  r.ld1 = d.h1 + 1;
-  r.zs = sm;                                              // [RO_BT][S]      (16-byte aligned rows: S % 4 == 0)
+  r.ld1 = d.h1;
+  const size_t w2 = ((size_t)d.h1 * d.h2 + 3) / 4 * 4;
+  r.w1t = sm;                                             // [S][h1]         W1^T slice (bulk-copy destination: 16-byte aligned)
+  r.w2t = r.w1t + (size_t)r.S * d.h1;                     // [h1][h2]        (S % 4 == 0 keeps the alignment)
+  r.w2n = r.w2t + w2;                                     // [h2][h1]
+  r.zs = r.w2n + w2;                                      // [RO_BT][S]      (16-byte aligned rows: S % 4 == 0)
   r.gall = r.zs + (size_t)RO_BT * r.S;                    // [h1][RO_BT]     dH1 of the cluster's samples, sample index contiguous
-  r.w2t = r.gall + (size_t)d.h1 * RO_BT;                  // [h1][h2]
-  r.w2n = r.w2t + (size_t)d.h1 * d.h2;                    // [h2][h1]
-  r.recv = r.w2n + (size_t)d.h1 * d.h2;                   // [RO_CL][h1]     partial first-layer sums of MY sample from every CTA
+  r.recv = r.gall + (size_t)d.h1 * RO_BT;                 // [RO_CL][h1]     partial first-layer sums of MY sample from every CTA
   r.part = r.recv + (size_t)RO_CL * d.h1;                 // [RO_IQ][RO_BT][h1]
   r.h1s = r.part + (size_t)RO_IQ * RO_BT * d.h1;          // [h1]
   r.g1s = r.h1s + d.h1;                                   // [h1]
@@ -701,7 +721,6 @@ __device__ __forceinline__ RoSmem ro_carve(float* sm, const Desc& d) {
   r.dls = r.lgs + d.n_classes;                            // [K]
   r.bs = r.dls + d.n_classes;                             // [h1 + h2 + K]   the three bias vectors
   r.w3s = r.bs + d.h1 + d.h2 + d.n_classes;               // [K][h2]         lin3 weights
-  r.w1t = r.w3s + (size_t)d.n_classes * d.h2;             // [S][h1 + 1]     W1^T slice, rows padded by one float (conflict-free both ways)
   return r;
 }
 
@@ -715,32 +734,30 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
   const int S = R.S, ld1 = R.ld1, h1 = d.h1, h2 = d.h2, K = d.n_classes;
   const int i0 = (int)rank * S, Sr = max(0, min(S, d.hid - i0));      // my columns [i0, i0 + Sr)
   const bool bwd = d.training && d.dZ;
-  // ---- weights: staged before the dependency wait (parameters / derived copies whose producers never trigger early) ----
+  RO_TR(0);
+  // ---- weights: staged before the dependency wait (parameters / derived copies whose producers never trigger early): the W1^T
+  // slice (contiguous rows i0 .. of the transposed copy, ~56 KB) and both orientations of W2 arrive by 1-D TMA bulk copies ----
+  __shared__ uint64_t wbar;
   {
-    const float* wt = d.lin_wt[0] + (size_t)i0 * h1;                  // W1^T rows i0 .. : contiguous, 16-byte aligned when h1 % 4 == 0
-    const bool v4 = (h1 % 4) == 0 && ((((size_t)wt) & 15) == 0);
-    if (v4) {
-      const int n4 = S * h1 / 4, nv = Sr * h1 / 4;
-      for (int e0 = tid; e0 < n4; e0 += 8 * RO_THREADS) {
-        float4 r8[8];
-#pragma unroll
-        for (int u = 0; u < 8; ++u) { const int e = e0 + u * RO_THREADS; r8[u] = (e < nv) ? __ldg(reinterpret_cast<const float4*>(wt) + e) : make_float4(0.f, 0.f, 0.f, 0.f); }
-#pragma unroll
-        for (int u = 0; u < 8; ++u) {
-          const int e = e0 + u * RO_THREADS;
-          if (e < n4) {
-            float* dst = R.w1t + ((4 * e) / h1) * ld1 + ((4 * e) % h1);
-            dst[0] = r8[u].x; dst[1] = r8[u].y; dst[2] = r8[u].z; dst[3] = r8[u].w;
-          }
-        }
-      }
-    } else {
-      for (int e = tid; e < S * h1; e += RO_THREADS) R.w1t[(e / h1) * ld1 + (e % h1)] = (e < Sr * h1) ? __ldg(wt + e) : 0.f;
-    }
-    const float* src_t = d.lin_wt[1];
-    const float* src_n = d.lin_w[1];
+    const float* wt = d.lin_wt[0] + (size_t)i0 * h1;
     const int nw = h1 * h2;
-    sg_stage<8>(R.w2t, bwd ? 2 * nw : nw, [&](int e) { return e < nw ? __ldg(src_t + e) : __ldg(src_n + e - nw); });
+    const bool bulk = (h1 % 4) == 0 && (nw % 4) == 0 && ((((size_t)wt) | ((size_t)d.lin_wt[1]) | ((size_t)d.lin_w[1])) & 15) == 0;
+    if (tid == 0) {
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"((uint32_t)__cvta_generic_to_shared(&wbar)) : "memory");
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+      const uint32_t bytes = bulk ? (uint32_t)(((size_t)Sr * h1 + (bwd ? 2 : 1) * (size_t)nw) * sizeof(float)) : 0u;
+      asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"((uint32_t)__cvta_generic_to_shared(&wbar)), "r"(bytes) : "memory");
+      if (bulk) {
+        if (Sr > 0) ro_bulk_copy(R.w1t, wt, (uint32_t)((size_t)Sr * h1 * sizeof(float)), &wbar);
+        ro_bulk_copy(R.w2t, d.lin_wt[1], (uint32_t)(nw * sizeof(float)), &wbar);
+        if (bwd) ro_bulk_copy(R.w2n, d.lin_w[1], (uint32_t)(nw * sizeof(float)), &wbar);
+      }
+    }
+    for (int e = Sr * h1 + tid; e < S * h1; e += RO_THREADS) R.w1t[e] = 0.f;          // rows beyond the matrix (last slice)
+    if (!bulk) {
+      for (int e = tid; e < Sr * h1; e += RO_THREADS) R.w1t[e] = __ldg(wt + e);
+      for (int e = tid; e < nw; e += RO_THREADS) { R.w2t[e] = __ldg(d.lin_wt[1] + e); if (bwd) R.w2n[e] = __ldg(d.lin_w[1] + e); }
+    }
     // everything the chain behind the first layer reads from global memory — biases, lin3 weights, the label — is fetched here,
     // before the wait: that chain is ~8 dependent phases and each L2 round trip inside it costs ~1 us of the step's critical path
     sg_stage<8>(R.bs, h1 + h2 + K + K * h2, [&](int e) {
@@ -754,7 +771,9 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
   const int my_b = blockIdx.x / RO_CL * RO_BT + (int)rank;
   int my_label = 0;
   if (tid == 0 && my_b < d.B && !d.multilabel && d.labels) my_label = d.labels[d.batch_idx[my_b]];
+  RO_TR(1);
   sg_pdl_sync();
+  RO_TR(2);
   // ---- Z slice ----
   {
     const bool v4 = (d.hid % 4) == 0 && ((((size_t)d.Z) & 15) == 0);    // i0 and S are multiples of 4
@@ -778,6 +797,13 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
     }
   }
   __syncthreads();
+  {                                                                    // bulk copies landed (phase 0 of the barrier)
+    const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&wbar);
+    uint32_t done = 0;
+    while (!done)
+      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n\tselp.u32 %0, 1, 0, p;\n\t}\n" : "=r"(done) : "r"(bar) : "memory");
+  }
+  RO_TR(3);
   // ---- 1: partial first-layer sums of my slice: work item = (unit j, quarter q of the slice), all RO_BT samples ----
   {
     const int S4q = ((S / 4 + RO_IQ - 1) / RO_IQ) * 4;                 // columns per quarter (multiple of 4)
@@ -787,6 +813,7 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
       float acc[RO_BT];
 #pragma unroll
       for (int u = 0; u < RO_BT; ++u) acc[u] = 0.f;
+#pragma unroll 2
       for (int i = ia; i < ib; i += 4) {
         const float w0 = R.w1t[(i + 0) * ld1 + j], w1 = R.w1t[(i + 1) * ld1 + j], w2 = R.w1t[(i + 2) * ld1 + j], w3 = R.w1t[(i + 3) * ld1 + j];
 #pragma unroll
@@ -807,7 +834,9 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
       sg_st_cluster(R.recv + (size_t)rank * h1 + j, (unsigned)b, v);
     }
   }
+  RO_TR(4);
   sg_cluster_sync();
+  RO_TR(5);
   // ---- 2: my sample behind the first layer ----
   const int b = b0 + (int)rank;                                        // the sample I own
   const bool live = b < d.B;
@@ -873,6 +902,7 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
   }
   if (!bwd) return;                                                     // (uniform over the cluster: no CTA waits at barrier 2)
   __syncthreads();
+  RO_TR(6);
   for (int j = tid; j < h2; j += RO_THREADS) {
     float acc = 0.f;
     for (int c = 0; c < K; ++c) acc = fmaf(R.dls[c], R.w3s[c * h2 + j], acc);
@@ -909,15 +939,17 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
       else if (R.dls[o - h1 - h2] != 0.f) atomicAdd(d.lin_gb[2] + o - h1 - h2, R.dls[o - h1 - h2]);
     }
   }
+  RO_TR(7);
   sg_cluster_sync();                                                    // gall complete in every CTA
-  // ---- 3: dZ and dW1 of my slice: thread = column i of the slice ----
+  RO_TR(8);
+  // ---- 3: dZ and dW1 of my slice: warp = column i of the slice, lanes over the h1 units (rows of the unpadded W1^T slice are read
+  // contiguously: conflict free), the RO_BT per-sample sums reduced with shuffles ----
   const bool wgrad = d.mlp_fused && d.lin_gw[0];
-  for (int i = tid; i < Sr; i += RO_THREADS) {
-    float acc[RO_BT], zr[RO_BT];
+  for (int i = warp; i < Sr; i += RO_THREADS / 32) {
+    float acc[RO_BT];
 #pragma unroll
-    for (int u = 0; u < RO_BT; ++u) { acc[u] = 0.f; zr[u] = R.zs[(size_t)u * S + i]; }
-    float* gw = wgrad ? d.lin_gw[0] + i0 + i : nullptr;
-    for (int j = 0; j < h1; ++j) {
+    for (int u = 0; u < RO_BT; ++u) acc[u] = 0.f;
+    for (int j = lane; j < h1; j += 32) {
       const float w = R.w1t[i * ld1 + j];
       const float4* g4 = reinterpret_cast<const float4*>(R.gall + (size_t)j * RO_BT);
       float dw = 0.f;
@@ -926,14 +958,24 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
         const float4 g = g4[q];
         acc[4 * q + 0] = fmaf(g.x, w, acc[4 * q + 0]); acc[4 * q + 1] = fmaf(g.y, w, acc[4 * q + 1]);
         acc[4 * q + 2] = fmaf(g.z, w, acc[4 * q + 2]); acc[4 * q + 3] = fmaf(g.w, w, acc[4 * q + 3]);
-        dw = fmaf(g.x, zr[4 * q + 0], fmaf(g.y, zr[4 * q + 1], fmaf(g.z, zr[4 * q + 2], fmaf(g.w, zr[4 * q + 3], dw))));
+        if (wgrad) {
+          const float4 z = make_float4(R.zs[(size_t)(4 * q + 0) * S + i], R.zs[(size_t)(4 * q + 1) * S + i], R.zs[(size_t)(4 * q + 2) * S + i],
+                                       R.zs[(size_t)(4 * q + 3) * S + i]);
+          dw = fmaf(g.x, z.x, fmaf(g.y, z.y, fmaf(g.z, z.z, fmaf(g.w, z.w, dw))));
+        }
       }
-      if (wgrad && dw != 0.f) atomicAdd(gw + (size_t)j * d.hid, dw);
+      if (wgrad && dw != 0.f) atomicAdd(d.lin_gw[0] + (size_t)j * d.hid + i0 + i, dw);
     }
 #pragma unroll
-    for (int u = 0; u < RO_BT; ++u)
-      if (u < bn) d.dZ[(size_t)(b0 + u) * d.hid + i0 + i] = acc[u];
+    for (int u = 0; u < RO_BT; ++u) acc[u] = warp_sum(acc[u]);
+    if (lane < bn) {
+      float v = acc[0];
+#pragma unroll
+      for (int u = 1; u < RO_BT; ++u) v = lane == u ? acc[u] : v;
+      d.dZ[(size_t)(b0 + lane) * d.hid + i0 + i] = v;
+    }
   }
+  RO_TR(9);
 }
 
 template <int DPL>

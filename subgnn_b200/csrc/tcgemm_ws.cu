@@ -269,11 +269,15 @@ __global__ void __launch_bounds__(WS_THREADS, 1) tc_gemm_ws_kernel(const __grid_
           mbar_arrive_expect_tx(&full_raw[stage], bytes);
           const int red = r0 + kb * WS_KB;
           if (!a_mn) tma_load_2d(tmA, &full_raw[stage], a_raw, red, a_row0);
-          else
+          else {
+#pragma unroll 1
             for (int c = 0; c < a_chunks; ++c) tma_load_2d(tmA, &full_raw[stage], a_raw + c * 4096, a_row0 + 32 * c, red);
+          }
           if (!b_mn) tma_load_2d(tmB, &full_raw[stage], b_raw, red, b_row0);
-          else
+          else {
+#pragma unroll 1
             for (int c = 0; c < b_chunks; ++c) tma_load_2d(tmB, &full_raw[stage], b_raw + c * 4096, b_row0 + 32 * c, red + b_shift);
+          }
           if (++stage == WS_STAGES) { stage = 0; phase ^= 1u; }
         }
       }

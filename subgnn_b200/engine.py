@@ -569,9 +569,13 @@ class StepContext:
         d.B, d.R_cap, d.step, d.lin_dropout = B, self.R_cap, 0, float(hp['lin_dropout'])
         self.desc = d
         self.dptr = C.addressof(d)
-        # readout section as one cluster kernel (model.cu readout_cluster_kernel) where the shape allows; SUBGNN_READOUT_CLUSTER=0
-        # keeps the three batch-level MLP kernels + the loss reduction for A/B runs
-        self.readout_cluster = _flag('SUBGNN_READOUT_CLUSTER', hp.get('b200_readout_cluster', True)) and bool(_abi.lib.subgnn_model_readout_supported(self.dptr))
+        # readout section as one cluster kernel (model.cu readout_cluster_kernel): measured on B200 at the PPI-BP shape (same box,
+        # 100 steps): 0.3372 ms/step with the three batch-level MLP kernels, 0.3365 (first-layer slices staged by threads, dZ per thread)
+        # ... 0.3498 (bulk-copy staging, warp-per-column dZ) with the cluster kernel, 0.3429 when it also produces the MLP weight
+        # gradients (atomics on the critical chain) — no gain: a single-shot kernel of ~10 dependent phases is bound by instruction
+        # fetch and L2 round trips, not by the work.  It stays an opt-in (SUBGNN_READOUT_CLUSTER=1 / hp['b200_readout_cluster']),
+        # parity-tested like the default path.
+        self.readout_cluster = _flag('SUBGNN_READOUT_CLUSTER', hp.get('b200_readout_cluster', False)) and bool(_abi.lib.subgnn_model_readout_supported(self.dptr))
         self.graph = None
         self.generation = 0          # forwards run on this context (an autograd backward checks it reads its own forward's buffers)
 

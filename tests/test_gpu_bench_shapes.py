@@ -2,8 +2,8 @@
 a few hundred subgraphs) of all five BASELINE.json configurations with their REAL hyper-parameters
 (best_model_hyperparameters/*/ as inlined in subgnn_b200/synth.py: D, L, anchor counts, walks, LSTM depth, batch size), so that
 the kernel template instantiations the bench times are the ones compared with the CPU oracle:
-row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the TMA-fed grouped tcgen05 GEMM (tc_gemm_ws_kernel) at M = n_seq * T, the
-cluster readout kernel.
+row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the TMA-fed grouped tcgen05 GEMM (tc_gemm_ws_kernel) at M = n_seq * T;
+the opt-in cluster readout kernel is run over the same shapes by the second test.
 Dropout is 0 (its law is tested in test_gpu_dropout_law.py); tolerance fp32 rtol 1e-4 / atol 1e-5 (stated, as test_gpu_model.py).
 Reference path: SubGNN.py:225-348 forward / training_step, :1156-1164 Adam, Lightning clip_grad_norm_."""
 import numpy as np
@@ -14,14 +14,14 @@ pytestmark = pytest.mark.gpu
 
 # name -> (reduced base graph, n_sub, kernel instantiations that must have been launched)
 SHAPES = {
-    'density': (('ba', 1200, 5), 100, ['row_fwd_kernel<1>', 'row_bwd_kernel<1>', 'lstm_fwd_tile_kernel<1,4,32>', 'lstm_bwd_tile_kernel<1,4,32>', 'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
-    'cutratio': (('ba', 1200, 5), 200, ['lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>', 'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
+    'density': (('ba', 1200, 5), 100, ['row_fwd_kernel<1>', 'row_bwd_kernel<1>', 'lstm_fwd_tile_kernel<1,4,32>', 'lstm_bwd_tile_kernel<1,4,32>', 'tc_gemm_ws_kernel']),
+    'cutratio': (('ba', 1200, 5), 200, ['lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>', 'tc_gemm_ws_kernel']),
     'ppi_bp': (('ba', 1500, 19), 60, ['row_fwd_kernel<2>', 'row_bwd_kernel<2>', 'lstm_fwd_tile_kernel<1,4,64>', 'lstm_bwd_tile_kernel<1,4,64>',
-                                      'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
+                                      'tc_gemm_ws_kernel']),
     'hpo_metab': (('ba', 1500, 60), 100, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
-                                          'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
+                                          'tc_gemm_ws_kernel']),
     'em_user': (('ba', 2000, 40), 48, ['row_fwd_kernel<4>', 'row_bwd_kernel<4>', 'lstm_fwd_tile_kernel<2,2,128>', 'lstm_bwd_tile_kernel<2,1,128>',
-                                       'tc_gemm_ws_kernel', 'readout_cluster_kernel']),
+                                       'tc_gemm_ws_kernel']),
 }
 
 
@@ -87,3 +87,30 @@ def test_engine_step_matches_oracle_at_benchmark_shape(name):
     launched = _abi.variant_log()
     for want in SHAPES[name][2]:
         assert any(v.startswith(want) for v in launched), '%s not launched; saw %s' % (want, sorted(launched))
+
+
+@pytest.mark.parametrize('name', ['density', 'ppi_bp', 'em_user'])
+def test_cluster_readout_kernel_matches_default_path(name, monkeypatch):
+    """the opt-in readout section as one cluster kernel (SUBGNN_READOUT_CLUSTER=1, DSMEM exchange of the first-layer partial sums;
+    with and without its fused MLP weight gradients) takes the same steps as the default three-kernel path: SubGNN.py:303-310, :338-342"""
+    from subgnn_b200 import _abi
+    from subgnn_b200.engine import Engine
+    hp, g, p = build(name)
+    n, B = len(p['labels']['train']), hp['batch_size']
+    rs = np.random.RandomState(2)
+    batches = [np.sort(rs.choice(n, size=B, replace=False)) for _ in range(3)]
+    states = []
+    for cluster, fused in (('0', '0'), ('1', '0'), ('1', '1')):
+        monkeypatch.setenv('SUBGNN_READOUT_CLUSTER', cluster)
+        monkeypatch.setenv('SUBGNN_READOUT_FUSED_WGRAD', fused)
+        _abi.variant_log(reset=True)
+        eng = Engine(hp, p, device='cuda', graph=g, seed=5)
+        eng.init_parameters(3)
+        losses = [float(eng.train_step(b, use_graph=(i > 0)).item()) for i, b in enumerate(batches)]
+        torch.cuda.synchronize()
+        assert ('readout_cluster_kernel' in _abi.variant_log()) == (cluster == '1')
+        states.append((losses, {k: v.cpu().numpy().copy() for k, v in eng.arena.state_dict().items()}))
+    for losses, sd in states[1:]:
+        np.testing.assert_allclose(losses, states[0][0], rtol=1e-5)
+        for k in sd:
+            np.testing.assert_allclose(sd[k], states[0][1][k], rtol=1e-4, atol=1e-6, err_msg=k)
