@@ -436,16 +436,16 @@ def measure(job, workload, K, W, batch_override=0, strong=False, detail=True, e2
             prof.setdefault(name, []).append((a, b))
 
         n_prof = min(K, 10)
-        ws = eng.world_size
+        ws, dp = eng.world_size, eng.dp                  # rank 0 alone from here on: no exchange (its barriers would wait for the peers)
         for i in range(n_prof):
             flush.zero_()
             torch.cuda.synchronize()
             _abi._profile_hook = hook
-            eng.world_size = 1
+            eng.world_size, eng.dp = 1, None
             try:
                 eng.train_step(batches[W + 1 + i], use_graph=False)
             finally:
-                eng.world_size = ws
+                eng.world_size, eng.dp = ws, dp
                 _abi._profile_hook = None
         torch.cuda.synchronize()
         per_entry = {k: (sum(a.elapsed_time(b) for a, b in v) / n_prof, len(v) // n_prof) for k, v in prof.items()}

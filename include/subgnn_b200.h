@@ -290,7 +290,9 @@ int subgnn_model_readout_supported(const subgnn_model_desc* d);
 int subgnn_model_readout(const subgnn_model_desc* d, void* stream);
 /* per-sample MLP backward from externally supplied dlogits (autograd entry) */
 int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream);
-int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);
+int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);          /* == q_bwd_part(POS | STRUC) */
+/* backward of q = w_p . x per anchor list: SUBGNN_Q_STRUC -> d emb_s (feeds the LSTM head gradient), SUBGNN_Q_POS -> rows of dE */
+int subgnn_model_q_bwd_part(const subgnn_model_desc* d, int which, void* stream);
 /* weight gradients of the N-channel MPN projections and the MLP */
 int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream);
 
@@ -311,6 +313,20 @@ int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, 
                      const int* step_dev /* [1] step count t >= 1 */, const float* sumsq_dev, float clip_norm, float grad_scale,
                      void* stream);
 int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
+
+/* ---- data-parallel exchange fused with the optimizer (dp.cu) ------------------------------------------------------------------
+ * The gradient / parameter arenas of all ranks are symmetric allocations mapped into every process (NVLink peer memory); the
+ * pointer tables are HOST arrays of device addresses, one per rank.  Rank r owns shard r = elements [r * shard, (r + 1) * shard):
+ *   reduce_scatter: gsum[i] = sum over ranks of grads_q[r * shard + i] (fixed order); slot r of EVERY rank's `slots` array receives
+ *                   the shard's sum of squares.  Needs a cross-GPU barrier before (all gradients complete) and after.
+ *   adam_allgather: global norm from the local slots (fixed order) -> clip_grad_norm_ coefficient; Adam on the shard with the rank's
+ *                   own m / v; the new parameters are stored into shard r of every rank's parameter arena.  Barrier after.
+ * Together: the averaged-gradient Adam step of SubGNN.py:1156-1164 under data parallelism, with sharded optimizer state. */
+int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, int world, int rank, long long n,
+                             long long shard, float* gsum, void* stream);
+int subgnn_dp_adam_allgather(const unsigned long long* peer_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
+                             float* v, float lr, float beta1, float beta2, float eps, const int* step_dev, const float* slots_local,
+                             float clip_norm, float grad_scale, void* stream);
 int subgnn_inc_step(int* step_dev, void* stream);
 
 #ifdef __cplusplus

@@ -187,13 +187,19 @@ __global__ void __launch_bounds__(256) q_fwd_kernel(Desc d, int which) {
 
 // grid (blocks_per_group, L * groups); group = one (channel side) parameter block, so that d w_p is reduced
 // inside the CTA and added once per CTA.
-__global__ void __launch_bounds__(256) q_bwd_kernel(Desc d) {
+// which: SUBGNN_Q_POS / SUBGNN_Q_STRUC select the groups a launch covers (the structure groups feed the LSTM head gradient: they
+// are on the step's critical chain; the position groups only scatter into dE and run beside the BPTT chain)
+__global__ void __launch_bounds__(256) q_bwd_kernel(Desc d, int which) {
   sg_pdl_sync();
   __shared__ float s_dwp[8][256];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int groups = (d.use_p ? 2 : 0) + (d.use_s ? 2 : 0);
   const int l = blockIdx.y / groups;
   int grp = blockIdx.y % groups;
+  {
+    const bool is_pos = d.use_p && grp < 2;
+    if (is_pos ? !(which & SUBGNN_Q_POS) : !(which & SUBGNN_Q_STRUC)) return;
+  }
   int e_beg, e_cnt;
   const int pi = d.B * d.A_pi;
   if (d.use_p && grp == 0) { e_beg = 0; e_cnt = pi; }
@@ -1318,21 +1324,27 @@ int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) 
   return subgnn_check_launch("row_bwd_kernel");
 }
 
-int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_q_bwd_part(const subgnn_model_desc* d, int which, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
+  if (!d->use_p) which &= ~SUBGNN_Q_POS;
+  if (!d->use_s) which &= ~SUBGNN_Q_STRUC;
   const int groups = (d->use_p ? 2 : 0) + (d->use_s ? 2 : 0);
-  if (groups == 0) return SUBGNN_OK;
-  // grid.x sized for the largest group (the B * A_pi position-internal entries): ~2-3 entries per warp keeps the dependent
-  // id -> row -> atomics chains short; CTAs of the small groups retire immediately
-  int max_cnt = d->use_p ? (d->B * d->A_pi > d->A_pb ? d->B * d->A_pi : d->A_pb) : d->A_s;
-  if (d->use_s && d->A_s > max_cnt) max_cnt = d->A_s;
+  if (groups == 0 || !which) return SUBGNN_OK;
+  // grid.x sized for the largest group of the launch (the B * A_pi position-internal entries): ~2-3 entries per warp keeps the
+  // dependent id -> row -> atomics chains short; CTAs of the small / unselected groups retire immediately
+  int max_cnt = 0;
+  if (which & SUBGNN_Q_POS) max_cnt = d->B * d->A_pi > d->A_pb ? d->B * d->A_pi : d->A_pb;
+  if ((which & SUBGNN_Q_STRUC) && d->A_s > max_cnt) max_cnt = d->A_s;
   int gx = sg_div_up(max_cnt, 24);
   gx = gx < 8 ? 8 : (gx > 96 ? 96 : gx);
   dim3 grid(gx, d->L * groups);
-  sg_launch_pdl<SG_PDL_CHAIN>(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d);
+  if (which & SUBGNN_Q_STRUC) sg_launch_pdl<SG_PDL_CHAIN>(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d, which);
+  else sg_launch_pdl(q_bwd_kernel, grid, dim3(256), 0, (cudaStream_t)stream, *d, which);
   return subgnn_check_launch("q_bwd_kernel");
 }
+
+int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream) { return subgnn_model_q_bwd_part(d, SUBGNN_Q_POS | SUBGNN_Q_STRUC, stream); }
 
 int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);

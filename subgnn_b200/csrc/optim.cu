@@ -17,6 +17,12 @@ __global__ void fill_zero_kernel(float4* __restrict__ p4, long long n4, float* _
   if (blockIdx.x == 0 && threadIdx.x < ntail) tail[threadIdx.x] = 0.f;
 }
 
+// Deterministic: every block writes its partial sum, the LAST block to finish (ticket) adds the partials in a fixed order.  The result
+// feeds the clip coefficient of every parameter, so an order-dependent sum (float atomics) lets data-parallel ranks — which hold
+// bit-identical all-reduced gradients — drift apart by a few ulps per step.
+#define SUMSQ_MAX_BLOCKS 2048
+__device__ float sg_sumsq_part[SUMSQ_MAX_BLOCKS];
+__device__ unsigned sg_sumsq_ticket = 0;
 __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g, long long n, float* __restrict__ out) {
   sg_pdl_sync();
   float s = 0.f;
@@ -29,13 +35,32 @@ __global__ void __launch_bounds__(256) sumsq_kernel(const float* __restrict__ g,
   if (blockIdx.x == 0)
     for (long long i = n4 * 4 + threadIdx.x; i < n; i += blockDim.x) s = fmaf(g[i], g[i], s);
   __shared__ float ws[8];
+  __shared__ bool last;
   s = warp_sum(s);
   if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = s;
   __syncthreads();
-  if (threadIdx.x < 32) {
-    float t = threadIdx.x < 8 ? ws[threadIdx.x] : 0.f;
-    t = warp_sum(t);
-    if (threadIdx.x == 0) atomicAdd(out, t);
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) t += ws[w];
+    sg_sumsq_part[blockIdx.x] = t;
+    __threadfence();
+    last = atomicAdd(&sg_sumsq_ticket, 1u) == gridDim.x - 1;
+  }
+  __syncthreads();
+  if (!last) return;
+  __threadfence();
+  float t = 0.f;
+  for (unsigned i = threadIdx.x; i < gridDim.x; i += 256) t += __ldcg(sg_sumsq_part + i);      // fixed assignment, fixed order
+  t = warp_sum(t);
+  if ((threadIdx.x & 31) == 0) ws[threadIdx.x >> 5] = t;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float tot = 0.f;
+#pragma unroll
+    for (int w = 0; w < 8; ++w) tot += ws[w];
+    *out += tot;
+    sg_sumsq_ticket = 0;                                      // ready for the next launch (launches of this kernel are stream ordered)
   }
 }
 
@@ -105,7 +130,9 @@ int subgnn_fill_zero(float* p, long long n, void* stream) {
 int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq, void* stream) {
   if (n <= 0) return SUBGNN_OK;
   SG_REQUIRE(((size_t)g & 15) == 0, "buffer must be 16-byte aligned");
-  sg_launch_pdl<SG_PDL_CHAIN>(sumsq_kernel, dim3(sg_grid_for(n / 4 + 1, 256, 4)), dim3(256), 0, (cudaStream_t)stream, g, n, out_sumsq);
+  int grid = sg_grid_for(n / 4 + 1, 256, 4);
+  if (grid > SUMSQ_MAX_BLOCKS) grid = SUMSQ_MAX_BLOCKS;
+  sg_launch_pdl<SG_PDL_CHAIN>(sumsq_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g, n, out_sumsq);
   return subgnn_check_launch("sumsq_kernel");
 }
 

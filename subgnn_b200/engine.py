@@ -15,6 +15,7 @@ Data layout in HBM:
 import ctypes as C
 import os
 import math
+import sys
 
 import numpy as np
 import torch
@@ -41,7 +42,7 @@ class ParamArena:
     """Flat fp32 storage for every trainable tensor, laid out for the kernels (see header comment of
     subgnn_model_desc) and exposed under the reference's state_dict names."""
 
-    def __init__(self, hp, n_nodes, num_classes, hid_dim, n_train=0, C_pad=0, device='cuda'):
+    def __init__(self, hp, n_nodes, num_classes, hid_dim, n_train=0, C_pad=0, device='cuda', alloc=None):
         D, L = hp['node_embed_size'], hp['n_layers']
         self.D, self.L = D, L
         self.device = torch.device(device)
@@ -102,7 +103,9 @@ class ParamArena:
                 add('train_%s_cc_embed' % nm, (n_train, C_pad, D)); pad()
         self.size = _align(off)
         z = lambda: torch.zeros(self.size, dtype=torch.float32, device=self.device)
-        self.params, self.grads, self.m, self.v = z(), z(), z(), z()
+        # alloc: allocator of the two arenas that peers map (data-parallel exchange over NVLink peer memory, DpExchange)
+        zs = (lambda: alloc(self.size).zero_()) if alloc is not None else z
+        self.params, self.grads, self.m, self.v = zs(), zs(), z(), z()
 
     def view(self, name, which='params'):
         off, shape = self.entries[name]
@@ -477,6 +480,61 @@ class LstmRunner:
 
 
 # ------------------------------------------------------------------------------------------------------
+class DpExchange:
+    """Gradient exchange + optimizer over NVLink peer memory (csrc/dp.cu): symmetric gradient / parameter arenas
+    (torch.distributed._symmetric_memory maps every peer's allocation into this process), reduce-scatter of the gradient shards by
+    direct peer loads, sharded Adam, all-gather of the updated parameters by direct peer stores, cross-GPU barriers on the signal
+    pads in between.  Replaces the NCCL all-reduce + two optimizer kernels of the data-parallel step."""
+
+    @staticmethod
+    def allocator(device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        try:
+            symm.enable_symm_mem_for_group(dist.group.WORLD.group_name)
+        except Exception:
+            pass
+        return lambda n: symm.empty(n, dtype=torch.float32, device=torch.device(device))
+
+    def __init__(self, arena, world, rank, device):
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm
+        self.world, self.rank = world, rank
+        self.n = arena.size
+        self.shard = _align((self.n + world - 1) // world)
+        self.slots = symm.empty(max(world, 4), dtype=torch.float32, device=torch.device(device)).zero_()
+        group = dist.group.WORLD
+        self.h_g, self.h_p, self.h_s = symm.rendezvous(arena.grads, group), symm.rendezvous(arena.params, group), symm.rendezvous(self.slots, group)
+        assert int(self.h_g.buffer_ptrs[rank]) == arena.grads.data_ptr() and int(self.h_p.buffer_ptrs[rank]) == arena.params.data_ptr()
+        tab = lambda h: (C.c_ulonglong * world)(*[int(x) for x in h.buffer_ptrs])
+        self.pg, self.pp, self.ps = tab(self.h_g), tab(self.h_p), tab(self.h_s)
+        self.gsum = torch.zeros(self.shard, dtype=torch.float32, device=torch.device(device))
+        self.arena = arena
+
+    def step(self, lr, step_dev, clip, st):
+        a = self.arena
+        self.h_g.barrier(channel=0)                    # every rank's gradient arena is complete
+        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
+        self.h_g.barrier(channel=1)                    # shard sums of squares published; peers are done reading my gradients
+        call('subgnn_dp_adam_allgather', self.pp, self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m), ptr(a.v), lr, 0.9, 0.999,
+             1e-8, ptr(step_dev), ptr(self.slots), clip, 1.0 / self.world, st)
+        self.h_g.barrier(channel=2)                    # every shard of my parameter arena has been written
+
+    def gather_moments(self):
+        """full Adam moments on every rank (checkpoints): each rank holds only its own shard"""
+        import torch.distributed as dist
+        out = []
+        for t in (self.arena.m, self.arena.v):
+            full = torch.zeros(self.shard * self.world, dtype=torch.float32, device=t.device)
+            lo, hi = self.rank * self.shard, min(self.n, (self.rank + 1) * self.shard)
+            if hi > lo:
+                full[lo:hi] = t[lo:hi]
+            dist.all_reduce(full)
+            out.append(full[:self.n])
+        return out
+
+
+# ------------------------------------------------------------------------------------------------------
 class StepContext:
     """All per-step scratch + the C descriptor for one (split tables, batch size, training flag)."""
 
@@ -601,7 +659,24 @@ class Engine:
         self.tables = {}
         self.tables['train'] = SplitTables(prepared, 'train', hp, self.device, graph)
         tt = self.tables['train']
-        self.arena = ParamArena(hp, self.n_nodes, self.num_classes, self.hid_dim, tt.n_sub, tt.C_pad, self.device)
+        # data parallel: gradient exchange + optimizer over NVLink peer memory (DpExchange) when symmetric memory is available;
+        # SUBGNN_DP_FUSED=0 (or a failed rendezvous) keeps the NCCL all-reduce captured inside the step graph
+        self.dp, alloc = None, None
+        if world_size > 1 and _flag('SUBGNN_DP_FUSED', hp.get('b200_dp_fused', True)):
+            try:
+                alloc = DpExchange.allocator(self.device)
+                alloc(16)
+            except Exception as e:                    # noqa: BLE001 — any failure here means: no peer memory, use NCCL
+                print('[subgnn_b200] symmetric memory unavailable (%s): data-parallel exchange through NCCL' % str(e).splitlines()[0], file=sys.stderr)
+                alloc = None
+        self.arena = ParamArena(hp, self.n_nodes, self.num_classes, self.hid_dim, tt.n_sub, tt.C_pad, self.device, alloc=alloc)
+        if alloc is not None:
+            import torch.distributed as dist
+            try:
+                self.dp = DpExchange(self.arena, world_size, dist.get_rank(), self.device)
+            except Exception as e:                    # noqa: BLE001
+                print('[subgnn_b200] symmetric-memory rendezvous failed (%s): data-parallel exchange through NCCL' % str(e).splitlines()[0], file=sys.stderr)
+                self.dp = None
         emb = torch.as_tensor(np.asarray(prepared['embeddings']), dtype=torch.float32).to(self.device)
         if self.arena.embed_trainable:
             self.arena.view('node_embeddings.weight').copy_(emb)
@@ -794,8 +869,11 @@ class Engine:
         if external_dlogits:
             call('subgnn_model_mlp_bwd', c.dptr, st)
         call('subgnn_model_rows_bwd', c.dptr, 2, st)                 # d q, d b_p
-        call('subgnn_model_q_bwd', c.dptr, st)                       # d emb_s, d w_p, position-anchor rows of dE
         fork = self.lstm is not None and self.concurrent
+        split_q = fork and _flag('SUBGNN_Q_BWD_SPLIT', True)
+        # the structure groups of q_bwd produce d emb_s, the input of the LSTM head gradient: on the chain; the position groups
+        # (B * A_pi + A_pb rows scattered into dE) run beside the BPTT chain
+        call('subgnn_model_q_bwd_part', c.dptr, 2 if split_q else 3, st)
         if fork:
             side = self._side_stream()
             side.wait_stream(main)
@@ -803,6 +881,8 @@ class Engine:
                 self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
         elif self.lstm is not None:
             self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), st)
+        if split_q:
+            call('subgnn_model_q_bwd_part', c.dptr, 1, st)
         call('subgnn_model_rows_bwd', c.dptr, 1, st)                 # neighbourhood chains + pooling
         call('subgnn_model_wgrad', c.dptr, st)
         if fork:
@@ -874,12 +954,20 @@ class Engine:
             import torch.distributed as dist
             dist.all_reduce(self.arena.grads)
 
+    def _exchange_and_optimize(self, c, st):
+        """[gradient exchange,] clip, Adam: fused over NVLink peer memory when available, else NCCL all-reduce + the two optimizer kernels"""
+        if self.dp is not None:
+            self.dp.step(self.lr, self.step_dev, self.grad_clip, st)
+        else:
+            self.allreduce_grads()
+            self._optimizer_launches(c, st)
+
     def _capture_step(self, c):
         """ONE CUDA graph for the whole step, data parallel included: the NCCL all-reduce of the gradient arena is captured between
         the backward pass and the optimizer (NCCL collectives are stream-capturable), so a replay is a single launch on every rank
         and the exchange is ordered by graph edges instead of by the host.  SUBGNN_DP_SPLIT_GRAPH=1 keeps the round-1 form (two
         graphs around an eagerly enqueued all-reduce) for A/B runs."""
-        split = self.world_size > 1 and _flag('SUBGNN_DP_SPLIT_GRAPH', False)
+        split = self.world_size > 1 and self.dp is None and _flag('SUBGNN_DP_SPLIT_GRAPH', False)
         if split:
             g1, g2 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
             with torch.cuda.graph(g1):
@@ -891,8 +979,7 @@ class Engine:
         g = torch.cuda.CUDAGraph()
         with torch.cuda.graph(g):
             self._grad_launches(c, _abi.stream_ptr())
-            self.allreduce_grads()
-            self._optimizer_launches(c, _abi.stream_ptr())
+            self._exchange_and_optimize(c, _abi.stream_ptr())
             c.loss_host.copy_(c.loss, non_blocking=True)
         return (g,)
 
@@ -906,14 +993,12 @@ class Engine:
         st = _abi.stream_ptr()
         if not use_graph:
             self._grad_launches(c, st)
-            self.allreduce_grads()
-            self._optimizer_launches(c, st)
+            self._exchange_and_optimize(c, st)
             c.loss_host.copy_(c.loss, non_blocking=True)
             return c.loss
         if c.graph is None:
             self._grad_launches(c, st)                         # warm-up (sets function attributes, NCCL communicator) — a real step
-            self.allreduce_grads()
-            self._optimizer_launches(c, st)
+            self._exchange_and_optimize(c, st)
             c.loss_host.copy_(c.loss, non_blocking=True)
             torch.cuda.synchronize()
             n0 = _abi.lib.subgnn_launch_count()
@@ -934,9 +1019,14 @@ class Engine:
         (== SubGNN.parameters() order), so a checkpoint written in fused mode restores into either optimizer."""
         t = int(self.step_dev.item())
         state = {}
+        if self.dp is not None:                          # sharded optimizer state: every rank assembles the full moments
+            m_full, v_full = self.dp.gather_moments()
+            mv = lambda name, which: (m_full if which == 'm' else v_full)[self.arena.entries[name][0]:self.arena.entries[name][0] + int(np.prod(self.arena.entries[name][1]))].view(self.arena.entries[name][1])
+        else:
+            mv = lambda name, which: self.arena.view(name, which)
         for i, name in enumerate(self.arena.entries):
-            state[i] = {'step': torch.tensor(float(t)), 'exp_avg': self.arena.view(name, 'm').detach().cpu().clone(),
-                        'exp_avg_sq': self.arena.view(name, 'v').detach().cpu().clone()}
+            state[i] = {'step': torch.tensor(float(t)), 'exp_avg': mv(name, 'm').detach().cpu().clone(),
+                        'exp_avg_sq': mv(name, 'v').detach().cpu().clone()}
         group = {'lr': self.lr, 'betas': (0.9, 0.999), 'eps': 1e-8, 'weight_decay': 0, 'amsgrad': False, 'params': list(range(len(self.arena.entries)))}
         return {'state': state, 'param_groups': [group], 'subgnn_b200_step': t, 'names': list(self.arena.entries)}
 
@@ -976,5 +1066,4 @@ class Engine:
 
     def _step_launches(self, c, st):
         self._grad_launches(c, st)
-        self.allreduce_grads()
-        self._optimizer_launches(c, st)
+        self._exchange_and_optimize(c, st)
