@@ -273,12 +273,24 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
 /* The row pass in phases, so that the neighbourhood chains (independent of the walk-encoder LSTM) can run concurrently
  * with it on another stream: SUBGNN_PHASE_N = pooling + N channel, SUBGNN_PHASE_PS = P / S property-aware outputs. */
 #define SUBGNN_PHASE_N 1
-#define SUBGNN_PHASE_PS 2
+#define SUBGNN_PHASE_P 2    /* position-channel property-aware outputs (depend on the batch only) */
+#define SUBGNN_PHASE_S 4    /* structure-channel property-aware outputs (depend on the walk-encoder LSTM) */
+#define SUBGNN_PHASE_PS 6
 /* rows_fwd + mlp_fwd together are SubGNN.py:225-312 forward for the batch (cc pooling :609-622, all SG_MPN layers
  * subgraph_mpn.py:133-241, masked_sum readout subgraph_utils.py:213-237, MLP :306-310) + loss :338-342; when d->training
  * mlp_fwd also runs the MLP backward down to dZ. */
 int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream);
 int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream);       /* readout MLP + loss (+ MLP backward when training); H1 must be zero on entry (split-K target) */
+/* The same in stages, restricted to column sets of Z: only the structure-channel columns of Z depend on the LSTM, so the first-layer
+ * product over every other column (SUBGNN_COLS_NOT_S) runs beside the LSTM chain and only the SUBGNN_COLS_S slices, the rest of the
+ * MLP and the S columns of dZ stay on the step's critical chain.  stages: bit mask, launched in this order. */
+#define SUBGNN_MLP_LIN1 1   /* H1pre += Z[:, cols] W1[:, cols]^T */
+#define SUBGNN_MLP_REST 2   /* bias / relu / dropout, lin2, lin3, loss, d logits, dH2, dH1 */
+#define SUBGNN_MLP_DZ 4     /* dZ[:, cols] = dH1 W1[:, cols] (training only) */
+#define SUBGNN_COLS_ALL 0
+#define SUBGNN_COLS_NOT_S 1
+#define SUBGNN_COLS_S 2
+int subgnn_model_mlp_stage(const subgnn_model_desc* d, int stages, int cols, void* stream);
 /* backward of all rows (autograd of the above): N-channel chains, property-aware outputs, pooling; scatters into dE / dq / Ndpre */
 int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream);
 /* The readout section as ONE launch of 8-CTA clusters (SubGNN.py:303-310 masked-sum output -> lin -> lin2 -> lin3, loss :338-342
@@ -321,10 +333,12 @@ int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
  *                   the shard's sum of squares.  Needs a cross-GPU barrier before (all gradients complete) and after.
  *   adam_allgather: global norm from the local slots (fixed order) -> clip_grad_norm_ coefficient; Adam on the shard with the rank's
  *                   own m / v; the new parameters are stored into shard r of every rank's parameter arena.  Barrier after.
- * Together: the averaged-gradient Adam step of SubGNN.py:1156-1164 under data parallelism, with sharded optimizer state. */
-int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, int world, int rank, long long n,
-                             long long shard, float* gsum, void* stream);
-int subgnn_dp_adam_allgather(const unsigned long long* peer_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
+ * Together: the averaged-gradient Adam step of SubGNN.py:1156-1164 under data parallelism, with sharded optimizer state.
+ * mc_grads / mc_params (may be NULL): NVLS multicast mappings of the two arenas — the shard sum becomes one multimem.ld_reduce per
+ * 16 bytes (reduced inside the NVSwitch), the parameter broadcast one multimem.st. */
+int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const float* mc_grads, int world, int rank,
+                             long long n, long long shard, float* gsum, void* stream);
+int subgnn_dp_adam_allgather(const unsigned long long* peer_params, float* mc_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
                              float* v, float lr, float beta1, float beta2, float eps, const int* step_dev, const float* slots_local,
                              float clip_norm, float grad_scale, void* stream);
 int subgnn_inc_step(int* step_dev, void* stream);

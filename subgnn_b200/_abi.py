@@ -61,6 +61,7 @@ SIGNATURES = {
     'subgnn_model_q_fwd_part': [P, I, P],
     'subgnn_model_rows_fwd': [P, I, P],
     'subgnn_model_mlp_fwd': [P, P],
+    'subgnn_model_mlp_stage': [P, I, I, P],
     'subgnn_model_readout': [P, P],
     'subgnn_model_rows_bwd': [P, I, P],
     'subgnn_model_mlp_bwd': [P, P],
@@ -73,8 +74,8 @@ SIGNATURES = {
     'subgnn_grad_sumsq': [P, LL, P, P],
     'subgnn_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],
     'subgnn_sum_to_scalar': [P, I, P, P],
-    'subgnn_dp_reduce_scatter': [P, P, I, I, LL, LL, P, P],
-    'subgnn_dp_adam_allgather': [P, I, I, LL, LL, P, P, P, F, F, F, F, P, P, F, F, P],
+    'subgnn_dp_reduce_scatter': [P, P, P, I, I, LL, LL, P, P],
+    'subgnn_dp_adam_allgather': [P, P, I, I, LL, LL, P, P, P, F, F, F, F, P, P, F, F, P],
     'subgnn_inc_step': [P, P],
 }
 _OTHER = {

@@ -13,6 +13,10 @@
 //                              m / v for that shard lives on rank r); the updated parameters are written into shard r of EVERY
 //                              rank's parameter arena (16-byte stores through NVLink)
 //
+// With NVLS multicast mappings (hdl.multicast_ptr) the shard sum is ONE multimem.ld_reduce per 16 bytes — the NVSwitch adds the ranks'
+// values — and the parameter broadcast ONE multimem.st: fabric traffic per rank drops from (world-1)/world of an arena each way to
+// 1/world.  Without multicast support the kernels fall back to per-peer loads / stores (same results up to summation order).
+//
 // Per step a rank reads (world-1)/world of one arena and writes (world-1)/world of one arena over the fabric — a reduce-scatter
 // plus an all-gather, the bandwidth-optimal decomposition of an all-reduce — and the optimizer state is sharded (ZeRO-1 style).
 // Every rank ends a step with bit-identical parameters: each shard has a single writer.
@@ -37,8 +41,19 @@ __device__ __forceinline__ float4 ld_peer(const float* p) {
   return v;
 }
 
-__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, DpPtrs slots, int world, int rank, long long n, long long shard,
-                                                               float* __restrict__ gsum) {
+// NVLS: one load from the MULTICAST mapping of the gradient arenas returns the sum over all ranks, reduced inside the NVSwitch
+// (multimem.ld_reduce), one store to the multicast mapping of the parameter arenas lands in every rank's copy (multimem.st)
+__device__ __forceinline__ float4 ld_reduce_mc(const float* p) {
+  float4 v;
+  asm volatile("multimem.ld_reduce.relaxed.sys.global.add.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_mc(float* p, const float4 v) {
+  asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+
+__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, DpPtrs slots, const float* __restrict__ mc_grads, int world, int rank,
+                                                               long long n, long long shard, float* __restrict__ gsum) {
   sg_pdl_sync();
   const long long base = (long long)rank * shard;
   const long long len = max(0LL, min(shard, n - base));            // elements of my shard (multiple of 4 except at the arena's end)
@@ -46,10 +61,13 @@ __global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, Dp
   float s = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len4; i += (long long)gridDim.x * blockDim.x) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-    for (int q = 0; q < world; ++q) {                               // fixed order: identical sums whatever the launch geometry
-      const float4 v = ld_peer(grads.p[q] + base + 4 * i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    if (mc_grads) acc = ld_reduce_mc(mc_grads + base + 4 * i);      // in-switch reduction: one load instead of `world`
+    else {
+#pragma unroll 8
+      for (int q = 0; q < world; ++q) {                             // fixed order: identical sums whatever the launch geometry
+        const float4 v = ld_peer(grads.p[q] + base + 4 * i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
     }
     reinterpret_cast<float4*>(gsum)[i] = acc;
     s = fmaf(acc.x, acc.x, s); s = fmaf(acc.y, acc.y, s); s = fmaf(acc.z, acc.z, s); s = fmaf(acc.w, acc.w, s);
@@ -94,7 +112,7 @@ __global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, Dp
 }
 
 __global__ void __launch_bounds__(256)
-dp_adam_allgather_kernel(DpPtrs params, int world, int rank, long long n, long long shard, const float* __restrict__ gsum, float* __restrict__ m,
+dp_adam_allgather_kernel(DpPtrs params, float* __restrict__ mc_params, int world, int rank, long long n, long long shard, const float* __restrict__ gsum, float* __restrict__ m,
                          float* __restrict__ v, float lr, float beta1, float beta2, float eps, const int* __restrict__ step_dev,
                          const float* slots_local, float clip_norm, float grad_scale) {
   sg_pdl_sync();
@@ -129,8 +147,11 @@ dp_adam_allgather_kernel(DpPtrs params, int world, int rank, long long n, long l
     upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
     reinterpret_cast<float4*>(ms)[i] = m4;
     reinterpret_cast<float4*>(vs)[i] = v4;
-#pragma unroll 4
-    for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(params.p[q] + base)[i] = p4;      // my shard of every rank's arena
+    if (mc_params) st_mc(mc_params + base + 4 * i, p4);                                         // one store, every rank's arena
+    else {
+#pragma unroll 8
+      for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(params.p[q] + base)[i] = p4;    // my shard of every rank's arena
+    }
   }
   if (blockIdx.x == 0)
     for (long long i = len4 * 4 + threadIdx.x; i < len; i += blockDim.x) {
@@ -145,8 +166,8 @@ dp_adam_allgather_kernel(DpPtrs params, int world, int rank, long long n, long l
 
 extern "C" {
 
-int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, int world, int rank, long long n,
-                             long long shard, float* gsum, void* stream) {
+int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const float* mc_grads, int world, int rank,
+                             long long n, long long shard, float* gsum, void* stream) {
   SG_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "bad world / rank");
   SG_REQUIRE(shard > 0 && (shard % 4) == 0 && shard * world >= n, "shard must be a multiple of 4 floats covering the arena");
   DpPtrs g, s;
@@ -156,11 +177,11 @@ int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigne
   }
   int grid = sg_grid_for(shard / 4, 256, 4);
   if (grid > DP_MAX_BLOCKS) grid = DP_MAX_BLOCKS;
-  sg_launch_pdl<SG_PDL_CHAIN>(dp_reduce_scatter_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g, s, world, rank, n, shard, gsum);
+  sg_launch_pdl<SG_PDL_CHAIN>(dp_reduce_scatter_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g, s, mc_grads, world, rank, n, shard, gsum);
   return subgnn_check_launch("dp_reduce_scatter_kernel");
 }
 
-int subgnn_dp_adam_allgather(const unsigned long long* peer_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
+int subgnn_dp_adam_allgather(const unsigned long long* peer_params, float* mc_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
                              float* v, float lr, float beta1, float beta2, float eps, const int* step_dev, const float* slots_local,
                              float clip_norm, float grad_scale, void* stream) {
   SG_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "bad world / rank");
@@ -168,7 +189,7 @@ int subgnn_dp_adam_allgather(const unsigned long long* peer_params, int world, i
   DpPtrs p;
   for (int q = 0; q < DP_MAX_WORLD; ++q) p.p[q] = q < world ? reinterpret_cast<float*>(peer_params[q]) : nullptr;
   int grid = sg_grid_for(shard / 4, 256, 4);
-  sg_launch_pdl<SG_PDL_CHAIN>(dp_adam_allgather_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, world, rank, n, shard, gsum, m, v, lr, beta1,
+  sg_launch_pdl<SG_PDL_CHAIN>(dp_adam_allgather_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, mc_params, world, rank, n, shard, gsum, m, v, lr, beta1,
                               beta2, eps, step_dev, slots_local, clip_norm, grad_scale);
   return subgnn_check_launch("dp_adam_allgather_kernel");
 }

@@ -245,6 +245,17 @@ __global__ void __launch_bounds__(256) q_bwd_kernel(Desc d, int which) {
     }
 }
 
+// column sets of Z (SUBGNN_COLS_*): the structure-channel property-aware outputs are the only columns that depend on the LSTM
+__device__ __forceinline__ bool z_col_selected(const Desc& d, int col, int cols) {
+  if (cols == SUBGNN_COLS_ALL) return true;
+  bool is_s = false;
+  if (d.use_s && col >= d.D) {
+    const int lw = layer_width(d);
+    is_s = (col - d.D) % lw >= lw - 2 * d.A_s;
+  }
+  return cols == SUBGNN_COLS_S ? is_s : !is_s;
+}
+
 __device__ __forceinline__ unsigned mlp_salt(const Desc& d) { return (d.step_dev ? (unsigned)*d.step_dev : d.step) * 4u; }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,12 +479,13 @@ __global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases
       }
     }
     // ---- position / structure channels: property-aware outputs relu(s q + b_p) ----
-    if (phases & 2) {
+    if (phases & SUBGNN_PHASE_PS) {
       const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
       const int per_layer = wp_ + ws_;
       for (int e = tid; e < d.L * per_layer; e += ROW_THREADS) {
         const int l = e / per_layer;
         int o = e % per_layer;
+        if (!(phases & (o < wp_ ? SUBGNN_PHASE_P : SUBGNN_PHASE_S))) continue;
         float s, q, bp;
         int zc;
         if (o < wp_) {
@@ -515,12 +527,17 @@ __global__ void __launch_bounds__(MLP_THREADS) mlp_bwd_kernel(Desc d) {
 //   mlp_dz_kernel    CTA per 64-column slice of hid: dZ[b][i] = sum_j dH1[b][j] W1[j][i]
 #define MLP_SLICE 64
 #define MLP_BT 128      // samples per CTA of the two sliced kernels (grid.y tiles larger batches)
-__global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
+__global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d, int cols) {
   extern __shared__ float sm[];
   const int b0 = blockIdx.y * MLP_BT, bn = min(MLP_BT, d.B - b0);
   float* zs = sm;                               // [bn][MLP_SLICE]
   float* ws = sm + (size_t)min(d.B, MLP_BT) * MLP_SLICE;     // [MLP_SLICE][h1]
   const int k0 = blockIdx.x * MLP_SLICE, kn = min(MLP_SLICE, d.hid - k0);
+  if (cols != SUBGNN_COLS_ALL) {                // slices without a column of the requested set retire at once
+    int any = 0;
+    for (int kk = threadIdx.x; kk < kn; kk += blockDim.x) any |= z_col_selected(d, k0 + kk, cols) ? 1 : 0;
+    if (!__syncthreads_or(any)) return;
+  }
   // the weight slice was transposed several launches ago (complete by transitivity of the dependency waits): staged before
   // this kernel's own wait, while the row kernel that finishes Z is still running
   const float* wt = d.lin_wt[0] + (size_t)k0 * d.h1;
@@ -528,7 +545,7 @@ __global__ void __launch_bounds__(256) mlp_lin1_kernel(Desc d) {
   sg_pdl_sync();
   sg_stage<8>(zs, bn * MLP_SLICE, [&](int e) {
     const int b = e / MLP_SLICE, kk = e % MLP_SLICE;
-    return kk < kn ? d.Z[(size_t)(b0 + b) * d.hid + k0 + kk] : 0.f;
+    return (kk < kn && z_col_selected(d, k0 + kk, cols)) ? d.Z[(size_t)(b0 + b) * d.hid + k0 + kk] : 0.f;
   });
   __syncthreads();
   for (int o = threadIdx.x; o < bn * d.h1; o += blockDim.x) {
@@ -550,6 +567,8 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   float* lg = h2s + d.h2;                        // [K]
   float* dl = lg + d.n_classes;                  // [K]
   float* g2 = dl + d.n_classes;                  // [h2]
+  float* bs = g2 + d.h2;                         // [h1 + h2 + K]  the three bias vectors
+  float* w3s = bs + d.h1 + d.h2 + d.n_classes;   // [K][h2]        lin3 weights
   const int b = blockIdx.x, tid = threadIdx.x, K = d.n_classes;
   const bool bwd = d.training && d.dZ;
   // both copies of the lin2 weights land in one staging pass (w1n directly follows w1t): 16 loads in flight per thread
@@ -557,16 +576,26 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   const float* src_n = d.lin_w[1];
   const int nw1 = d.h1 * d.h2;
   sg_stage<16>(w1t, bwd ? 2 * nw1 : nw1, [&](int e) { return e < nw1 ? __ldg(src_t + e) : __ldg(src_n + e - nw1); });
+  // every other global operand of the dependent phases below (biases, lin3 weights, the label) is fetched before the wait too:
+  // each L2 round trip inside the chain is ~1 us of the step's critical path
+  sg_stage<8>(bs, d.h1 + d.h2 + K + K * d.h2, [&](int e) {
+    if (e < d.h1) return __ldg(d.lin_b[0] + e);
+    if (e < d.h1 + d.h2) return __ldg(d.lin_b[1] + e - d.h1);
+    if (e < d.h1 + d.h2 + K) return __ldg(d.lin_b[2] + e - d.h1 - d.h2);
+    return __ldg(d.lin_w[2] + e - d.h1 - d.h2 - K);
+  });
+  int my_label = 0;                              // (batch_idx is written by the step's H2D copy before any kernel; labels are static)
+  if (tid == 0 && !d.multilabel && d.labels) my_label = d.labels[d.batch_idx[b]];
   sg_pdl_sync();                                 // (weights staged before the wait: not written by the preceding launch)
   for (int j = tid; j < d.h1; j += blockDim.x) {
-    float acc = fmaxf(d.H1[(size_t)b * d.h1 + j] + d.lin_b[0][j], 0.f);
+    float acc = fmaxf(d.H1[(size_t)b * d.h1 + j] + bs[j], 0.f);
     if (d.training) acc *= sg_dropout_scale(d.seed, mlp_salt(d) + 0, (uint64_t)b * d.h1 + j, d.lin_dropout);
     h1s[j] = acc;
     d.H1[(size_t)b * d.h1 + j] = acc;
   }
   __syncthreads();
   for (int j = tid; j < d.h2; j += blockDim.x) {
-    float acc = d.lin_b[1][j];
+    float acc = bs[d.h1 + j];
 #pragma unroll 8
     for (int i = 0; i < d.h1; ++i) acc = fmaf(h1s[i], w1t[i * d.h2 + j], acc);
     acc = fmaxf(acc, 0.f);
@@ -579,10 +608,10 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
     const int warp = tid >> 5, lane = tid & 31, nw = blockDim.x >> 5;
     for (int c = warp; c < K; c += nw) {
       float acc = 0.f;
-      for (int i = lane; i < d.h2; i += 32) acc = fmaf(h2s[i], __ldg(d.lin_w[2] + (size_t)c * d.h2 + i), acc);
+      for (int i = lane; i < d.h2; i += 32) acc = fmaf(h2s[i], w3s[c * d.h2 + i], acc);
       acc = warp_sum(acc);
       if (lane == 0) {
-        acc += d.lin_b[2][c];
+        acc += bs[d.h1 + d.h2 + c];
         lg[c] = acc;
         d.logits[(size_t)b * K + c] = acc;
       }
@@ -590,7 +619,6 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   }
   __syncthreads();
   if (tid == 0) {                                // loss term and d logits (K is tiny)
-    const int sub = d.batch_idx[b];
     float loss = 0.f;
     if (!d.multilabel) {
       float mx = lg[0];
@@ -598,13 +626,14 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
       float se = 0.f;
       for (int c = 0; c < K; ++c) se += expf(lg[c] - mx);
       const float lse = mx + logf(se);
-      const int y = d.labels ? d.labels[sub] : 0;
+      const int y = my_label;
       loss = (lse - lg[y]) / (float)d.B;
       for (int c = 0; c < K; ++c) {
         dl[c] = (expf(lg[c] - lse) - (c == y ? 1.f : 0.f)) / (float)d.B;
         if (d.dlogits) d.dlogits[(size_t)b * K + c] = dl[c];
       }
     } else {
+      const int sub = d.batch_idx[b];
       const float inv = 1.f / ((float)d.B * (float)K);
       for (int c = 0; c < K; ++c) {
         const float x = lg[c], y = d.labels_multi[(size_t)sub * K + c];
@@ -619,7 +648,7 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   __syncthreads();
   for (int j = tid; j < d.h2; j += blockDim.x) {
     float acc = 0.f;
-    for (int c = 0; c < K; ++c) acc = fmaf(dl[c], __ldg(d.lin_w[2] + (size_t)c * d.h2 + j), acc);
+    for (int c = 0; c < K; ++c) acc = fmaf(dl[c], w3s[c * d.h2 + j], acc);
     const float sc = sg_dropout_scale(d.seed, mlp_salt(d) + 1, (uint64_t)b * d.h2 + j, d.lin_dropout);
     acc = h2s[j] > 0.f ? acc * sc : 0.f;
     g2[j] = acc;
@@ -635,12 +664,17 @@ __global__ void __launch_bounds__(256) mlp_rest_kernel(Desc d) {
   }
 }
 
-__global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
+__global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d, int cols) {
   extern __shared__ float sm[];
   const int b0 = blockIdx.y * MLP_BT, bn = min(MLP_BT, d.B - b0);
   float* g1s = sm;                               // [bn][h1]
   float* ws = sm + (size_t)min(d.B, MLP_BT) * d.h1;           // [h1][MLP_SLICE]
   const int i0 = blockIdx.x * MLP_SLICE, in = min(MLP_SLICE, d.hid - i0);
+  if (cols != SUBGNN_COLS_ALL) {
+    int any = 0;
+    for (int ii = threadIdx.x; ii < in; ii += blockDim.x) any |= z_col_selected(d, i0 + ii, cols) ? 1 : 0;
+    if (!__syncthreads_or(any)) return;
+  }
   // the W1 slice is a PARAMETER (last written by the previous step's Adam, a full stream dependency ago): staged before the
   // programmatic-dependency wait, i.e. while mlp_rest_kernel is still running
   const float* w0 = d.lin_w[0];
@@ -653,7 +687,7 @@ __global__ void __launch_bounds__(256) mlp_dz_kernel(Desc d) {
   __syncthreads();
   for (int o = threadIdx.x; o < bn * MLP_SLICE; o += blockDim.x) {
     const int b = o / MLP_SLICE, ii = o % MLP_SLICE;
-    if (ii >= in) continue;
+    if (ii >= in || !z_col_selected(d, i0 + ii, cols)) continue;
     const float* gr = g1s + (size_t)b * d.h1;
     float acc = 0.f;
 #pragma unroll 8
@@ -1080,7 +1114,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases
       }
     }
     // ---- property-aware outputs backward: d q (global atomics) and d b_p (CTA reduction) ----
-    if (phases & 2) {
+    if (phases & SUBGNN_PHASE_PS) {
       const int wp_ = (d.use_p ? d.A_pi + d.A_pb : 0), ws_ = (d.use_s ? 2 * d.A_s : 0);
       const int per_layer = wp_ + ws_;
       // every warp runs the same number of iterations (out-of-range lanes carry key -1): the bias-gradient terms of a warp are
@@ -1091,7 +1125,7 @@ __global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases
         const int e = e0 + tid;
         int key = -1;
         float g_ = 0.f;
-        if (e < n_ent) {
+        if (e < n_ent && (phases & ((e % per_layer) < wp_ ? SUBGNN_PHASE_P : SUBGNN_PHASE_S))) {
         const int l = e / per_layer;
         int o = e % per_layer;
         float s, q, bp;
@@ -1235,7 +1269,8 @@ int subgnn_model_q_fwd_part(const subgnn_model_desc* d, int which, void* stream)
 int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
+  if (!d->use_p) phases &= ~SUBGNN_PHASE_P;
+  if (!d->use_s) phases &= ~SUBGNN_PHASE_S;
   if (!phases) return SUBGNN_OK;
   const size_t smem = row_smem_bytes(d->D, d->L);
   if (smem > 48 * 1024) {                       // deep / wide configurations: opt in to the large dynamic shared-memory window
@@ -1251,30 +1286,42 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) 
 }
 
 // requires d->H1 zeroed on entry (it is the split-K accumulation target of the first layer)
-int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
+int subgnn_model_mlp_stage(const subgnn_model_desc* d, int stages, int cols, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
+  SG_REQUIRE(cols >= SUBGNN_COLS_ALL && cols <= SUBGNN_COLS_S, "unknown column set");
   cudaStream_t st = (cudaStream_t)stream;
   const int slices = sg_div_up(d->hid, MLP_SLICE);
   const int bt = d->B < MLP_BT ? d->B : MLP_BT, b_tiles = sg_div_up(d->B, MLP_BT);
   const size_t s1 = (size_t)(bt * MLP_SLICE + MLP_SLICE * d->h1) * sizeof(float);
-  const size_t s2 = (size_t)(2 * d->h1 * d->h2 + d->h1 + 2 * d->h2 + 2 * d->n_classes + 8) * sizeof(float);
+  const size_t s2 = (size_t)(2 * d->h1 * d->h2 + d->h1 + 2 * d->h2 + 2 * d->n_classes + (d->h1 + d->h2 + d->n_classes + d->n_classes * d->h2) + 8) * sizeof(float);
   const size_t s3 = (size_t)(bt * d->h1 + d->h1 * MLP_SLICE) * sizeof(float);
   if (s1 > 200 * 1024 || s2 > 200 * 1024 || s3 > 200 * 1024) { subgnn_set_error("MLP dimensions too large for shared memory"); return SUBGNN_ERR_ARG; }
   if (s1 > 48 * 1024) cudaFuncSetAttribute(mlp_lin1_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s1);
   if (s2 > 48 * 1024) cudaFuncSetAttribute(mlp_rest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s2);
   if (s3 > 48 * 1024) cudaFuncSetAttribute(mlp_dz_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)s3);
-  sg_launch_pdl<SG_PDL_CHAIN>(mlp_lin1_kernel, dim3(slices, b_tiles), dim3(256), s1, st, *d);
-  rc = subgnn_check_launch("mlp_lin1_kernel");
-  if (rc) return rc;
-  sg_launch_pdl<SG_PDL_CHAIN>(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
-  rc = subgnn_check_launch("mlp_rest_kernel");
-  if (rc) return rc;
-  if (d->training && d->dZ) {
-    sg_launch_pdl<SG_PDL_CHAIN>(mlp_dz_kernel, dim3(slices, b_tiles), dim3(256), s3, st, *d);
+  if (stages & SUBGNN_MLP_LIN1) {
+    // the LSTM-independent columns run beside the LSTM chain: launched normally (an early-scheduled grid would take SM slots from it)
+    if (cols == SUBGNN_COLS_NOT_S) sg_launch_pdl(mlp_lin1_kernel, dim3(slices, b_tiles), dim3(256), s1, st, *d, cols);
+    else sg_launch_pdl<SG_PDL_CHAIN>(mlp_lin1_kernel, dim3(slices, b_tiles), dim3(256), s1, st, *d, cols);
+    rc = subgnn_check_launch("mlp_lin1_kernel");
+    if (rc) return rc;
+  }
+  if (stages & SUBGNN_MLP_REST) {
+    sg_launch_pdl<SG_PDL_CHAIN>(mlp_rest_kernel, dim3(d->B), dim3(256), s2, st, *d);
+    rc = subgnn_check_launch("mlp_rest_kernel");
+    if (rc) return rc;
+  }
+  if ((stages & SUBGNN_MLP_DZ) && d->training && d->dZ) {
+    if (cols == SUBGNN_COLS_NOT_S) sg_launch_pdl(mlp_dz_kernel, dim3(slices, b_tiles), dim3(256), s3, st, *d, cols);
+    else sg_launch_pdl<SG_PDL_CHAIN>(mlp_dz_kernel, dim3(slices, b_tiles), dim3(256), s3, st, *d, cols);
     rc = subgnn_check_launch("mlp_dz_kernel");
   }
   return rc;
+}
+
+int subgnn_model_mlp_fwd(const subgnn_model_desc* d, void* stream) {
+  return subgnn_model_mlp_stage(d, SUBGNN_MLP_LIN1 | SUBGNN_MLP_REST | SUBGNN_MLP_DZ, SUBGNN_COLS_ALL, stream);
 }
 
 int subgnn_model_readout_supported(const subgnn_model_desc* d) {
@@ -1318,7 +1365,8 @@ int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream) {
 int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
-  if (!(d->use_p || d->use_s)) phases &= ~SUBGNN_PHASE_PS;
+  if (!d->use_p) phases &= ~SUBGNN_PHASE_P;
+  if (!d->use_s) phases &= ~SUBGNN_PHASE_S;
   if (!phases) return SUBGNN_OK;
   DISPATCH_DPL(d->D, row_bwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), bwd_smem(*d), (cudaStream_t)stream, *d, phases);
   return subgnn_check_launch("row_bwd_kernel");

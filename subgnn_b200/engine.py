@@ -510,13 +510,22 @@ class DpExchange:
         self.pg, self.pp, self.ps = tab(self.h_g), tab(self.h_p), tab(self.h_s)
         self.gsum = torch.zeros(self.shard, dtype=torch.float32, device=torch.device(device))
         self.arena = arena
+        # NVLS multicast mappings (in-switch reduction / broadcast) when the fabric offers them; SUBGNN_DP_MULTICAST=0: per-peer loads / stores
+        self.mc_g = self.mc_p = None
+        if _flag('SUBGNN_DP_MULTICAST', True):
+            try:
+                mg, mp = int(self.h_g.multicast_ptr or 0), int(self.h_p.multicast_ptr or 0)      # 0: the fabric / driver offers no multicast
+                if mg and mp:
+                    self.mc_g, self.mc_p = mg, mp
+            except Exception:                         # noqa: BLE001 — no multicast: peer loads / stores
+                self.mc_g = self.mc_p = None
 
     def step(self, lr, step_dev, clip, st):
         a = self.arena
         self.h_g.barrier(channel=0)                    # every rank's gradient arena is complete
-        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
+        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.mc_g, self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
         self.h_g.barrier(channel=1)                    # shard sums of squares published; peers are done reading my gradients
-        call('subgnn_dp_adam_allgather', self.pp, self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m), ptr(a.v), lr, 0.9, 0.999,
+        call('subgnn_dp_adam_allgather', self.pp, self.mc_p, self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m), ptr(a.v), lr, 0.9, 0.999,
              1e-8, ptr(step_dev), ptr(self.slots), clip, 1.0 / self.world, st)
         self.h_g.barrier(channel=2)                    # every shard of my parameter arena has been written
 
@@ -813,7 +822,11 @@ class Engine:
             self._qs = torch.cuda.Stream(device=self.device)
         return self._qs
 
-    def _forward_launches(self, c, st, zero_grads=False):
+    def _forward_launches(self, c, st, zero_grads=False, split=False):
+        """split (fused training step only): only the structure-channel columns of Z depend on the LSTM, so the position outputs and
+        the first MLP layer over every other column run beside the LSTM chain; behind the join stay the structure outputs, their
+        slices of the first layer, the rest of the MLP and the structure columns of dZ (the others are produced in the backward
+        pass, beside the BPTT chain)."""
         main = torch.cuda.current_stream()
         fork = self.lstm is not None and self.concurrent
         if fork:                                  # the LSTM chain is the longest of the step: it starts before the zero fills
@@ -854,21 +867,46 @@ class Engine:
         call('subgnn_model_rows_fwd', c.dptr, 1, st)                 # pooling + neighbourhood channel
         if bfork:
             main.wait_stream(qs)
+        if split:
+            call('subgnn_model_rows_fwd', c.dptr, 2, st)             # position property-aware outputs
+            call('subgnn_model_mlp_stage', c.dptr, 1, 1, st)         # first MLP layer over the LSTM-independent columns of Z
+            main.wait_stream(side)
+            call('subgnn_model_q_fwd_part', c.dptr, 2, st)           # structure anchors (LSTM output)
+            call('subgnn_model_rows_fwd', c.dptr, 4, st)             # structure property-aware outputs
+            call('subgnn_model_mlp_stage', c.dptr, 1, 2, st)         # their slices of the first layer
+            call('subgnn_model_mlp_stage', c.dptr, 2, 0, st)         # lin2, lin3, loss, d logits, dH2, dH1
+            call('subgnn_model_mlp_stage', c.dptr, 4, 2, st)         # structure columns of dZ (the chain continues through them)
+            return
         if fork:
             main.wait_stream(side)
         call('subgnn_model_q_fwd_part', c.dptr, 2, st)               # structure anchors (LSTM output)
-        call('subgnn_model_rows_fwd', c.dptr, 2, st)                 # P / S property-aware outputs
+        call('subgnn_model_rows_fwd', c.dptr, 6, st)                 # P / S property-aware outputs
         if c.readout_cluster:
             call('subgnn_model_readout', c.dptr, st)                 # lin -> lin2 -> lin3 -> loss (-> dZ [, MLP gradients]) in one launch
         else:
             call('subgnn_model_mlp_fwd', c.dptr, st)
             call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
 
-    def _backward_launches(self, c, st, external_dlogits=False):
+    def _backward_launches(self, c, st, external_dlogits=False, split=False):
         main = torch.cuda.current_stream()
+        if split:
+            call('subgnn_model_rows_bwd', c.dptr, 4, st)             # structure outputs: d q_s, d b_p
+            call('subgnn_model_q_bwd_part', c.dptr, 2, st)           # d emb_s
+            side = self._side_stream()
+            side.wait_stream(main)
+            with torch.cuda.stream(side):
+                self.lstm.backward(self.E_ptr(), self.dE_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
+            call('subgnn_model_mlp_stage', c.dptr, 4, 1, st)         # every other column of dZ
+            call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
+            call('subgnn_model_rows_bwd', c.dptr, 2, st)             # position outputs: d q_p, d b_p
+            call('subgnn_model_q_bwd_part', c.dptr, 1, st)
+            call('subgnn_model_rows_bwd', c.dptr, 1, st)             # neighbourhood chains + pooling
+            call('subgnn_model_wgrad', c.dptr, st)
+            main.wait_stream(side)
+            return
         if external_dlogits:
             call('subgnn_model_mlp_bwd', c.dptr, st)
-        call('subgnn_model_rows_bwd', c.dptr, 2, st)                 # d q, d b_p
+        call('subgnn_model_rows_bwd', c.dptr, 6, st)                 # d q, d b_p
         fork = self.lstm is not None and self.concurrent
         split_q = fork and _flag('SUBGNN_Q_BWD_SPLIT', True)
         # the structure groups of q_bwd produce d emb_s, the input of the LSTM head gradient: on the chain; the position groups
@@ -1058,9 +1096,11 @@ class Engine:
         # fused step: the readout kernel's own d logits are THE gradient, so it also produces the MLP weight / bias gradients
         # (the descriptor is copied by value at every launch: the flag is per call)
         c.desc.mlp_fused = 1 if (c.readout_cluster and _flag('SUBGNN_READOUT_FUSED_WGRAD', self.hp.get('b200_readout_fused_wgrad', False))) else 0
+        split = (self.lstm is not None and self.concurrent and not c.readout_cluster and
+                 _flag('SUBGNN_READOUT_SPLIT', self.hp.get('b200_readout_split', True)))
         try:
-            self._forward_launches(c, st, zero_grads=True)
-            self._backward_launches(c, st)
+            self._forward_launches(c, st, zero_grads=True, split=split)
+            self._backward_launches(c, st, split=split)
         finally:
             c.desc.mlp_fused = 0
 

@@ -114,3 +114,27 @@ def test_cluster_readout_kernel_matches_default_path(name, monkeypatch):
         np.testing.assert_allclose(losses, states[0][0], rtol=1e-5)
         for k in sd:
             np.testing.assert_allclose(sd[k], states[0][1][k], rtol=1e-4, atol=1e-6, err_msg=k)
+
+
+@pytest.mark.parametrize('name', ['density', 'ppi_bp'])
+def test_split_readout_schedule_takes_the_same_steps(name, monkeypatch):
+    """the default step schedule computes the LSTM-independent columns of the first MLP layer (and of dZ) beside the LSTM / BPTT chains
+    (SUBGNN_READOUT_SPLIT, engine._forward_launches): same steps as the unsplit schedule, dropout on (same Philox masks both ways)."""
+    from subgnn_b200 import synth
+    from subgnn_b200.engine import Engine
+    hp, g, p = build(name)
+    hp = dict(hp, lin_dropout=synth.hparams(name)['lin_dropout'], lstm_dropout=synth.hparams(name)['lstm_dropout'])
+    n, B = len(p['labels']['train']), hp['batch_size']
+    rs = np.random.RandomState(4)
+    batches = [np.sort(rs.choice(n, size=B, replace=False)) for _ in range(4)]
+    states = []
+    for split in ('1', '0'):
+        monkeypatch.setenv('SUBGNN_READOUT_SPLIT', split)
+        eng = Engine(hp, p, device='cuda', graph=g, seed=5)
+        eng.init_parameters(3)
+        losses = [float(eng.train_step(b, use_graph=(i > 0)).item()) for i, b in enumerate(batches)]
+        torch.cuda.synchronize()
+        states.append((losses, {k: v.cpu().numpy().copy() for k, v in eng.arena.state_dict().items()}))
+    np.testing.assert_allclose(states[0][0], states[1][0], rtol=1e-5)
+    for k in states[0][1]:
+        np.testing.assert_allclose(states[0][1][k], states[1][1][k], rtol=1e-4, atol=1e-6, err_msg=k)
