@@ -330,17 +330,23 @@ int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
  * The gradient / parameter arenas of all ranks are symmetric allocations mapped into every process (NVLink peer memory); the
  * pointer tables are HOST arrays of device addresses, one per rank.  Rank r owns shard r = elements [r * shard, (r + 1) * shard):
  *   reduce_scatter: gsum[i] = sum over ranks of grads_q[r * shard + i] (fixed order); slot r of EVERY rank's `slots` array receives
- *                   the shard's sum of squares.  Needs a cross-GPU barrier before (all gradients complete) and after.
- *   adam_allgather: global norm from the local slots (fixed order) -> clip_grad_norm_ coefficient; Adam on the shard with the rank's
- *                   own m / v; the new parameters are stored into shard r of every rank's parameter arena.  Barrier after.
+ *                   the shard's sum of squares.  Waits (inside the kernel) until every rank has signalled that its gradients are complete.
+ *   adam_allgather: waits for every rank's reduce_scatter; global norm from the local slots (fixed order) -> clip_grad_norm_
+ *                   coefficient; Adam on the shard with the rank's own m / v; the new parameters are stored into shard r of every
+ *                   rank's parameter arena; a closing 1-thread kernel waits until every shard of the own arena has been written and
+ *                   advances *epoch_dev.
+ * Cross-GPU synchronisation: peer_flags[q] -> rank q's symmetric flag array of subgnn_dp_flag_words() 32-bit words (zero-initialised),
+ * *epoch_dev (device counter, starts at 1, advanced once per exchange identically on every rank) is the value signalled.
  * Together: the averaged-gradient Adam step of SubGNN.py:1156-1164 under data parallelism, with sharded optimizer state.
  * mc_grads / mc_params (may be NULL): NVLS multicast mappings of the two arenas — the shard sum becomes one multimem.ld_reduce per
  * 16 bytes (reduced inside the NVSwitch), the parameter broadcast one multimem.st. */
-int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const float* mc_grads, int world, int rank,
-                             long long n, long long shard, float* gsum, void* stream);
-int subgnn_dp_adam_allgather(const unsigned long long* peer_params, float* mc_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
-                             float* v, float lr, float beta1, float beta2, float eps, const int* step_dev, const float* slots_local,
-                             float clip_norm, float grad_scale, void* stream);
+int subgnn_dp_flag_words(void);
+int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const unsigned long long* peer_flags,
+                             const float* mc_grads, const unsigned* epoch_dev, int world, int rank, long long n, long long shard, float* gsum,
+                             void* stream);
+int subgnn_dp_adam_allgather(const unsigned long long* peer_params, const unsigned long long* peer_flags, float* mc_params, unsigned* epoch_dev, int world,
+                             int rank, long long n, long long shard, const float* gsum, float* m, float* v, float lr, float beta1, float beta2,
+                             float eps, const int* step_dev, const float* slots_local, float clip_norm, float grad_scale, void* stream);
 int subgnn_inc_step(int* step_dev, void* stream);
 
 #ifdef __cplusplus

@@ -74,8 +74,8 @@ SIGNATURES = {
     'subgnn_grad_sumsq': [P, LL, P, P],
     'subgnn_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],
     'subgnn_sum_to_scalar': [P, I, P, P],
-    'subgnn_dp_reduce_scatter': [P, P, P, I, I, LL, LL, P, P],
-    'subgnn_dp_adam_allgather': [P, P, I, I, LL, LL, P, P, P, F, F, F, F, P, P, F, F, P],
+    'subgnn_dp_reduce_scatter': [P, P, P, P, P, I, I, LL, LL, P, P],
+    'subgnn_dp_adam_allgather': [P, P, P, P, I, I, LL, LL, P, P, P, F, F, F, F, P, P, F, F, P],
     'subgnn_inc_step': [P, P],
 }
 _OTHER = {
@@ -86,6 +86,7 @@ _OTHER = {
     'subgnn_gemm_desc_size': ([], I),
     'subgnn_model_readout_supported': ([P], I),
     'subgnn_tc_ws_available': ([], I),
+    'subgnn_dp_flag_words': ([], I),
     'subgnn_launch_count': ([], U64),
     'subgnn_lstm_fused_dropout_supported': ([I], I),
     'subgnn_variant_log': ([C.c_char_p, I], I),

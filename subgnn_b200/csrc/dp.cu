@@ -4,7 +4,8 @@
 // torch.optim.Adam / clip_grad_norm_ (SubGNN.py:1156-1164 under Lightning's distributed back-ends).  Round 1 did
 // all-reduce (NCCL) -> sum of squares -> Adam: the 4 flat arenas streamed three times and a library collective between two
 // graph halves.  Here the gradient arenas of all ranks are SYMMETRIC allocations (torch.distributed._symmetric_memory: every rank
-// maps every peer's arena), and the exchange is two kernels around cross-GPU barriers:
+// maps every peer's arena), and the exchange is two kernels with the cross-GPU barriers inside them (epoch flags in symmetric
+// memory: release stores into the peers' flag arrays, acquire loads of the own one — no barrier launches on the chain):
 //
 //   dp_reduce_scatter_kernel   rank r sums shard r of the gradient arena over all peers (16-byte loads straight from the peers'
 //                              HBM through NVLink / NVSwitch, fixed summation order), keeps the sum in a local shard buffer and
@@ -25,16 +26,20 @@
 
 #define DP_MAX_WORLD 16
 #define DP_MAX_BLOCKS 1024
+#define DP_UNROLL 4          // 16-byte words per thread and round: DP_UNROLL x world peer loads in flight
 
 struct DpPtrs {
   float* p[DP_MAX_WORLD];
 };
+struct DpFlags {
+  unsigned* p[DP_MAX_WORLD];   // every rank's flag array [3][DP_MAX_WORLD] (symmetric): [phase][sender]
+};
 
 __device__ float dp_part[DP_MAX_BLOCKS];
-__device__ unsigned dp_ticket = 0;
+__device__ unsigned dp_ticket = 0, dp_ticket2 = 0;
 
 // peer memory is read with ld.volatile (never served from a stale cache line of the previous step) and written with plain stores
-// followed by a system-scope fence; the cross-GPU barriers around the kernels carry the release / acquire
+// followed by a system-scope fence
 __device__ __forceinline__ float4 ld_peer(const float* p) {
   float4 v;
   asm volatile("ld.volatile.global.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p));
@@ -52,25 +57,68 @@ __device__ __forceinline__ void st_mc(float* p, const float4 v) {
   asm volatile("multimem.st.relaxed.sys.global.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(p), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
 }
 
-__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, DpPtrs slots, const float* __restrict__ mc_grads, int world, int rank,
-                                                               long long n, long long shard, float* __restrict__ gsum) {
+// Cross-GPU barriers inside the kernels: flags[phase][sender] in every rank's symmetric flag array carry the epoch (a device
+// counter every rank advances once per exchange).  signal = release store of the epoch into my slot of every peer's array,
+// wait = acquire loads of my own array until every sender's slot has reached the epoch.  A waiter spins for at most ~10 s
+// (a lost peer traps the kernel instead of hanging the GPU).
+__device__ __forceinline__ void dp_signal(const DpFlags& f, int phase, int world, int rank, unsigned epoch) {
+  __threadfence_system();
+  for (int q = 0; q < world; ++q)
+    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f.p[q] + phase * DP_MAX_WORLD + rank), "r"(epoch) : "memory");
+}
+__device__ __forceinline__ void dp_wait(const unsigned* mine, int phase, int world, unsigned epoch) {
+  const long long t0 = clock64();
+  for (int q = 0; q < world; ++q) {
+    unsigned v = 0;
+    while (true) {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + phase * DP_MAX_WORLD + q) : "memory");
+      if ((int)(v - epoch) >= 0) break;
+      if (clock64() - t0 > 20000000000ll) __trap();                 // ~10 s: a peer is gone
+    }
+  }
+}
+
+// phase 0: "my gradient arena is complete" (signalled by the first block, which runs after every kernel of my backward pass);
+// phase 1: "my shard's sum of squares is in your slot and I am done reading your gradients" (last block).
+__global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, DpPtrs slots, DpFlags flags, const float* __restrict__ mc_grads,
+                                                               const unsigned* __restrict__ epoch_dev, int world, int rank, long long n, long long shard,
+                                                               float* __restrict__ gsum) {
   sg_pdl_sync();
+  const unsigned epoch = *epoch_dev;
+  if (threadIdx.x == 0) {
+    if (blockIdx.x == 0) dp_signal(flags, 0, world, rank, epoch);
+    dp_wait(flags.p[rank], 0, world, epoch);
+  }
+  __syncthreads();
   const long long base = (long long)rank * shard;
   const long long len = max(0LL, min(shard, n - base));            // elements of my shard (multiple of 4 except at the arena's end)
   const long long len4 = len / 4;
+  const long long stride = (long long)gridDim.x * blockDim.x;
   float s = 0.f;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len4; i += (long long)gridDim.x * blockDim.x) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (mc_grads) acc = ld_reduce_mc(mc_grads + base + 4 * i);      // in-switch reduction: one load instead of `world`
-    else {
-#pragma unroll 8
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < len4; i0 += DP_UNROLL * stride) {
+    float4 acc[DP_UNROLL];
+    if (mc_grads) {
+#pragma unroll
+      for (int u = 0; u < DP_UNROLL; ++u)                            // in-switch reduction: one load instead of `world`
+        acc[u] = (i0 + u * stride < len4) ? ld_reduce_mc(mc_grads + base + 4 * (i0 + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+    } else {
+#pragma unroll
+      for (int u = 0; u < DP_UNROLL; ++u) acc[u] = make_float4(0.f, 0.f, 0.f, 0.f);
       for (int q = 0; q < world; ++q) {                             // fixed order: identical sums whatever the launch geometry
-        const float4 v = ld_peer(grads.p[q] + base + 4 * i);
-        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+        float4 v[DP_UNROLL];
+#pragma unroll
+        for (int u = 0; u < DP_UNROLL; ++u)
+          v[u] = (i0 + u * stride < len4) ? ld_peer(grads.p[q] + base + 4 * (i0 + u * stride)) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int u = 0; u < DP_UNROLL; ++u) { acc[u].x += v[u].x; acc[u].y += v[u].y; acc[u].z += v[u].z; acc[u].w += v[u].w; }
       }
     }
-    reinterpret_cast<float4*>(gsum)[i] = acc;
-    s = fmaf(acc.x, acc.x, s); s = fmaf(acc.y, acc.y, s); s = fmaf(acc.z, acc.z, s); s = fmaf(acc.w, acc.w, s);
+#pragma unroll
+    for (int u = 0; u < DP_UNROLL; ++u)
+      if (i0 + u * stride < len4) {
+        reinterpret_cast<float4*>(gsum)[i0 + u * stride] = acc[u];
+        s = fmaf(acc[u].x, acc[u].x, s); s = fmaf(acc[u].y, acc[u].y, s); s = fmaf(acc[u].z, acc[u].z, s); s = fmaf(acc[u].w, acc[u].w, s);
+      }
   }
   if (blockIdx.x == 0)
     for (long long i = len4 * 4 + threadIdx.x; i < len; i += blockDim.x) {
@@ -106,16 +154,21 @@ __global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, Dp
 #pragma unroll
     for (int w = 0; w < 8; ++w) tot += ws[w];
     for (int q = 0; q < world; ++q) slots.p[q][rank] = tot;         // slot `rank` of every peer
-    __threadfence_system();
     dp_ticket = 0;
+    dp_signal(flags, 1, world, rank, epoch);                        // (fence inside) every read of the peers' gradients has completed
   }
 }
 
+// waits for phase 1 of every rank, updates shard `rank`, writes it into every rank's parameter arena, last block signals phase 2
 __global__ void __launch_bounds__(256)
-dp_adam_allgather_kernel(DpPtrs params, float* __restrict__ mc_params, int world, int rank, long long n, long long shard, const float* __restrict__ gsum, float* __restrict__ m,
-                         float* __restrict__ v, float lr, float beta1, float beta2, float eps, const int* __restrict__ step_dev,
-                         const float* slots_local, float clip_norm, float grad_scale) {
+dp_adam_allgather_kernel(DpPtrs params, DpFlags flags, float* __restrict__ mc_params, const unsigned* __restrict__ epoch_dev, int world, int rank,
+                         long long n, long long shard, const float* __restrict__ gsum, float* __restrict__ m, float* __restrict__ v, float lr,
+                         float beta1, float beta2, float eps, const int* __restrict__ step_dev, const float* slots_local, float clip_norm,
+                         float grad_scale) {
   sg_pdl_sync();
+  const unsigned epoch = *epoch_dev;
+  if (threadIdx.x == 0) dp_wait(flags.p[rank], 1, world, epoch);
+  __syncthreads();
   const long long base = (long long)rank * shard;
   const long long len = max(0LL, min(shard, n - base));
   const int t = *step_dev;
@@ -141,16 +194,30 @@ dp_adam_allgather_kernel(DpPtrs params, float* __restrict__ mc_params, int world
     pi -= step_size * (mi / (sqrtf(vi) * inv_sqrt_bc2 + eps));
   };
   const long long len4 = len / 4;
-  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < len4; i += (long long)gridDim.x * blockDim.x) {
-    const float4 g4 = reinterpret_cast<const float4*>(gsum)[i];
-    float4 p4 = reinterpret_cast<float4*>(mine)[i], m4 = reinterpret_cast<float4*>(ms)[i], v4 = reinterpret_cast<float4*>(vs)[i];
-    upd(g4.x, p4.x, m4.x, v4.x); upd(g4.y, p4.y, m4.y, v4.y); upd(g4.z, p4.z, m4.z, v4.z); upd(g4.w, p4.w, m4.w, v4.w);
-    reinterpret_cast<float4*>(ms)[i] = m4;
-    reinterpret_cast<float4*>(vs)[i] = v4;
-    if (mc_params) st_mc(mc_params + base + 4 * i, p4);                                         // one store, every rank's arena
-    else {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i0 = blockIdx.x * (long long)blockDim.x + threadIdx.x; i0 < len4; i0 += 2 * stride) {
+    float4 g4[2], p4[2], m4[2], v4[2];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i < len4) {
+        g4[u] = reinterpret_cast<const float4*>(gsum)[i];
+        p4[u] = reinterpret_cast<float4*>(mine)[i]; m4[u] = reinterpret_cast<float4*>(ms)[i]; v4[u] = reinterpret_cast<float4*>(vs)[i];
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const long long i = i0 + u * stride;
+      if (i >= len4) continue;
+      upd(g4[u].x, p4[u].x, m4[u].x, v4[u].x); upd(g4[u].y, p4[u].y, m4[u].y, v4[u].y);
+      upd(g4[u].z, p4[u].z, m4[u].z, v4[u].z); upd(g4[u].w, p4[u].w, m4[u].w, v4[u].w);
+      reinterpret_cast<float4*>(ms)[i] = m4[u];
+      reinterpret_cast<float4*>(vs)[i] = v4[u];
+      if (mc_params) st_mc(mc_params + base + 4 * i, p4[u]);                                      // one store, every rank's arena
+      else {
 #pragma unroll 8
-      for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(params.p[q] + base)[i] = p4;    // my shard of every rank's arena
+        for (int q = 0; q < world; ++q) reinterpret_cast<float4*>(params.p[q] + base)[i] = p4[u]; // my shard of every rank's arena
+      }
     }
   }
   if (blockIdx.x == 0)
@@ -161,37 +228,70 @@ dp_adam_allgather_kernel(DpPtrs params, float* __restrict__ mc_params, int world
       vs[i] = vi;
       for (int q = 0; q < world; ++q) params.p[q][base + i] = pi;
     }
+  // every block fences its peer stores, the last one tells every rank that shard `rank` of its parameter arena is written
   __threadfence_system();
+  __shared__ bool last;
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(&dp_ticket2, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x == 0) {
+    dp_ticket2 = 0;
+    dp_signal(flags, 2, world, rank, epoch);
+  }
+}
+
+// closes the exchange: every shard of my parameter arena has been written (phase 2 of every rank); advances the epoch
+__global__ void dp_finish_kernel(const unsigned* mine, unsigned* epoch_dev, int world) {
+  sg_pdl_sync();
+  if (threadIdx.x == 0) {
+    const unsigned epoch = *epoch_dev;
+    dp_wait(mine, 2, world, epoch);
+    *epoch_dev = epoch + 1;
+  }
 }
 
 extern "C" {
 
-int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const float* mc_grads, int world, int rank,
-                             long long n, long long shard, float* gsum, void* stream) {
+int subgnn_dp_flag_words(void) { return 3 * DP_MAX_WORLD; }
+
+int subgnn_dp_reduce_scatter(const unsigned long long* peer_grads, const unsigned long long* peer_slots, const unsigned long long* peer_flags,
+                             const float* mc_grads, const unsigned* epoch_dev, int world, int rank, long long n, long long shard, float* gsum,
+                             void* stream) {
   SG_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "bad world / rank");
   SG_REQUIRE(shard > 0 && (shard % 4) == 0 && shard * world >= n, "shard must be a multiple of 4 floats covering the arena");
   DpPtrs g, s;
+  DpFlags f;
   for (int q = 0; q < DP_MAX_WORLD; ++q) {
     g.p[q] = q < world ? reinterpret_cast<float*>(peer_grads[q]) : nullptr;
     s.p[q] = q < world ? reinterpret_cast<float*>(peer_slots[q]) : nullptr;
+    f.p[q] = q < world ? reinterpret_cast<unsigned*>(peer_flags[q]) : nullptr;
   }
-  int grid = sg_grid_for(shard / 4, 256, 4);
+  int grid = sg_grid_for(shard / 4, 256 * DP_UNROLL, 2);             // every block resident: waiting blocks cannot starve signalling ones
   if (grid > DP_MAX_BLOCKS) grid = DP_MAX_BLOCKS;
-  sg_launch_pdl<SG_PDL_CHAIN>(dp_reduce_scatter_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g, s, mc_grads, world, rank, n, shard, gsum);
+  sg_launch_pdl<SG_PDL_CHAIN>(dp_reduce_scatter_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, g, s, f, mc_grads, epoch_dev, world, rank, n,
+                              shard, gsum);
   return subgnn_check_launch("dp_reduce_scatter_kernel");
 }
 
-int subgnn_dp_adam_allgather(const unsigned long long* peer_params, float* mc_params, int world, int rank, long long n, long long shard, const float* gsum, float* m,
-                             float* v, float lr, float beta1, float beta2, float eps, const int* step_dev, const float* slots_local,
-                             float clip_norm, float grad_scale, void* stream) {
+int subgnn_dp_adam_allgather(const unsigned long long* peer_params, const unsigned long long* peer_flags, float* mc_params, unsigned* epoch_dev, int world,
+                             int rank, long long n, long long shard, const float* gsum, float* m, float* v, float lr, float beta1, float beta2,
+                             float eps, const int* step_dev, const float* slots_local, float clip_norm, float grad_scale, void* stream) {
   SG_REQUIRE(world >= 1 && world <= DP_MAX_WORLD && rank >= 0 && rank < world, "bad world / rank");
   SG_REQUIRE(shard > 0 && (shard % 4) == 0 && shard * world >= n, "shard must be a multiple of 4 floats covering the arena");
   DpPtrs p;
-  for (int q = 0; q < DP_MAX_WORLD; ++q) p.p[q] = q < world ? reinterpret_cast<float*>(peer_params[q]) : nullptr;
-  int grid = sg_grid_for(shard / 4, 256, 4);
-  sg_launch_pdl<SG_PDL_CHAIN>(dp_adam_allgather_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, mc_params, world, rank, n, shard, gsum, m, v, lr, beta1,
-                              beta2, eps, step_dev, slots_local, clip_norm, grad_scale);
-  return subgnn_check_launch("dp_adam_allgather_kernel");
+  DpFlags f;
+  for (int q = 0; q < DP_MAX_WORLD; ++q) {
+    p.p[q] = q < world ? reinterpret_cast<float*>(peer_params[q]) : nullptr;
+    f.p[q] = q < world ? reinterpret_cast<unsigned*>(peer_flags[q]) : nullptr;
+  }
+  int grid = sg_grid_for(shard / 4, 256 * 2, 2);
+  if (grid > DP_MAX_BLOCKS) grid = DP_MAX_BLOCKS;
+  sg_launch_pdl<SG_PDL_CHAIN>(dp_adam_allgather_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, f, mc_params, (const unsigned*)epoch_dev, world, rank,
+                              n, shard, gsum, m, v, lr, beta1, beta2, eps, step_dev, slots_local, clip_norm, grad_scale);
+  int rc = subgnn_check_launch("dp_adam_allgather_kernel");
+  if (rc) return rc;
+  sg_launch_pdl<SG_PDL_CHAIN>(dp_finish_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const unsigned*)f.p[rank], epoch_dev, world);
+  return subgnn_check_launch("dp_finish_kernel");
 }
 
 }  // extern "C"

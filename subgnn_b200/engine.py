@@ -483,8 +483,9 @@ class LstmRunner:
 class DpExchange:
     """Gradient exchange + optimizer over NVLink peer memory (csrc/dp.cu): symmetric gradient / parameter arenas
     (torch.distributed._symmetric_memory maps every peer's allocation into this process), reduce-scatter of the gradient shards by
-    direct peer loads, sharded Adam, all-gather of the updated parameters by direct peer stores, cross-GPU barriers on the signal
-    pads in between.  Replaces the NCCL all-reduce + two optimizer kernels of the data-parallel step."""
+    direct peer loads (or one in-switch multimem.ld_reduce), sharded Adam, all-gather of the updated parameters by direct peer stores
+    (or one multimem.st), cross-GPU barriers inside the kernels (epoch flags in a symmetric array).  Replaces the NCCL all-reduce +
+    two optimizer kernels of the data-parallel step."""
 
     @staticmethod
     def allocator(device):
@@ -503,11 +504,16 @@ class DpExchange:
         self.n = arena.size
         self.shard = _align((self.n + world - 1) // world)
         self.slots = symm.empty(max(world, 4), dtype=torch.float32, device=torch.device(device)).zero_()
+        self.flags = symm.empty(int(_abi.lib.subgnn_dp_flag_words()), dtype=torch.int32, device=torch.device(device)).zero_()
+        self.epoch = torch.ones(1, dtype=torch.int32, device=torch.device(device))      # advanced by the closing kernel of every exchange
         group = dist.group.WORLD
         self.h_g, self.h_p, self.h_s = symm.rendezvous(arena.grads, group), symm.rendezvous(arena.params, group), symm.rendezvous(self.slots, group)
+        self.h_f = symm.rendezvous(self.flags, group)
         assert int(self.h_g.buffer_ptrs[rank]) == arena.grads.data_ptr() and int(self.h_p.buffer_ptrs[rank]) == arena.params.data_ptr()
         tab = lambda h: (C.c_ulonglong * world)(*[int(x) for x in h.buffer_ptrs])
-        self.pg, self.pp, self.ps = tab(self.h_g), tab(self.h_p), tab(self.h_s)
+        self.pg, self.pp, self.ps, self.pf = tab(self.h_g), tab(self.h_p), tab(self.h_s), tab(self.h_f)
+        torch.cuda.synchronize()
+        dist.barrier()                                 # every rank's flag array is zeroed before anyone signals into it
         self.gsum = torch.zeros(self.shard, dtype=torch.float32, device=torch.device(device))
         self.arena = arena
         # NVLS multicast mappings (in-switch reduction / broadcast) when the fabric offers them; SUBGNN_DP_MULTICAST=0: per-peer loads / stores
@@ -525,12 +531,11 @@ class DpExchange:
 
     def step(self, lr, step_dev, clip, st):
         a = self.arena
-        self.h_g.barrier(channel=0)                    # every rank's gradient arena is complete
-        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.mc_g, self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
-        self.h_g.barrier(channel=1)                    # shard sums of squares published; peers are done reading my gradients
-        call('subgnn_dp_adam_allgather', self.pp, self.mc_p, self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m), ptr(a.v), lr, 0.9, 0.999,
-             1e-8, ptr(step_dev), ptr(self.slots), clip, 1.0 / self.world, st)
-        self.h_g.barrier(channel=2)                    # every shard of my parameter arena has been written
+        # the cross-GPU barriers are inside the kernels: "gradients complete" opens the first, "shard reduced" the second, and the
+        # closing kernel of the second entry point waits until every shard of my parameter arena has been written
+        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.pf, self.mc_g, ptr(self.epoch), self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
+        call('subgnn_dp_adam_allgather', self.pp, self.pf, self.mc_p, ptr(self.epoch), self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m),
+             ptr(a.v), lr, 0.9, 0.999, 1e-8, ptr(step_dev), ptr(self.slots), clip, 1.0 / self.world, st)
 
     def gather_moments(self):
         """full Adam moments on every rank (checkpoints): each rank holds only its own shard"""

@@ -113,7 +113,7 @@ def test_cluster_readout_kernel_matches_default_path(name, monkeypatch):
     for losses, sd in states[1:]:
         np.testing.assert_allclose(losses, states[0][0], rtol=1e-5)
         for k in sd:
-            np.testing.assert_allclose(sd[k], states[0][1][k], rtol=1e-4, atol=1e-6, err_msg=k)
+            np.testing.assert_allclose(sd[k], states[0][1][k], rtol=1e-4, atol=1e-5, err_msg=k)
 
 
 @pytest.mark.parametrize('name', ['density', 'ppi_bp'])
@@ -137,4 +137,4 @@ def test_split_readout_schedule_takes_the_same_steps(name, monkeypatch):
         states.append((losses, {k: v.cpu().numpy().copy() for k, v in eng.arena.state_dict().items()}))
     np.testing.assert_allclose(states[0][0], states[1][0], rtol=1e-5)
     for k in states[0][1]:
-        np.testing.assert_allclose(states[0][1][k], states[1][1][k], rtol=1e-4, atol=1e-6, err_msg=k)
+        np.testing.assert_allclose(states[0][1][k], states[1][1][k], rtol=1e-4, atol=1e-5, err_msg=k)
