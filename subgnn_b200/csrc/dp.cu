@@ -5,7 +5,7 @@
 // all-reduce (NCCL) -> sum of squares -> Adam: the 4 flat arenas streamed three times and a library collective between two
 // graph halves.  Here the gradient arenas of all ranks are SYMMETRIC allocations (torch.distributed._symmetric_memory: every rank
 // maps every peer's arena), and the exchange is two kernels with the cross-GPU barriers inside them (epoch flags in symmetric
-// memory: release stores into the peers' flag arrays, acquire loads of the own one — no barrier launches on the chain):
+// memory: a system fence + flag stores into the peers' flag arrays, polls of the own one + a system fence — no barrier launches):
 //
 //   dp_reduce_scatter_kernel   rank r sums shard r of the gradient arena over all peers (16-byte loads straight from the peers'
 //                              HBM through NVLink / NVSwitch, fixed summation order), keeps the sum in a local shard buffer and
@@ -62,20 +62,17 @@ __device__ __forceinline__ void st_mc(float* p, const float4 v) {
 // wait = acquire loads of my own array until every sender's slot has reached the epoch.  A waiter spins for at most ~10 s
 // (a lost peer traps the kernel instead of hanging the GPU).
 __device__ __forceinline__ void dp_signal(const DpFlags& f, int phase, int world, int rank, unsigned epoch) {
-  __threadfence_system();
-  for (int q = 0; q < world; ++q)
-    asm volatile("st.release.sys.global.u32 [%0], %1;" :: "l"(f.p[q] + phase * DP_MAX_WORLD + rank), "r"(epoch) : "memory");
+  __threadfence_system();                                            // ONE fence, then plain (volatile) flag stores: a release store per
+  for (int q = 0; q < world; ++q)                                    // peer would drain the fabric `world` times in a row
+    *reinterpret_cast<volatile unsigned*>(f.p[q] + phase * DP_MAX_WORLD + rank) = epoch;
 }
 __device__ __forceinline__ void dp_wait(const unsigned* mine, int phase, int world, unsigned epoch) {
   const long long t0 = clock64();
   for (int q = 0; q < world; ++q) {
-    unsigned v = 0;
-    while (true) {
-      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(mine + phase * DP_MAX_WORLD + q) : "memory");
-      if ((int)(v - epoch) >= 0) break;
+    while ((int)(*reinterpret_cast<volatile const unsigned*>(mine + phase * DP_MAX_WORLD + q) - epoch) < 0)
       if (clock64() - t0 > 20000000000ll) __trap();                 // ~10 s: a peer is gone
-    }
   }
+  __threadfence_system();                                            // acquire: the data the flags announce is visible to what follows
 }
 
 // phase 0: "my gradient arena is complete" (signalled by the first block, which runs after every kernel of my backward pass);
