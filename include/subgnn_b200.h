@@ -337,6 +337,8 @@ int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
  *                   advances *epoch_dev.
  * Cross-GPU synchronisation: peer_flags[q] -> rank q's symmetric flag array of subgnn_dp_flag_words() 32-bit words (zero-initialised),
  * *epoch_dev (device counter, starts at 1, advanced once per exchange identically on every rank) is the value signalled.
+ * epoch_dev == NULL: no synchronisation inside the kernels — the caller brackets them with its own cross-GPU barriers (before
+ * reduce_scatter, between the two, after adam_allgather).
  * Together: the averaged-gradient Adam step of SubGNN.py:1156-1164 under data parallelism, with sharded optimizer state.
  * mc_grads / mc_params (may be NULL): NVLS multicast mappings of the two arenas — the shard sum becomes one multimem.ld_reduce per
  * 16 bytes (reduced inside the NVSwitch), the parameter broadcast one multimem.st. */

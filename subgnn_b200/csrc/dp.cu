@@ -81,12 +81,15 @@ __global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, Dp
                                                                const unsigned* __restrict__ epoch_dev, int world, int rank, long long n, long long shard,
                                                                float* __restrict__ gsum) {
   sg_pdl_sync();
-  const unsigned epoch = *epoch_dev;
-  if (threadIdx.x == 0) {
-    if (blockIdx.x == 0) dp_signal(flags, 0, world, rank, epoch);
-    dp_wait(flags.p[rank], 0, world, epoch);
+  const bool sync = epoch_dev != nullptr;                           // nullptr: the caller brackets the kernels with its own cross-GPU barriers
+  const unsigned epoch = sync ? *epoch_dev : 0u;
+  if (sync) {
+    if (threadIdx.x == 0) {
+      if (blockIdx.x == 0) dp_signal(flags, 0, world, rank, epoch);
+      dp_wait(flags.p[rank], 0, world, epoch);
+    }
+    __syncthreads();
   }
-  __syncthreads();
   const long long base = (long long)rank * shard;
   const long long len = max(0LL, min(shard, n - base));            // elements of my shard (multiple of 4 except at the arena's end)
   const long long len4 = len / 4;
@@ -152,7 +155,8 @@ __global__ void __launch_bounds__(256) dp_reduce_scatter_kernel(DpPtrs grads, Dp
     for (int w = 0; w < 8; ++w) tot += ws[w];
     for (int q = 0; q < world; ++q) slots.p[q][rank] = tot;         // slot `rank` of every peer
     dp_ticket = 0;
-    dp_signal(flags, 1, world, rank, epoch);                        // (fence inside) every read of the peers' gradients has completed
+    if (sync) dp_signal(flags, 1, world, rank, epoch);              // (fence inside) every read of the peers' gradients has completed
+    else __threadfence_system();
   }
 }
 
@@ -163,9 +167,12 @@ dp_adam_allgather_kernel(DpPtrs params, DpFlags flags, float* __restrict__ mc_pa
                          float beta1, float beta2, float eps, const int* __restrict__ step_dev, const float* slots_local, float clip_norm,
                          float grad_scale) {
   sg_pdl_sync();
-  const unsigned epoch = *epoch_dev;
-  if (threadIdx.x == 0) dp_wait(flags.p[rank], 1, world, epoch);
-  __syncthreads();
+  const bool sync = epoch_dev != nullptr;
+  const unsigned epoch = sync ? *epoch_dev : 0u;
+  if (sync) {
+    if (threadIdx.x == 0) dp_wait(flags.p[rank], 1, world, epoch);
+    __syncthreads();
+  }
   const long long base = (long long)rank * shard;
   const long long len = max(0LL, min(shard, n - base));
   const int t = *step_dev;
@@ -227,6 +234,7 @@ dp_adam_allgather_kernel(DpPtrs params, DpFlags flags, float* __restrict__ mc_pa
     }
   // every block fences its peer stores, the last one tells every rank that shard `rank` of its parameter arena is written
   __threadfence_system();
+  if (!sync) return;
   __shared__ bool last;
   __syncthreads();
   if (threadIdx.x == 0) last = atomicAdd(&dp_ticket2, 1u) == gridDim.x - 1;
@@ -286,7 +294,7 @@ int subgnn_dp_adam_allgather(const unsigned long long* peer_params, const unsign
   sg_launch_pdl<SG_PDL_CHAIN>(dp_adam_allgather_kernel, dim3(grid), dim3(256), 0, (cudaStream_t)stream, p, f, mc_params, (const unsigned*)epoch_dev, world, rank,
                               n, shard, gsum, m, v, lr, beta1, beta2, eps, step_dev, slots_local, clip_norm, grad_scale);
   int rc = subgnn_check_launch("dp_adam_allgather_kernel");
-  if (rc) return rc;
+  if (rc || !epoch_dev) return rc;
   sg_launch_pdl<SG_PDL_CHAIN>(dp_finish_kernel, dim3(1), dim3(32), 0, (cudaStream_t)stream, (const unsigned*)f.p[rank], epoch_dev, world);
   return subgnn_check_launch("dp_finish_kernel");
 }

@@ -516,9 +516,10 @@ class DpExchange:
         dist.barrier()                                 # every rank's flag array is zeroed before anyone signals into it
         self.gsum = torch.zeros(self.shard, dtype=torch.float32, device=torch.device(device))
         self.arena = arena
+        self.in_kernel_barrier = os.environ.get('SUBGNN_DP_BARRIER', 'torch') == 'kernel'
         # NVLS multicast mappings (in-switch reduction / broadcast) when the fabric offers them; SUBGNN_DP_MULTICAST=0: per-peer loads / stores
         self.mc_g = self.mc_p = None
-        if _flag('SUBGNN_DP_MULTICAST', True):
+        if _flag('SUBGNN_DP_MULTICAST', world > 2):
             try:
                 mg, mp = int(self.h_g.multicast_ptr or 0), int(self.h_p.multicast_ptr or 0)      # 0: the fabric / driver offers no multicast
                 if mg and mp:
@@ -531,11 +532,20 @@ class DpExchange:
 
     def step(self, lr, step_dev, clip, st):
         a = self.arena
-        # the cross-GPU barriers are inside the kernels: "gradients complete" opens the first, "shard reduced" the second, and the
-        # closing kernel of the second entry point waits until every shard of my parameter arena has been written
-        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.pf, self.mc_g, ptr(self.epoch), self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
-        call('subgnn_dp_adam_allgather', self.pp, self.pf, self.mc_p, ptr(self.epoch), self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m),
+        # cross-GPU barriers: symmetric-memory signal-pad barriers (1-warp kernels) around the two exchange kernels, or
+        # (SUBGNN_DP_BARRIER=kernel) epoch flags inside the kernels.  Measured (tools/dp_bench.py): 2 GPUs 46.6 vs 50.3 us per exchange,
+        # 8 GPUs: flags polled by every block of 8 ranks are slower still (78 - 110 us) — the barrier kernels stay the default
+        in_kernel = self.in_kernel_barrier
+        ep = ptr(self.epoch) if in_kernel else None
+        if not in_kernel:
+            self.h_g.barrier(channel=0)                # every rank's gradient arena is complete
+        call('subgnn_dp_reduce_scatter', self.pg, self.ps, self.pf, self.mc_g, ep, self.world, self.rank, self.n, self.shard, ptr(self.gsum), st)
+        if not in_kernel:
+            self.h_g.barrier(channel=1)                # shard sums of squares published; peers are done reading my gradients
+        call('subgnn_dp_adam_allgather', self.pp, self.pf, self.mc_p, ep, self.world, self.rank, self.n, self.shard, ptr(self.gsum), ptr(a.m),
              ptr(a.v), lr, 0.9, 0.999, 1e-8, ptr(step_dev), ptr(self.slots), clip, 1.0 / self.world, st)
+        if not in_kernel:
+            self.h_g.barrier(channel=2)                # every shard of my parameter arena has been written
 
     def gather_moments(self):
         """full Adam moments on every rank (checkpoints): each rank holds only its own shard"""

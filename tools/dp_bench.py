@@ -37,14 +37,19 @@ def main():
     dist.all_reduce(torch.zeros(1, device=dev))
     res = {}
     for mc in (0, 1):
-        os.environ['SUBGNN_DP_MULTICAST'] = str(mc)
-        dp = DpExchange(a, world, rank, dev)
-        pieces = {
-            'torch symm-mem barrier (for scale)': lambda st: dp.h_g.barrier(channel=0),
-            'whole exchange': lambda st: dp.step(1e-3, step_dev, 0.2, st),
-        }
-        for name, fn in pieces.items():
-            res['%s (multicast %s)' % (name, 'on' if dp.mc_g else 'off')] = timeit(fn)
+        for bar in ('torch', 'kernel'):
+            os.environ['SUBGNN_DP_MULTICAST'] = str(mc)
+            os.environ['SUBGNN_DP_BARRIER'] = bar
+            dp = DpExchange(a, world, rank, dev)
+            res['whole exchange (multicast %s, %s barriers)' % ('on' if dp.mc_g else 'off', 'signal-pad kernel' if bar == 'torch' else 'in-kernel flag')] = \
+                timeit(lambda st: dp.step(1e-3, step_dev, 0.2, st))
+            if mc == 0 and bar == 'torch':
+                res['  one signal-pad barrier'] = timeit(lambda st: dp.h_g.barrier(channel=0))
+                res['  reduce_scatter kernel alone (unsynchronised)'] = timeit(lambda st: call('subgnn_dp_reduce_scatter', dp.pg, dp.ps, dp.pf, dp.mc_g, None, world, rank, n,
+                                                                                                dp.shard, ptr(dp.gsum), st))
+                res['  adam_allgather kernel alone (unsynchronised)'] = timeit(lambda st: call('subgnn_dp_adam_allgather', dp.pp, dp.pf, dp.mc_p, None, world, rank, n, dp.shard,
+                                                                                                ptr(dp.gsum), ptr(a.m), ptr(a.v), 1e-3, 0.9, 0.999, 1e-8, ptr(step_dev),
+                                                                                                ptr(dp.slots), 0.2, 1.0 / world, st))
     nccl = {
         'nccl all_reduce': lambda st: dist.all_reduce(a.grads),
         'sumsq + adam (local)': lambda st: (call('subgnn_grad_sumsq', ptr(a.grads), n, ptr(sumsq), st),
@@ -56,7 +61,7 @@ def main():
     if rank == 0:
         print('world %d, arena %d floats (%.1f MB), shard %.2f MB' % (world, n, 4e-6 * n, 4e-6 * n / world))
         for k, v in res.items():
-            print('  %-42s %7.1f us' % (k, v))
+            print('  %-72s %7.1f us' % (k, v))
     dist.barrier()
     dist.destroy_process_group()
 
