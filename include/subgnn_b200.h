@@ -141,6 +141,8 @@ int subgnn_tc_linear_bwd_weight(const float* dy, int ldy, const float* x, int ld
  *   SUBGNN_GEMM_BWD_WEIGHT_SHIFT  out[N][K]     += sum_m a[m][N]^T . b[m + shift][K] over the rows with (m % period) != (shift < 0 ? 0 :
  *                                 period - 1): the recurrent-weight gradient dW_hh = sum_t dG_t^T h_(t-1) of nn.LSTM (SubGNN.py:73)
  *                                 for sequences of `period` steps stored row after row (shift = -1 forward, +1 reverse direction).
+ * accumulate (BWD_INPUT without scatter_ids): 0 = store, 1 = add onto the destination (read-add-store; one writer per element),
+ * 2 = add with atomics (another problem of the same group adds into the same rows; the destination must hold the initial value).
  * max_ctas > 0 caps the grid (a companion launch leaves the other SMs to the kernel on the critical chain). */
 #define SUBGNN_GEMM_FWD 0
 #define SUBGNN_GEMM_BWD_INPUT 1
@@ -305,8 +307,11 @@ int subgnn_model_mlp_bwd(const subgnn_model_desc* d, void* stream);
 int subgnn_model_q_bwd(const subgnn_model_desc* d, void* stream);          /* == q_bwd_part(POS | STRUC) */
 /* backward of q = w_p . x per anchor list: SUBGNN_Q_STRUC -> d emb_s (feeds the LSTM head gradient), SUBGNN_Q_POS -> rows of dE */
 int subgnn_model_q_bwd_part(const subgnn_model_desc* d, int which, void* stream);
-/* weight gradients of the N-channel MPN projections and the MLP */
+/* weight gradients of the N-channel MPN projections and (unless d->mlp_fused says they are produced elsewhere) the MLP */
 int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream);
+/* the MLP's weight / bias gradients alone (dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2: SubGNN.py:303-310 backward): ready as soon
+ * as the readout section has run, so a caller can launch them beside the backward chain and set mlp_fused for subgnn_model_wgrad */
+int subgnn_model_mlp_wgrad(const subgnn_model_desc* d, void* stream);
 
 /* ---- stand-alone SG_MPN.forward (mpn.cu): subgraph_mpn.py:36-131,176-231 on the reference's materialised inputs ----
  * cc (R x D), anchor_embeds (R x A x D), sims (R x n_opt), mask (R x A, uint8).  Exactly one of anchor_ids (R x A: first node id
@@ -324,6 +329,10 @@ int subgnn_grad_sumsq(const float* g, long long n, float* out_sumsq /* [1], accu
 int subgnn_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
                      const int* step_dev /* [1] step count t >= 1 */, const float* sumsq_dev, float clip_norm, float grad_scale,
                      void* stream);
+/* both of the above in one launch (one CTA per SM, grid barrier between the norm and the update): sumsq_dev (may be NULL) is
+ * ACCUMULATED like subgnn_grad_sumsq's output; clip_norm <= 0 disables clipping */
+int subgnn_clip_adam_step(float* p, const float* g, float* m, float* v, long long n, float lr, float beta1, float beta2, float eps,
+                          const int* step_dev, float* sumsq_dev, float clip_norm, float grad_scale, void* stream);
 int subgnn_sum_to_scalar(const float* x, int n, float* out, void* stream);
 
 /* ---- data-parallel exchange fused with the optimizer (dp.cu) ------------------------------------------------------------------

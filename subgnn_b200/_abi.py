@@ -68,11 +68,13 @@ SIGNATURES = {
     'subgnn_model_q_bwd': [P, P],
     'subgnn_model_q_bwd_part': [P, I, P],
     'subgnn_model_wgrad': [P, P],
+    'subgnn_model_mlp_wgrad': [P, P],
     'subgnn_mpn_fwd': [P, P, P, I, P, P, P, P, P, P, P, P, I, I, I, P],
     'subgnn_mpn_bwd': [P, P, P, P, P, P, P, P, I, I, I, P],
     'subgnn_fill_zero': [P, LL, P],
     'subgnn_grad_sumsq': [P, LL, P, P],
     'subgnn_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],
+    'subgnn_clip_adam_step': [P, P, P, P, LL, F, F, F, F, P, P, F, F, P],
     'subgnn_sum_to_scalar': [P, I, P, P],
     'subgnn_dp_reduce_scatter': [P, P, P, P, P, I, I, LL, LL, P, P],
     'subgnn_dp_adam_allgather': [P, P, P, P, I, I, LL, LL, P, P, P, F, F, F, F, P, P, F, F, P],

@@ -301,14 +301,19 @@ __device__ void mlp_backward(const Desc& d, int b, float* dzs, float* work) {
 }
 
 // ------------------------------------------------------------------------------------------------
-// ROW kernels: one CTA per connected component (row) of the batch, 8 warps cooperate on it:
-// warps 0-3 own the internal side, warps 4-7 the border side of the N channel; inside a side the four warps
-// split the anchor gathers (16 independent row gathers in flight per side) and the 2D x D projection.
+// ROW kernels: one CTA per connected component (row) of the batch, ROW_THREADS / 32 warps cooperate on it:
+// the first half of the warps owns the internal side, the second half the border side of the N channel; inside a side the warps
+// split the anchor gathers (8 independent row gathers in flight per warp) and the 2D x D projection.
 // The subgraph readout is a global atomicAdd into Z[b] (zeroed every step); the per-sample MLP is its own
 // small kernel (grid = B) after all rows are done.
-#define ROW_THREADS 256
-#define SIDE_THREADS 128
-#define SIDE_WARPS 4
+// [r2] two widths, chosen per launch from the row capacity (row_width): 16 warps per row (8 per side) when all rows of the batch fit the
+// GPU in one wave — the anchor gathers of a layer are ONE batch of 8 rows in flight per warp instead of two, the 2D-long projection
+// reductions are split four ways: the row's dependent chain is shorter — and 8 warps per row when rows outnumber the CTA slots
+// (throughput: more rows resident per SM).  Measured on B200, same box, 256 against 512 threads: PPI-BP shape 0.3163 -> 0.3077
+// ms/step (100 steps), density 0.166 -> 0.153, HPO-METAB 0.654 -> 0.645; the whole train split as one batch (R ~ 8 k rows):
+// 2.03 -> 2.29 ms with 512 — hence the choice by capacity.
+#define ROW_WIDE 512
+#define ROW_NARROW 256
 
 struct RowSmem {
   float* x0;      // [D]
@@ -319,7 +324,7 @@ struct RowSmem {
   float* partl;   // [L][2][SIDE_WARPS][D]  their per-warp partials
 };
 
-__device__ __forceinline__ RowSmem row_smem(float* sm, int D, int L) {
+__device__ __forceinline__ RowSmem row_smem(float* sm, int D, int L, int SIDE_WARPS) {
   RowSmem r;
   r.x0 = sm;
   r.h = r.x0 + D;
@@ -329,17 +334,19 @@ __device__ __forceinline__ RowSmem row_smem(float* sm, int D, int L) {
   r.partl = r.aggl + (size_t)L * 2 * D;
   return r;
 }
-static size_t row_smem_bytes(int D, int L) {
+static size_t row_smem_bytes(int D, int L, int row_threads) {
+  const int SIDE_WARPS = row_threads / 64;
   return (size_t)(D + 2 * D + 4 * D + 2 * SIDE_WARPS * D + L * 2 * D + L * 2 * SIDE_WARPS * D + 16) * sizeof(float);
 }
 
 // phases: bit 0 = pooling + neighbourhood channel, bit 1 = position / structure property-aware outputs (needs q)
-template <int DPL>
-__global__ void __launch_bounds__(ROW_THREADS) row_fwd_kernel(Desc d, int phases) {
+template <int DPL, int RT>
+__global__ void __launch_bounds__(RT, RT > 256 ? 2 : (DPL <= 2 ? 4 : 2)) row_fwd_kernel(Desc d, int phases) {   // <= 64 registers (<= 128: narrow, D > 64)
+  constexpr int ROW_THREADS = RT, SIDE_THREADS = RT / 2, SIDE_WARPS = RT / 64;
   sg_pdl_sync();
   extern __shared__ float sm[];
   const int D = d.D;
-  const RowSmem S = row_smem(sm, D, d.L);
+  const RowSmem S = row_smem(sm, D, d.L, SIDE_WARPS);
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int side = warp / SIDE_WARPS, sw = warp % SIDE_WARPS, st = tid % SIDE_THREADS;
   const int R = d.meta[0], maxlen = d.meta[1];
@@ -1018,8 +1025,9 @@ __global__ void __launch_bounds__(RO_THREADS) readout_cluster_kernel(Desc d) {
   RO_TR(9);
 }
 
-template <int DPL>
-__global__ void __launch_bounds__(ROW_THREADS) row_bwd_kernel(Desc d, int phases) {
+template <int DPL, int RT>
+__global__ void __launch_bounds__(RT) row_bwd_kernel(Desc d, int phases) {
+  constexpr int ROW_THREADS = RT, SIDE_THREADS = RT / 2, SIDE_WARPS = RT / 64;
   sg_pdl_sync();
   extern __shared__ float sm[];
   const int D = d.D;
@@ -1217,14 +1225,36 @@ static int check_desc(const Desc* d) {
   return SUBGNN_OK;
 }
 
-#define DISPATCH_DPL(D, KERNEL, ...)                                   \
-  do {                                                                 \
-    const int dpl_ = ((D) + 31) / 32;                                  \
-    subgnn_note_variant(#KERNEL "<%d>", dpl_ <= 1 ? 1 : dpl_ <= 2 ? 2 : dpl_ <= 4 ? 4 : 8);   \
-    if (dpl_ <= 1) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<1>, __VA_ARGS__); }          \
-    else if (dpl_ <= 2) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<2>, __VA_ARGS__); }     \
-    else if (dpl_ <= 4) { sg_launch_pdl<SG_PDL_ROW>(KERNEL<4>, __VA_ARGS__); }     \
-    else { sg_launch_pdl<SG_PDL_ROW>(KERNEL<8>, __VA_ARGS__); }                    \
+static int row_grid(const Desc* d);
+// 16 warps per row while every row of the batch gets a CTA slot of the wide kernel's first wave (2 per SM), else 8 (see ROW_WIDE)
+static int row_width(const Desc* d) {
+  if (const char* e = getenv("SUBGNN_ROW_THREADS")) { const int v = atoi(e); if (v == ROW_WIDE || v == ROW_NARROW) return v; }
+  return d->R_cap <= 4 * subgnn_sm_count() ? ROW_WIDE : ROW_NARROW;
+}
+
+template <int DPL, int RT>
+static void launch_row_fwd(const Desc* d, int phases, cudaStream_t st) {
+  const size_t smem = row_smem_bytes(d->D, d->L, RT);
+  if (smem > 48 * 1024)                          // deep / wide configurations: opt in to the large dynamic shared-memory window
+    cudaFuncSetAttribute(row_fwd_kernel<DPL, RT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  subgnn_note_variant("row_fwd_kernel<%d>[%d threads]", DPL, RT);
+  sg_launch_pdl<SG_PDL_ROW>(row_fwd_kernel<DPL, RT>, dim3(row_grid(d)), dim3(RT), smem, st, *d, phases);
+}
+template <int DPL, int RT>
+static void launch_row_bwd(const Desc* d, int phases, size_t smem, cudaStream_t st) {
+  subgnn_note_variant("row_bwd_kernel<%d>[%d threads]", DPL, RT);
+  sg_launch_pdl<SG_PDL_ROW>(row_bwd_kernel<DPL, RT>, dim3(row_grid(d)), dim3(RT), smem, st, *d, phases);
+}
+#define DISPATCH_ROW(D, RT, FN, ...)                                                                 \
+  do {                                                                                               \
+    const int dpl_ = ((D) + 31) / 32;                                                                \
+    if ((RT) == ROW_WIDE) {                                                                          \
+      if (dpl_ <= 1) FN<1, ROW_WIDE>(__VA_ARGS__); else if (dpl_ <= 2) FN<2, ROW_WIDE>(__VA_ARGS__); \
+      else if (dpl_ <= 4) FN<4, ROW_WIDE>(__VA_ARGS__); else FN<8, ROW_WIDE>(__VA_ARGS__);           \
+    } else {                                                                                         \
+      if (dpl_ <= 1) FN<1, ROW_NARROW>(__VA_ARGS__); else if (dpl_ <= 2) FN<2, ROW_NARROW>(__VA_ARGS__); \
+      else if (dpl_ <= 4) FN<4, ROW_NARROW>(__VA_ARGS__); else FN<8, ROW_NARROW>(__VA_ARGS__);       \
+    }                                                                                                \
   } while (0)
 
 static int row_grid(const Desc* d) {
@@ -1272,16 +1302,9 @@ int subgnn_model_rows_fwd(const subgnn_model_desc* d, int phases, void* stream) 
   if (!d->use_p) phases &= ~SUBGNN_PHASE_P;
   if (!d->use_s) phases &= ~SUBGNN_PHASE_S;
   if (!phases) return SUBGNN_OK;
-  const size_t smem = row_smem_bytes(d->D, d->L);
-  if (smem > 48 * 1024) {                       // deep / wide configurations: opt in to the large dynamic shared-memory window
-    SG_REQUIRE(smem <= 200 * 1024, "n_layers x node_embed_size too large for the row kernel's shared-memory aggregates");
-    const int dpl = (d->D + 31) / 32;
-    if (dpl <= 1) cudaFuncSetAttribute(row_fwd_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else if (dpl <= 2) cudaFuncSetAttribute(row_fwd_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else if (dpl <= 4) cudaFuncSetAttribute(row_fwd_kernel<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    else cudaFuncSetAttribute(row_fwd_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  }
-  DISPATCH_DPL(d->D, row_fwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), smem, (cudaStream_t)stream, *d, phases);
+  const int rt = row_width(d);
+  SG_REQUIRE(row_smem_bytes(d->D, d->L, rt) <= 200 * 1024, "n_layers x node_embed_size too large for the row kernel's shared-memory aggregates");
+  DISPATCH_ROW(d->D, rt, launch_row_fwd, d, phases, (cudaStream_t)stream);
   return subgnn_check_launch("row_fwd_kernel");
 }
 
@@ -1368,7 +1391,7 @@ int subgnn_model_rows_bwd(const subgnn_model_desc* d, int phases, void* stream) 
   if (!d->use_p) phases &= ~SUBGNN_PHASE_P;
   if (!d->use_s) phases &= ~SUBGNN_PHASE_S;
   if (!phases) return SUBGNN_OK;
-  DISPATCH_DPL(d->D, row_bwd_kernel, dim3(row_grid(d)), dim3(ROW_THREADS), bwd_smem(*d), (cudaStream_t)stream, *d, phases);
+  DISPATCH_ROW(d->D, row_width(d), launch_row_bwd, d, phases, bwd_smem(*d), (cudaStream_t)stream);
   return subgnn_check_launch("row_bwd_kernel");
 }
 
@@ -1407,17 +1430,24 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
     rc = subgnn_check_launch("n_wgrad_kernel");
     if (rc) return rc;
   }
-  if (d->lin_gw[0] && !d->mlp_fused) {
-    // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)
-    rc = subgnn_linear_bwd_weight(d->dH1, d->h1, d->Z, d->hid, nullptr, d->lin_gw[0], d->hid, d->lin_gb[0], d->B, d->h1, d->hid, nullptr, stream);
-    if (rc) return rc;
-    rc = subgnn_linear_bwd_weight(d->dH2, d->h2, d->H1, d->h1, nullptr, d->lin_gw[1], d->h1, d->lin_gb[1], d->B, d->h2, d->h1, nullptr, stream);
-    if (rc) return rc;
-    rc = subgnn_linear_bwd_weight(d->dlogits, d->n_classes, d->H2, d->h2, nullptr, d->lin_gw[2], d->h2, d->lin_gb[2], d->B, d->n_classes, d->h2,
-                                  nullptr, stream);
-    if (rc) return rc;
-  }
+  if (d->lin_gw[0] && !d->mlp_fused) return subgnn_model_mlp_wgrad(d, stream);
   return SUBGNN_OK;
+}
+
+// weight / bias gradients of the readout MLP: they need dH1, dH2, d logits and the forward activations only, i.e. everything the
+// readout section has produced — the fused step launches them right behind it, on a branch beside the backward chain, instead of
+// at the end of the main stream (where they queued behind the last BPTT recurrence and shared the SMs with the GEMM tail)
+int subgnn_model_mlp_wgrad(const subgnn_model_desc* d, void* stream) {
+  int rc = check_desc(d);
+  if (rc) return rc;
+  if (!d->lin_gw[0]) return SUBGNN_OK;
+  // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)
+  rc = subgnn_linear_bwd_weight(d->dH1, d->h1, d->Z, d->hid, nullptr, d->lin_gw[0], d->hid, d->lin_gb[0], d->B, d->h1, d->hid, nullptr, stream);
+  if (rc) return rc;
+  rc = subgnn_linear_bwd_weight(d->dH2, d->h2, d->H1, d->h1, nullptr, d->lin_gw[1], d->h1, d->lin_gb[1], d->B, d->h2, d->h1, nullptr, stream);
+  if (rc) return rc;
+  return subgnn_linear_bwd_weight(d->dlogits, d->n_classes, d->H2, d->h2, nullptr, d->lin_gw[2], d->h2, d->lin_gb[2], d->B, d->n_classes, d->h2,
+                                  nullptr, stream);
 }
 
 }  // extern "C"

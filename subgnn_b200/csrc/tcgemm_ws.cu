@@ -555,8 +555,10 @@ int subgnn_tc_gemm_group(const subgnn_gemm_desc* g, int n, int max_ctas, void* s
       rc = make_map(&pr.tmA, d.a, d.N, d.M, d.lda, WS_M);
       if (!rc) rc = make_map(&pr.tmB, d.b, d.K, d.N, d.ldb, 32, true);
       pr.scatter_ids = d.scatter_ids;
-      pr.mode = d.scatter_ids ? WS_SCATTER : (d.accumulate ? WS_ACCUM : WS_STORE);
-      splittable = d.scatter_ids != nullptr || d.accumulate != 0;
+      // accumulate: 1 = read-add-store (one writer per element; atomics when the reduction is split), 2 = atomics from the start
+      // (another product of the SAME group adds into the same rows, e.g. the reverse direction's last-step rows of a layer)
+      pr.mode = d.scatter_ids ? WS_SCATTER : (d.accumulate == 2 ? WS_ATOMIC : d.accumulate ? WS_ACCUM : WS_STORE);
+      splittable = d.scatter_ids != nullptr || d.accumulate == 1;
     } else {                                       // out[N][K] += a[M][N]^T . b[row + shift][K]
       SG_REQUIRE(d.op == SUBGNN_GEMM_BWD_WEIGHT || d.op == SUBGNN_GEMM_BWD_WEIGHT_SHIFT, "unknown op");
       pr.a_mn = 1; pr.b_mn = 1; pr.out_rows = d.N; pr.out_cols = d.K; pr.red_len = d.M; pr.nt = pick_nt(d.K);

@@ -249,6 +249,13 @@ class LstmRunner:
         # keep the round-1 per-GEMM launches for A/B runs.
         self.ws = self.use_tc and bool(_abi.lib.subgnn_tc_ws_available()) and not _flag('SUBGNN_TC_LEGACY', False) and hp.get('b200_ws_gemm', True)
         self.grouped = int(os.environ.get('SUBGNN_GEMM_GROUPED', hp.get('b200_gemm_grouped', 1))) if self.ws else 0
+        # top layer of a multi-layer stack: the all-rows and the last-step-rows input-gradient products in ONE launch (atomics onto a
+        # zero-filled dOUT) instead of two dependent launches on the chain.  Measured on B200 (PPI-BP shape, same box): 0.3357 ms/step
+        # with the merge against 0.3224 without — the vector atomics of the 79-tile product cost more than the 7 us launch they
+        # save — so it is a switch, off.  Likewise SUBGNN_LSTM_PREP_BESIDE (weight packing on a branch beside the gather): 0.3357
+        # against 0.3148.
+        self.bi_merge = _flag('SUBGNN_BI_MERGE', hp.get('b200_bi_merge', False))
+        self.prep_beside = _flag('SUBGNN_LSTM_PREP_BESIDE', hp.get('b200_lstm_prep_beside', False))
         self.X0 = z(M, self.D) if (self.ws and walks is not None) else None
         self.fwd_fn = 'subgnn_tc_linear_fwd' if self.use_tc else 'subgnn_linear_fwd'
         self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
@@ -270,19 +277,28 @@ class LstmRunner:
             self._aux = [torch.cuda.Stream(device=self.dev) for _ in range(3)]
         return self._aux
 
-    def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None):
+    def forward(self, E_ptr, training, seed, step_dev, st, dense_x=None, step_event=None):
+        """step_event: recorded by the caller once *step_dev holds this step's counter (fused step: the chain is forked BEFORE the
+        counter kernel; only the recurrences with fused dropout / the dropout kernels read it)."""
         a, H, D, M, T = self.arena, self.H, self.D, self.n_seq * self.T, self.T
         cur = torch.cuda.current_stream()
         aux = self._aux_streams()
         self.dense_x = dense_x
         if dense_x is not None:
             E_ptr = ptr(dense_x)
+        gather = self.X0 is not None and dense_x is None
+        # weight packing (W_hh^T, b_ih + b_hh) of every layer beside the once-per-step embedding gather, not in front of it
+        ps = aux[0] if (gather and self.prep_beside) else cur
+        if ps is not cur:
+            ps.wait_stream(cur)
         for k in range(self.nl):
             o = a.lstm_off[k]
             call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
-                 ptr(self.whh_t[k]), ptr(self.bsum[k]), H, st)
-        if self.X0 is not None and dense_x is None:
+                 ptr(self.whh_t[k]), ptr(self.bsum[k]), H, ps.cuda_stream)
+        if gather:
             call('subgnn_gather_rows', E_ptr, ptr(self.ids_flat), ptr(self.X0), M, D, st)     # anchor_patch_samplers.py:409, once per step
+        if ps is not cur:
+            cur.wait_stream(ps)
         for k in range(self.nl):
             o = a.lstm_off[k]
             fused = self.fused_drop and self.p_drop > 0 and training
@@ -308,6 +324,8 @@ class LstmRunner:
                          G + 4 * (((T - 1) * 2 + 1) * 4 * H), T * 8 * H, self.n_seq, 4 * H, din, 0, aux[0].cuda_stream)
                 call(self.fwd_fn, x_ptr, ldx, ids, w_ih, din, ptr(self.bsum[k]), G, 8 * H, M, 4 * H, din, 0, st)
                 cur.wait_stream(aux[0])
+            if k == 0 and step_event is not None:
+                cur.wait_event(step_event)           # the gather and the first projection do not read the step counter; everything below may
             if fused and k + 1 < self.nl:            # also writes X[k+1] = dropout(OUT[k]), the next layer's input
                 call('subgnn_lstm_recur_fwd_drop', G, ptr(self.whh_t[k]), ptr(self.OUT[k]), ptr(self.CS[k]), self.n_seq, T, H, sf, sr,
                      ptr(self.X[k + 1]), self.p_drop, seed, 8 + k + 1, step_dev, st)
@@ -356,6 +374,10 @@ class LstmRunner:
         g = 'grads'
         aux[1].wait_stream(cur)
         with torch.cuda.stream(aux[1]):
+            if self.ws and self.bi_merge and self.nl > 1 and self.steps(self.nl - 1)[1] != T:
+                # the top layer's two input-gradient products (all rows x forward gates, last-step rows x reverse gates) add into
+                # dOUT[nl-2] with atomics in one grouped launch: its zero fill runs here, beside the head gradient
+                call('subgnn_fill_zero', ptr(self.dOUT[self.nl - 2]), self.dOUT[self.nl - 2].numel(), aux[1].cuda_stream)
             call('subgnn_linear_bwd_weight', ptr(self.dEMB), D, ptr(self.AGG), 2 * H, None, a.addr('lstm.linear.weight', g), 2 * H,
                  None, self.n_groups, D, 2 * H, None, aux[1].cuda_stream)
         call('subgnn_lstm_head_bwd', ptr(self.dEMB), a.addr('lstm.linear.weight'), ptr(self.dOUT[-1]), a.addr('lstm.linear.bias', g),
@@ -456,6 +478,11 @@ class LstmRunner:
                 if scat:
                     bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr, lddx, self.n_seq, 4 * H, din,
                                  scatter_ids=ptr(self.ids_last), accumulate=1))
+                elif self.bi_merge and k > 0 and k == self.nl - 1:   # both products add with atomics onto the zero-filled dOUT[k-1] (backward()): ONE launch on the chain
+                    bi[0] = gd(_abi.GEMM_BWD_INPUT, dG, 8 * H, w_ih, din, dx_ptr, lddx, M, n_out, din, accumulate=2)
+                    bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx, self.n_seq,
+                                 4 * H, din, accumulate=2))
+                    cur.wait_stream(aux[1])              # the zero fill
                 else:          # read-add-store onto rows the main product writes: after it, not beside it
                     bi_after.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx, self.n_seq,
                                        4 * H, din, accumulate=1))
@@ -840,19 +867,37 @@ class Engine:
             self._qs = torch.cuda.Stream(device=self.device)
         return self._qs
 
-    def _forward_launches(self, c, st, zero_grads=False, split=False):
+    def _forward_launches(self, c, st, zero_grads=False, split=False, inc_step=False):
         """split (fused training step only): only the structure-channel columns of Z depend on the LSTM, so the position outputs and
         the first MLP layer over every other column run beside the LSTM chain; behind the join stay the structure outputs, their
         slices of the first layer, the rest of the MLP and the structure columns of dZ (the others are produced in the backward
         pass, beside the BPTT chain)."""
         main = torch.cuda.current_stream()
         fork = self.lstm is not None and self.concurrent
+        # launch order of the two branches inside the captured graph: [r2] with the faster projection GEMMs the neighbourhood branch
+        # (zero fills -> batch prep -> weight transposes -> position q -> row_fwd phase 1, ~75 us of dependent launches, starved
+        # while the first recurrence owns every SM) ends AFTER the LSTM chain; its nodes are recorded first (measured, same box:
+        # 0.3182 -> 0.3140 ms/step; SUBGNN_NBRANCH_FIRST=0 restores the round-1 order)
+        nfirst = fork and _flag('SUBGNN_NBRANCH_FIRST', self.hp.get('b200_nbranch_first', True))
+        step_ev = None
+        # fork_early: the LSTM chain forks before the step-counter kernel and waits for it (event) in front of the first recurrence.
+        # Measured on B200 (PPI-BP shape, same box, 100 steps): 0.3225 ms/step with, 0.3101 without — the second incoming edge
+        # takes the programmatic (PDL) edge projection -> recurrence away — so it is off.
+        fork_early = _flag('SUBGNN_FORK_EARLY', self.hp.get('b200_fork_early', False))
+        if inc_step and not (fork and fork_early):
+            call('subgnn_inc_step', ptr(self.step_dev), st)
+            inc_step = False
         if fork:                                  # the LSTM chain is the longest of the step: it starts before the zero fills
             side = self._side_stream()
-            side.wait_stream(main)
+            side.wait_stream(main)                # fork_early: BEFORE the step-counter kernel (gather + first projection do not read it)
             self._prep_stream().wait_stream(main)
+        if inc_step:
+            call('subgnn_inc_step', ptr(self.step_dev), st)
+            step_ev = torch.cuda.Event()
+            step_ev.record(main)
+        if fork and not nfirst:
             with torch.cuda.stream(side):
-                self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream)
+                self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream, step_event=step_ev)
         if zero_grads:
             self.zero_grads(c, st, include_fwd=True)
         else:
@@ -883,6 +928,9 @@ class Engine:
         if pfork:
             main.wait_stream(prep)
         call('subgnn_model_rows_fwd', c.dptr, 1, st)                 # pooling + neighbourhood channel
+        if nfirst:
+            with torch.cuda.stream(side):
+                self.lstm.forward(self.E_ptr(), c.training, self.seed, ptr(self.step_dev), side.cuda_stream, step_event=step_ev)
         if bfork:
             main.wait_stream(qs)
         if split:
@@ -954,6 +1002,10 @@ class Engine:
     def _optimizer_launches(self, c, st):
         a = self.arena
         clip = self.grad_clip
+        if _flag('SUBGNN_FUSED_ADAM', self.hp.get('b200_fused_adam', False)):      # norm + clip + Adam in one launch (optim.cu)
+            call('subgnn_clip_adam_step', ptr(a.params), ptr(a.grads), ptr(a.m), ptr(a.v), a.size, self.lr, 0.9, 0.999, 1e-8,
+                 ptr(self.step_dev), c.sumsq.data_ptr(), clip, 1.0 / self.world_size, st)
+            return
         call('subgnn_grad_sumsq', ptr(a.grads), a.size, c.sumsq.data_ptr(), st)
         call('subgnn_adam_step', ptr(a.params), ptr(a.grads), ptr(a.m), ptr(a.v), a.size, self.lr, 0.9, 0.999, 1e-8, ptr(self.step_dev),
              c.sumsq.data_ptr(), clip, 1.0 / self.world_size, st)
@@ -1110,7 +1162,6 @@ class Engine:
         return c.loss_host.item()
 
     def _grad_launches(self, c, st):
-        call('subgnn_inc_step', ptr(self.step_dev), st)
         # fused step: the readout kernel's own d logits are THE gradient, so it also produces the MLP weight / bias gradients
         # (the descriptor is copied by value at every launch: the flag is per call)
         c.desc.mlp_fused = 1 if (c.readout_cluster and _flag('SUBGNN_READOUT_FUSED_WGRAD', self.hp.get('b200_readout_fused_wgrad', False))) else 0
@@ -1120,9 +1171,21 @@ class Engine:
         # end of the BPTT chain and compete with the recurrences for SMs.  Kept as a switch, off.
         split = (self.lstm is not None and self.concurrent and not c.readout_cluster and
                  _flag('SUBGNN_READOUT_SPLIT', self.hp.get('b200_readout_split', False)))
+        # MLP weight gradients launched right behind the readout section on a branch of their own (model.cu: subgnn_model_mlp_wgrad)
+        # instead of at the end of the main stream: measured 0.3189 -> 0.3225 ms/step (same box) — three more small kernels beside
+        # the head of the BPTT chain cost more than they free at the tail — a switch, off.
+        early = (self.concurrent and not c.desc.mlp_fused and _flag('SUBGNN_MLP_WGRAD_EARLY', self.hp.get('b200_mlp_wgrad_early', False)))
         try:
-            self._forward_launches(c, st, zero_grads=True, split=split)
+            self._forward_launches(c, st, zero_grads=True, split=split, inc_step=True)
+            if early:
+                main, aux = torch.cuda.current_stream(), self._prep_stream()
+                aux.wait_stream(main)
+                with torch.cuda.stream(aux):
+                    call('subgnn_model_mlp_wgrad', c.dptr, aux.cuda_stream)
+                c.desc.mlp_fused = 1                 # subgnn_model_wgrad (end of the main stream) leaves the MLP products out
             self._backward_launches(c, st, split=split)
+            if early:
+                main.wait_stream(aux)
         finally:
             c.desc.mlp_fused = 0
 

@@ -4,7 +4,8 @@ a few hundred subgraphs) of all five BASELINE.json configurations with their REA
 the kernel template instantiations the bench times are the ones compared with the CPU oracle:
 row_fwd/row_bwd<2|4>, lstm_{fwd,bwd}_tile<1,4,64> / <2,.,128> (2-CTA clusters), the TMA-fed grouped tcgen05 GEMM (tc_gemm_ws_kernel) at M = n_seq * T;
 the opt-in cluster readout kernel is run over the same shapes by the second test.
-Dropout is 0 (its law is tested in test_gpu_dropout_law.py); tolerance fp32 rtol 1e-4 / atol 1e-5 (stated, as test_gpu_model.py).
+Dropout is 0 (its law is tested in test_gpu_dropout_law.py); tolerance fp32 rtol 1e-4 / atol 1e-5 (stated, as test_gpu_model.py;
+weights after two Adam steps: atol 3e-5, see the comment at the assertion).
 Reference path: SubGNN.py:225-348 forward / training_step, :1156-1164 Adam, Lightning clip_grad_norm_."""
 import numpy as np
 import pytest
@@ -83,7 +84,10 @@ def test_engine_step_matches_oracle_at_benchmark_shape(name):
                     np.testing.assert_allclose(got, want, rtol=3e-4, atol=tol, err_msg='grad ' + k)
     sd = m.state_dict()
     for k in eng.arena.entries:
-        np.testing.assert_allclose(eng.arena.view(k).cpu().numpy(), sd[k].numpy(), rtol=1e-4, atol=1e-5, err_msg='weights after 2 steps: ' + k)
+        # Adam normalises every element's step to ~lr = 1e-3 whatever the gradient's size, so an element whose gradient is at rounding
+        # level (summation order of float atomics) moves by a visible fraction of lr: atol 3e-5 = 3 % of one step (observed: 1 element in
+        # 120 k at 1.3e-5); the gradients themselves are compared above at 2e-6
+        np.testing.assert_allclose(eng.arena.view(k).cpu().numpy(), sd[k].numpy(), rtol=1e-4, atol=3e-5, err_msg='weights after 2 steps: ' + k)
     launched = _abi.variant_log()
     for want in SHAPES[name][2]:
         assert any(v.startswith(want) for v in launched), '%s not launched; saw %s' % (want, sorted(launched))
