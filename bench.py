@@ -208,16 +208,25 @@ ENTRY_KERNELS = {'subgnn_tc_gemm_group': ['tc_gemm_ws_kernel'], 'subgnn_tc_linea
                  'subgnn_fill_zero': ['fill_zero_kernel']}
 
 
+# source files that define each entry point's kernels (plus the shared device headers): the stamp checked by ncu_traffic
+ENTRY_SOURCES = {'subgnn_tc_gemm_group': ['tcgemm_ws.cu'], 'subgnn_tc_linear_bwd_weight': ['tcgemm.cu'], 'subgnn_tc_linear_fwd': ['tcgemm.cu'],
+                 'subgnn_tc_linear_bwd_input': ['tcgemm.cu'], 'subgnn_lstm_recur_fwd': ['lstm_reg.cu', 'lstm_reg.cuh'],
+                 'subgnn_lstm_recur_bwd': ['lstm_reg.cu', 'lstm_reg.cuh'], 'subgnn_model_rows_fwd': ['model.cu'], 'subgnn_model_rows_bwd': ['model.cu'],
+                 'subgnn_adam_step': ['optim.cu'], 'subgnn_grad_sumsq': ['optim.cu'], 'subgnn_fill_zero': ['optim.cu']}
+
+
 def ncu_traffic(workload, entry):
     """mean DRAM bytes per launch of the entry point's kernel from the committed ncu --set full capture of this workload, or None.
-    The table is stamped with the digest of the CUDA sources it was captured on (tools/ncu_traffic.py); a table of other
-    kernels is refused (traffic = null) instead of being reported against kernels that have changed since."""
+    The table is stamped with the digest of every CUDA source it was captured on (tools/ncu_traffic.py); it is refused
+    (traffic = null) when the files that define THIS entry point's kernels (ENTRY_SOURCES + common.cuh) have changed since."""
     f = ROOT / 'profiles' / ('r02_traffic_%s.json' % workload)
     if not f.exists() or entry not in ENTRY_KERNELS:
         return None, None
     tab = json.loads(f.read_text())
-    if tab.get('csrc_digest') != csrc_digest():
-        return None, None
+    stamps, now = tab.get('csrc_files') or {}, csrc_file_digests()
+    for src in ENTRY_SOURCES.get(entry, sorted(now)) + ['common.cuh']:
+        if src not in stamps or stamps[src] != now.get(src):
+            return None, None
     ks = [tab['kernels'][k] for k in ENTRY_KERNELS[entry] if k in tab['kernels']]
     if not ks:
         return None, None
@@ -319,6 +328,12 @@ def csrc_digest():
         h.update(f.name.encode())
         h.update(f.read_bytes())
     return h.hexdigest()[:16]
+
+
+def csrc_file_digests():
+    """{file name: sha256[:16]} of every CUDA source / header under csrc/"""
+    import hashlib
+    return {f.name: hashlib.sha256(f.read_bytes()).hexdigest()[:16] for f in sorted((ROOT / 'subgnn_b200' / 'csrc').glob('*.cu*'))}
 
 
 class Job:

@@ -179,6 +179,11 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
    next layer's input; backward applies the same mask to dOUT (then the gradient w.r.t. xdrop) on load.  Mask stream = the one of
    subgnn_dropout(seed, salt, step_dev).  Available when subgnn_lstm_fused_dropout_supported(H). */
 int subgnn_lstm_fused_dropout_supported(int H);
+/* the same forward recurrence on the tensor cores (lstm_tc.cu: tcgen05 3xTF32, 4-CTA clusters split by hidden unit, h exchanged through
+ * distributed shared memory); H = 64 only; whh is the NATIVE nn.LSTM weight_hh [2][4H][H] (not the packed copy); xdrop may be NULL */
+int subgnn_lstm_recur_fwd_tc_supported(int H);
+int subgnn_lstm_recur_fwd_tc(float* G, const float* whh, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
+                             float* xdrop, float p, unsigned long long seed, unsigned salt, const int* step_dev, void* stream);
 int subgnn_lstm_recur_fwd_drop(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
                                float* xdrop, float p, unsigned long long seed, unsigned salt, const int* step_dev, void* stream);
 int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,

@@ -52,6 +52,8 @@ SIGNATURES = {
     'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
     'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'subgnn_lstm_recur_fwd_drop': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
+    'subgnn_lstm_recur_fwd_tc': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
+    'subgnn_lstm_recur_fwd_tc_supported': [I],
     'subgnn_lstm_recur_bwd_drop': [P, P, P, P, P, I, I, I, I, I, I, P, P, F, U64, U32, P, P],
     'subgnn_lstm_head_fwd': [P, P, P, P, P, I, I, I, I, I, I, P],
     'subgnn_lstm_head_bwd': [P, P, P, P, I, I, I, I, I, I, P],

@@ -1226,10 +1226,10 @@ static int check_desc(const Desc* d) {
 }
 
 static int row_grid(const Desc* d);
-// 16 warps per row while every row of the batch gets a CTA slot of the wide kernel's first wave (2 per SM), else 8 (see ROW_WIDE)
+// 16 warps per row while the row capacity (B x most components of a subgraph: an upper bound of the rows) stays within the grid cap, else 8 (see ROW_WIDE)
 static int row_width(const Desc* d) {
   if (const char* e = getenv("SUBGNN_ROW_THREADS")) { const int v = atoi(e); if (v == ROW_WIDE || v == ROW_NARROW) return v; }
-  return d->R_cap <= 4 * subgnn_sm_count() ? ROW_WIDE : ROW_NARROW;
+  return d->R_cap <= 8 * subgnn_sm_count() ? ROW_WIDE : ROW_NARROW;
 }
 
 template <int DPL, int RT>

@@ -38,6 +38,20 @@ def run(name, n_seq, T, H, reps=30):
         if i >= 3:
             tf.append(e[0].elapsed_time(e[1]))
             tb.append(e[1].elapsed_time(e[2]))
+    ttc = []
+    if H == 64:                                # tensor-core forward recurrence (lstm_tc.cu), same inputs
+        for i in range(reps + 3):
+            G = G0.clone()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+            e[0].record()
+            call('subgnn_lstm_recur_fwd_tc', ptr(G), ptr(whh), ptr(OUT), ptr(CS), n_seq, T, H, T, T, None, 0.0, 0, 0, None, st)
+            e[1].record()
+            torch.cuda.synchronize()
+            if i >= 3:
+                ttc.append(e[0].elapsed_time(e[1]))
+        ttc.sort()
+        print('%-10s tensor-core forward recurrence (tcgen05, 4-CTA clusters): %.1f us (%.2f us/step)' %
+              (name, 1e3 * ttc[len(ttc) // 2], 1e3 * ttc[len(ttc) // 2] / T), flush=True)
     tf.sort(), tb.sort()
     print('%-10s n_seq=%d T=%d H=%d tile=%s  fwd %.1f us (%.2f us/step)  bwd %.1f us (%.2f us/step)' %
           (name, n_seq, T, H, os.environ.get('SUBGNN_LSTM_TILE', 'auto'), 1e3 * tf[len(tf) // 2], 1e3 * tf[len(tf) // 2] / T,

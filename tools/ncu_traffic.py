@@ -4,7 +4,8 @@ captured step) and duration from an `ncu --set full` report -> JSON for profiles
 
     python tools/ncu_traffic.py gpurun_out/full.ncu-rep > profiles/r02_traffic_<workload>.json
 
-The table is stamped with bench.csrc_digest() (sha256 of subgnn_b200/csrc): bench.py refuses a table captured on other kernels."""
+The table is stamped with the sha256 of every file under subgnn_b200/csrc: bench.py refuses it for an entry point whose source
+files have changed since the capture."""
 import collections
 import csv
 import json
@@ -34,7 +35,7 @@ def main(path):
     res = {k: {'launches_per_step': v['launches'], 'dram_bytes_per_launch': v['dram_bytes'] / v['launches'], 'us_per_launch': v['us'] / v['launches']}
            for k, v in agg.items()}
     import bench
-    print(json.dumps({'source': path.split('/')[-1], 'csrc_digest': bench.csrc_digest(), 'note': 'ncu --set full --clock-control none, one eager step, caches flushed before every kernel '
+    print(json.dumps({'source': path.split('/')[-1], 'csrc_digest': bench.csrc_digest(), 'csrc_files': bench.csrc_file_digests(), 'note': 'ncu --set full --clock-control none, one eager step, caches flushed before every kernel '
                       '(cold): an upper bound on the traffic of the same kernel inside the step graph, where producers leave their outputs in L2',
                       'kernels': res}, indent=1))
 
