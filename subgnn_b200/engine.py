@@ -1172,9 +1172,12 @@ class Engine:
         split = (self.lstm is not None and self.concurrent and not c.readout_cluster and
                  _flag('SUBGNN_READOUT_SPLIT', self.hp.get('b200_readout_split', False)))
         # MLP weight gradients launched right behind the readout section on a branch of their own (model.cu: subgnn_model_mlp_wgrad)
-        # instead of at the end of the main stream: measured 0.3189 -> 0.3225 ms/step (same box) — three more small kernels beside
-        # the head of the BPTT chain cost more than they free at the tail — a switch, off.
-        early = (self.concurrent and not c.desc.mlp_fused and _flag('SUBGNN_MLP_WGRAD_EARLY', self.hp.get('b200_mlp_wgrad_early', False)))
+        # instead of at the end of the main stream.  Measured (same box, 100 steps): with a ONE-layer walk encoder the backward chain
+        # behind the readout is short and these three kernels end the step — density 0.1741 -> 0.1464 ms/step, EM-USER 0.5709 ->
+        # 0.5599; with two layers they hide behind the BPTT chain and the early launch only adds work beside its head — PPI-BP
+        # 0.3189 -> 0.3225, cutratio 0.3323 -> 0.3346, HPO-METAB 0.5901 -> 0.5882.  Default: by layer count.
+        one_layer = self.lstm is not None and self.lstm.nl == 1
+        early = (self.concurrent and not c.desc.mlp_fused and _flag('SUBGNN_MLP_WGRAD_EARLY', self.hp.get('b200_mlp_wgrad_early', one_layer)))
         try:
             self._forward_launches(c, st, zero_grads=True, split=split, inc_step=True)
             if early:
