@@ -941,7 +941,11 @@ class Engine:
             call('subgnn_model_rows_fwd', c.dptr, 4, st)             # structure property-aware outputs
             call('subgnn_model_mlp_stage', c.dptr, 1, 2, st)         # their slices of the first layer
             call('subgnn_model_mlp_stage', c.dptr, 2, 0, st)         # lin2, lin3, loss, d logits, dH2, dH1
-            call('subgnn_model_mlp_stage', c.dptr, 4, 2, st)         # structure columns of dZ (the chain continues through them)
+            if split == 'fwd':                                       # forward half only: all of dZ here, the usual backward pass behind it
+                call('subgnn_model_mlp_stage', c.dptr, 4, 0, st)
+                call('subgnn_sum_to_scalar', ptr(c.loss_b), c.B, ptr(c.loss), st)
+            else:
+                call('subgnn_model_mlp_stage', c.dptr, 4, 2, st)     # structure columns of dZ (the chain continues through them)
             return
         if fork:
             main.wait_stream(side)
@@ -955,7 +959,7 @@ class Engine:
 
     def _backward_launches(self, c, st, external_dlogits=False, split=False):
         main = torch.cuda.current_stream()
-        if split:
+        if split and split != 'fwd':
             call('subgnn_model_rows_bwd', c.dptr, 4, st)             # structure outputs: d q_s, d b_p
             call('subgnn_model_q_bwd_part', c.dptr, 2, st)           # d emb_s
             side = self._side_stream()
@@ -1171,6 +1175,11 @@ class Engine:
         # end of the BPTT chain and compete with the recurrences for SMs.  Kept as a switch, off.
         split = (self.lstm is not None and self.concurrent and not c.readout_cluster and
                  _flag('SUBGNN_READOUT_SPLIT', self.hp.get('b200_readout_split', False)))
+        # forward half of that schedule alone (the main stream idles ~35 us before the join: position outputs and the first MLP
+        # layer over the LSTM-independent columns fit there; behind the join only the structure columns' slices remain)
+        if not split and self.lstm is not None and self.concurrent and not c.readout_cluster and \
+                _flag('SUBGNN_READOUT_SPLIT_FWD', self.hp.get('b200_readout_split_fwd', False)):
+            split = 'fwd'
         # MLP weight gradients launched right behind the readout section on a branch of their own (model.cu: subgnn_model_mlp_wgrad)
         # instead of at the end of the main stream.  Measured (same box, 100 steps): with a ONE-layer walk encoder the backward chain
         # behind the readout is short and these three kernels end the step — density 0.1741 -> 0.1464 ms/step, EM-USER 0.5709 ->
