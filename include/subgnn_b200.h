@@ -164,6 +164,9 @@ int subgnn_gather_rows(const float* table, const int* ids, float* out, int M, in
 
 /* ---- walk-encoder LSTM (lstm.cu): SubGNN.py:60-88, anchor_patch_samplers.py:413-433 ------------------ */
 int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, float* whh_t, float* bsum, int H, void* stream);
+/* the same for every layer of a stack in ONE launch: HOST arrays of n_layers device pointers each */
+int subgnn_lstm_prep_layers(const float* const* whh, const float* const* b_ih, const float* const* b_hh, float* const* whh_t,
+                            float* const* bsum, int n_layers, int H, void* stream);
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
                           void* stream);
 /* db_ih / db_hh (optional, [2][4H]): += column sums of d(pre-activation), the gradient of both bias vectors.
@@ -189,6 +192,12 @@ int subgnn_lstm_recur_fwd_drop(float* G, const float* whh_t, float* OUT, float* 
 int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H,
                                int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed,
                                unsigned salt, const int* step_dev, void* stream);
+/* BPTT with a second gradient source: dOUT_add has dOUT's layout, only its rows t = T-1 are written (and read) — the input gradient of
+   the reverse direction of the layer ABOVE, which consumed this layer's output at the last step only ('last' aggregator, SubGNN.py:83).
+   Lets that product run in the same grouped launch as the all-rows input gradient instead of behind it.  p = 0: no dropout mask. */
+int subgnn_lstm_recur_bwd_add(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, const float* dOUT_add, int n_seq,
+                              int T, int H, int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p,
+                              unsigned long long seed, unsigned salt, const int* step_dev, void* stream);
 /* walk-group head (anchor_patch_samplers.py:429-433: patch embedding = sum over its walks of Linear(agg(lstm_out)), SubGNN.py:83-88).
    The head is linear, so the walks are summed first: fwd  AGG[g] = sum_w agg(OUT[g*group+w]),  EMB[g] = W AGG[g] + group * bias;
    bwd  dOUT rows <- W^T dEMB[g] (t = T-1 only for 'last'),  db += group * sum_g dEMB[g]   (dW = dEMB^T AGG: subgnn_linear_bwd_weight).

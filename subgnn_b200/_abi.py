@@ -49,12 +49,14 @@ SIGNATURES = {
     'subgnn_gather_rows': [P, P, P, I, I, P],
     'subgnn_colsum': [P, I, P, I, I, P, P],
     'subgnn_lstm_prep': [P, P, P, P, P, I, P],
+    'subgnn_lstm_prep_layers': [P, P, P, P, P, I, I, P],
     'subgnn_lstm_recur_fwd': [P, P, P, P, I, I, I, I, I, P],
     'subgnn_lstm_recur_bwd': [P, P, P, P, P, I, I, I, I, I, I, P, P, P],
     'subgnn_lstm_recur_fwd_drop': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
     'subgnn_lstm_recur_fwd_tc': [P, P, P, P, I, I, I, I, I, P, F, U64, U32, P, P],
     'subgnn_lstm_recur_fwd_tc_supported': [I],
     'subgnn_lstm_recur_bwd_drop': [P, P, P, P, P, I, I, I, I, I, I, P, P, F, U64, U32, P, P],
+    'subgnn_lstm_recur_bwd_add': [P, P, P, P, P, P, I, I, I, I, I, I, P, P, F, U64, U32, P, P],
     'subgnn_lstm_head_fwd': [P, P, P, P, P, I, I, I, I, I, I, P],
     'subgnn_lstm_head_bwd': [P, P, P, P, I, I, I, I, I, I, P],
     'subgnn_dropout': [P, P, LL, F, U64, U32, P, P],

@@ -383,9 +383,8 @@ __global__ void dropout_kernel(const float* __restrict__ x, float* __restrict__ 
 //   cl == 0: WhhT[dir][k][j] = Whh[dir][j][k]                                   (streaming kernels above), or
 //   cl >= 1: Wp[dir][rank][k][half][p][g2][o] = Whh[dir][(2 half + g2)*H + rank*U + 2p + o][k], U = H / cl   (lstm_reg.cu: every
 //            CTA's slice is one contiguous block for its bulk copy; a thread's two float4 per k are contiguous across the warp).
-__global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
-                                 float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
-  sg_pdl_wait_only();        // the recurrence kernels stage WhhT before their dependency wait (lstm_reg.cu)
+__device__ __forceinline__ void lstm_prep_body(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                               float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
   const int H4 = 4 * H;
   const long long total = (long long)2 * H4 * H;
   for (long long e = blockIdx.x * (long long)blockDim.x + threadIdx.x; e < total; e += (long long)gridDim.x * blockDim.x) {
@@ -404,6 +403,25 @@ __global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __r
     if (e < 2 * H4) bsum[e] = b_ih[e] + b_hh[e];
   }
 }
+__global__ void lstm_prep_kernel(const float* __restrict__ Whh, const float* __restrict__ b_ih, const float* __restrict__ b_hh,
+                                 float* __restrict__ WhhT, float* __restrict__ bsum, int H, int cl) {
+  sg_pdl_wait_only();        // the recurrence kernels stage WhhT before their dependency wait (lstm_reg.cu)
+  lstm_prep_body(Whh, b_ih, b_hh, WhhT, bsum, H, cl);
+}
+// every layer of the stack in ONE launch (grid.y = layer): the packing sits in front of the first projection on the step's chain
+#define LSTM_PREP_MAX_LAYERS 8
+struct LstmPrepLayers {
+  const float* whh[LSTM_PREP_MAX_LAYERS];
+  const float* b_ih[LSTM_PREP_MAX_LAYERS];
+  const float* b_hh[LSTM_PREP_MAX_LAYERS];
+  float* whh_t[LSTM_PREP_MAX_LAYERS];
+  float* bsum[LSTM_PREP_MAX_LAYERS];
+};
+__global__ void lstm_prep_layers_kernel(LstmPrepLayers a, int H, int cl) {
+  sg_pdl_wait_only();
+  const int l = blockIdx.y;
+  lstm_prep_body(a.whh[l], a.b_ih[l], a.b_hh[l], a.whh_t[l], a.bsum[l], H, cl);
+}
 
 extern "C" {
 
@@ -414,6 +432,17 @@ int subgnn_lstm_prep(const float* whh, const float* b_ih, const float* b_hh, flo
   sg_launch_pdl(lstm_prep_kernel, dim3(sg_grid_for((long long)8 * H * H, 256, 4)), dim3(256), 0, (cudaStream_t)stream, whh, b_ih, b_hh, whh_t, bsum, H,
                                                                                                   lstm_reg_supported(H) ? lstm_reg_cluster(H) : 0);
   return subgnn_check_launch("lstm_prep_kernel");
+}
+
+int subgnn_lstm_prep_layers(const float* const* whh, const float* const* b_ih, const float* const* b_hh, float* const* whh_t,
+                            float* const* bsum, int n_layers, int H, void* stream) {
+  SG_REQUIRE(H >= 1 && H <= 256, "hidden size must be in [1, 256]");
+  SG_REQUIRE(n_layers >= 1 && n_layers <= LSTM_PREP_MAX_LAYERS, "1 .. 8 layers per launch");
+  LstmPrepLayers a = {};
+  for (int l = 0; l < n_layers; ++l) { a.whh[l] = whh[l]; a.b_ih[l] = b_ih[l]; a.b_hh[l] = b_hh[l]; a.whh_t[l] = whh_t[l]; a.bsum[l] = bsum[l]; }
+  sg_launch_pdl(lstm_prep_layers_kernel, dim3(sg_grid_for((long long)8 * H * H, 256, 4), n_layers), dim3(256), 0, (cudaStream_t)stream, a, H,
+                lstm_reg_supported(H) ? lstm_reg_cluster(H) : 0);
+  return subgnn_check_launch("lstm_prep_layers_kernel");
 }
 
 int subgnn_lstm_recur_fwd(float* G, const float* whh_t, float* OUT, float* CS, int n_seq, int T, int H, int steps_fwd, int steps_rev,
@@ -460,7 +489,17 @@ int subgnn_lstm_recur_bwd_drop(float* G, const float* whh, const float* OUT, con
   SG_REQUIRE(lstm_reg_supported(H), "fused inter-layer dropout needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
   SG_REQUIRE(n_seq >= 0 && T >= 1 && p >= 0.f && p < 1.f, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
-  return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, p, seed, salt, step_dev,
+  return lstm_reg_bwd(G, whh, OUT, CS, dOUT, nullptr, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, p, seed, salt, step_dev,
+                      (cudaStream_t)stream);
+}
+
+int subgnn_lstm_recur_bwd_add(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, const float* dOUT_add, int n_seq,
+                              int T, int H, int steps_fwd, int steps_rev, int zero_untaken, float* db_ih, float* db_hh, float p,
+                              unsigned long long seed, unsigned salt, const int* step_dev, void* stream) {
+  SG_REQUIRE(lstm_reg_supported(H), "the two-source BPTT needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
+  SG_REQUIRE(n_seq >= 0 && T >= 1 && p >= 0.f && p < 1.f, "bad sizes");
+  if (n_seq == 0) return SUBGNN_OK;
+  return lstm_reg_bwd(G, whh, OUT, CS, dOUT, dOUT_add, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, p, seed, salt, step_dev,
                       (cudaStream_t)stream);
 }
 
@@ -469,7 +508,8 @@ int subgnn_lstm_recur_bwd(float* G, const float* whh, const float* OUT, const fl
   SG_REQUIRE(H >= 1 && H <= 256 && n_seq >= 0 && T >= 1, "bad sizes");
   if (n_seq == 0) return SUBGNN_OK;
   if (lstm_reg_supported(H))
-    return lstm_reg_bwd(G, whh, OUT, CS, dOUT, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, 0.f, 0ull, 0u, nullptr, (cudaStream_t)stream);
+    return lstm_reg_bwd(G, whh, OUT, CS, dOUT, nullptr, n_seq, T, H, steps_fwd, steps_rev, zero_untaken, db_ih, db_hh, 0.f, 0ull, 0u, nullptr,
+                        (cudaStream_t)stream);
   SG_REQUIRE(!(zero_untaken & SUBGNN_LSTM_DOUT_LAST_ONLY), "SUBGNN_LSTM_DOUT_LAST_ONLY needs the register-tiled recurrence (H % 8 == 0, H <= 128)");
   zero_untaken &= SUBGNN_LSTM_ZERO_UNTAKEN;
   size_t smem = (size_t)(S_TILE * 4 * H + 2 * S_TILE * H + 4 * S_TILE * H) * sizeof(float);

@@ -294,8 +294,8 @@ lstm_fwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Wp, float*
 template <int CL, int KS, int HC>
 __global__ void __launch_bounds__(512)
 lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const float* __restrict__ OUT, const float* __restrict__ CS,
-                     const float* __restrict__ dOUT, int n_seq, int T, int H_arg, int steps_fwd, int steps_rev, int zero_untaken,
-                     float* __restrict__ db_ih, float* __restrict__ db_hh, int tile, DropArgs drop) {
+                     const float* __restrict__ dOUT, const float* __restrict__ dOUT_add, int n_seq, int T, int H_arg, int steps_fwd,
+                     int steps_rev, int zero_untaken, float* __restrict__ db_ih, float* __restrict__ db_hh, int tile, DropArgs drop) {
   const int H = HC > 0 ? HC : H_arg;
   extern __shared__ __align__(16) float sm[];
   __shared__ uint64_t wbar;
@@ -370,6 +370,9 @@ lstm_bwd_tile_kernel(float* __restrict__ G, const float* __restrict__ Whh, const
         v.cp = st > 0 ? CS[o_off[it][q] + (size_t)t_prev * 2 * H] : 0.f;
         // flag 2: the caller's dOUT is non-zero (and written) only at t = T-1 ('last' aggregator, top layer)
         v.dho = (!(zero_untaken & SUBGNN_LSTM_DOUT_LAST_ONLY) || t == T - 1) ? dOUT[oe] : 0.f;
+        // second gradient source for the rows t = T-1 (same layout, only those rows written): the layer above's reverse direction,
+        // which read this layer's output at its last step only
+        if (dOUT_add && t == T - 1) v.dho += dOUT_add[oe];
       }
     }
   };
@@ -534,8 +537,8 @@ int launch_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, int 
 }
 
 template <int CL, int KS, int HC>
-int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
-               int zero_untaken, float* db_ih, float* db_hh, DropArgs drop, cudaStream_t st) {
+int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, const float* dOUT_add, int n_seq, int T, int H,
+               int sf, int sr, int zero_untaken, float* db_ih, float* db_hh, DropArgs drop, cudaStream_t st) {
   const int U = H / CL;
   const size_t fixed = (size_t)(4 * U * H + 4 * U) * sizeof(float), per_seq = (size_t)(4 * U + U + 4 * KS * CL * U) * sizeof(float);
   const int tile = pick_tile(n_seq, CL, KS * 4 * (H / 8), fixed, per_seq);
@@ -555,7 +558,8 @@ int launch_bwd(float* G, const float* whh, const float* OUT, const float* CS, co
   cfg.attrs = attr;
   cfg.numAttrs = 2;
   subgnn_note_variant("lstm_bwd_tile_kernel<%d,%d,%d>", CL, KS, HC);
-  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS, HC>, G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile, drop);
+  cudaLaunchKernelEx(&cfg, lstm_bwd_tile_kernel<CL, KS, HC>, G, whh, OUT, CS, dOUT, dOUT_add, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, tile,
+                     drop);
   return subgnn_check_launch("lstm_bwd_tile_kernel");
 }
 
@@ -576,11 +580,11 @@ int lstm_reg_fwd(float* G, const float* wp, float* OUT, float* CS, int n_seq, in
   return launch_fwd<1, 2, 0>(G, wp, OUT, CS, n_seq, T, H, sf, sr, drop, st);
 }
 
-int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, int n_seq, int T, int H, int sf, int sr,
-                 int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed, unsigned salt, const int* step_dev,
-                 cudaStream_t st) {
+int lstm_reg_bwd(float* G, const float* whh, const float* OUT, const float* CS, const float* dOUT, const float* dOUT_add, int n_seq, int T, int H,
+                 int sf, int sr, int zero_untaken, float* db_ih, float* db_hh, float p, unsigned long long seed, unsigned salt,
+                 const int* step_dev, cudaStream_t st) {
   const DropArgs drop = {nullptr, p, seed, salt, step_dev};
-#define SG_BWD_ARGS G, whh, OUT, CS, dOUT, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st
+#define SG_BWD_ARGS G, whh, OUT, CS, dOUT, dOUT_add, n_seq, T, H, sf, sr, zero_untaken, db_ih, db_hh, drop, st
   if (H == 128) return launch_bwd<2, 1, 128>(SG_BWD_ARGS);
   if (H == 64) return launch_bwd<1, 4, 64>(SG_BWD_ARGS);
   if (H == 32) return launch_bwd<1, 4, 32>(SG_BWD_ARGS);

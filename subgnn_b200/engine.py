@@ -256,6 +256,11 @@ class LstmRunner:
         # against 0.3148.
         self.bi_merge = _flag('SUBGNN_BI_MERGE', hp.get('b200_bi_merge', False))
         self.prep_beside = _flag('SUBGNN_LSTM_PREP_BESIDE', hp.get('b200_lstm_prep_beside', False))
+        # top layer with the 'last' aggregator: the input gradient of its reverse direction (last-step rows only) is STORED into a side
+        # buffer by the same grouped launch as the all-rows product and added by the next BPTT on load (subgnn_lstm_recur_bwd_add),
+        # instead of a second, dependent launch that read-add-stores onto the first one's rows
+        self.bi_side = _flag('SUBGNN_BI_SIDE', hp.get('b200_bi_side', True)) and bool(_abi.lib.subgnn_lstm_fused_dropout_supported(self.H))
+        self.dOUT_side = z(M, 2 * H) if (self.bi_side and self.nl > 1) else None      # only its rows t = T-1 are ever written / read
         self.X0 = z(M, self.D) if (self.ws and walks is not None) else None
         self.fwd_fn = 'subgnn_tc_linear_fwd' if self.use_tc else 'subgnn_linear_fwd'
         self.bwi_fn = 'subgnn_tc_linear_bwd_input' if self.use_tc else 'subgnn_linear_bwd_input'
@@ -291,10 +296,18 @@ class LstmRunner:
         ps = aux[0] if (gather and self.prep_beside) else cur
         if ps is not cur:
             ps.wait_stream(cur)
-        for k in range(self.nl):
-            o = a.lstm_off[k]
-            call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
-                 ptr(self.whh_t[k]), ptr(self.bsum[k]), H, ps.cuda_stream)
+        if self.nl > 1 and self.nl <= 8:            # every layer's packing in one launch
+            if getattr(self, '_prep_tabs', None) is None:
+                tab = lambda f: (C.c_ulonglong * self.nl)(*[int(f(k)) for k in range(self.nl)])
+                self._prep_tabs = (tab(lambda k: a.base_addr(a.lstm_off[k]['weight_hh'])), tab(lambda k: a.base_addr(a.lstm_off[k]['bias_ih'])),
+                                   tab(lambda k: a.base_addr(a.lstm_off[k]['bias_hh'])), tab(lambda k: self.whh_t[k].data_ptr()),
+                                   tab(lambda k: self.bsum[k].data_ptr()))
+            call('subgnn_lstm_prep_layers', *self._prep_tabs, self.nl, H, ps.cuda_stream)
+        else:
+            for k in range(self.nl):
+                o = a.lstm_off[k]
+                call('subgnn_lstm_prep', a.base_addr(o['weight_hh']), a.base_addr(o['bias_ih']), a.base_addr(o['bias_hh']),
+                     ptr(self.whh_t[k]), ptr(self.bsum[k]), H, ps.cuda_stream)
         if gather:
             call('subgnn_gather_rows', E_ptr, ptr(self.ids_flat), ptr(self.X0), M, D, st)     # anchor_patch_samplers.py:409, once per step
         if ps is not cur:
@@ -382,6 +395,7 @@ class LstmRunner:
                  None, self.n_groups, D, 2 * H, None, aux[1].cuda_stream)
         call('subgnn_lstm_head_bwd', ptr(self.dEMB), a.addr('lstm.linear.weight'), ptr(self.dOUT[-1]), a.addr('lstm.linear.bias', g),
              self.n_groups, self.W, T, 2 * H, D, 2 if self.last_only else self.sum_mode, st)
+        side_for = -1                                # layer whose BPTT adds the side buffer
         for k in range(self.nl - 1, -1, -1):
             o = a.lstm_off[k]
             sf, sr = self.steps(k)
@@ -389,7 +403,12 @@ class LstmRunner:
             # the bias gradients (d b_ih == d b_hh == column sums of dG) are accumulated inside the recurrence kernel
             fused = self.fused_drop and self.p_drop > 0 and training
             flags = (1 if full else 0) | (2 if (self.last_only and k == self.nl - 1) else 0)
-            if fused and k + 1 < self.nl:            # dOUT[k] is the gradient w.r.t. X[k+1] = dropout(OUT[k]): mask applied on load
+            if side_for == k:                        # two gradient sources: dOUT[k] + the side buffer's rows t = T-1 (written by layer k+1)
+                masked = fused and k + 1 < self.nl
+                call('subgnn_lstm_recur_bwd_add', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]),
+                     ptr(self.dOUT[k]), ptr(self.dOUT_side), self.n_seq, T, H, sf, sr, flags, a.base_addr(o['bias_ih'], g),
+                     a.base_addr(o['bias_hh'], g), self.p_drop if masked else 0.0, seed, 8 + k + 1, step_dev if masked else None, st)
+            elif fused and k + 1 < self.nl:          # dOUT[k] is the gradient w.r.t. X[k+1] = dropout(OUT[k]): mask applied on load
                 call('subgnn_lstm_recur_bwd_drop', ptr(self.G[k]), a.base_addr(o['weight_hh']), ptr(self.OUT[k]), ptr(self.CS[k]),
                      ptr(self.dOUT[k]), self.n_seq, T, H, sf, sr, flags, a.base_addr(o['bias_ih'], g),
                      a.base_addr(o['bias_hh'], g), self.p_drop, seed, 8 + k + 1, step_dev, st)
@@ -402,7 +421,10 @@ class LstmRunner:
             n_out = 8 * H if full else 4 * H                      # gate columns that carry gradient on every row
             dG_last = dG + 4 * (((T - 1) * 2 + 1) * 4 * H)         # reverse-direction gates of the rows t = T-1
             if self.ws and ids is None:
-                self._backward_gemms_ws(k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux)
+                side = None
+                if self.dOUT_side is not None and k > 0 and not full and not (self.p_drop > 0 and training and not fused):
+                    side, side_for = ptr(self.dOUT_side), k - 1
+                self._backward_gemms_ws(k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux, side)
                 if k > 0 and self.p_drop > 0 and training and not fused:
                     call('subgnn_dropout', ptr(self.dOUT[k - 1]), ptr(self.dOUT[k - 1]), M * 2 * H, self.p_drop, seed, 8 + k, step_dev, st)
                 continue
@@ -445,7 +467,7 @@ class LstmRunner:
             cur.wait_stream(a_)
 
 
-    def _backward_gemms_ws(self, k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux):
+    def _backward_gemms_ws(self, k, dG, dG_last, x_ptr, ldx, din, full, n_out, dE_ptr, dense, dense_dx, st, cur, aux, side=None):
         """the consumers of layer k's gate gradients on the TMA-fed grouped kernel (tcgemm_ws.cu): input gradient (the chain) and the
         three weight gradients.  grouped == 2: ONE launch per layer; grouped == 1: one launch for the LAST processed layer (nothing
         of the chain follows it: the tail of the backward pass), otherwise the input gradient on the chain stream and the weight
@@ -478,6 +500,9 @@ class LstmRunner:
                 if scat:
                     bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr, lddx, self.n_seq, 4 * H, din,
                                  scatter_ids=ptr(self.ids_last), accumulate=1))
+                elif side is not None and k > 0:   # stored into the side buffer (rows t = T-1) by the same launch; the next BPTT adds it
+                    bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, side + 4 * ((T - 1) * lddx), T * lddx, self.n_seq,
+                                 4 * H, din))
                 elif self.bi_merge and k > 0 and k == self.nl - 1:   # both products add with atomics onto the zero-filled dOUT[k-1] (backward()): ONE launch on the chain
                     bi[0] = gd(_abi.GEMM_BWD_INPUT, dG, 8 * H, w_ih, din, dx_ptr, lddx, M, n_out, din, accumulate=2)
                     bi.append(gd(_abi.GEMM_BWD_INPUT, dG_last, T * 8 * H, w_rev, din, dx_ptr + 4 * ((T - 1) * lddx), T * lddx, self.n_seq,
