@@ -278,6 +278,8 @@ typedef struct subgnn_model_desc {
   float lin_dropout;
   int mlp_fused;             /* subgnn_model_readout also accumulates the MLP weight / bias gradients (from its own d logits): the fused
                                 training step; subgnn_model_wgrad then skips them */
+  int wgrad_rows;            /* rows of the batch per CTA of the N-channel weight-gradient launch (0: one chunk of up to 512 rows: few CTAs,
+                                out of the way of a long BPTT chain; 64: many CTAs, when that launch itself ends the backward pass) */
 } subgnn_model_desc;
 
 /* batch bookkeeping + per-step weight transposes + q = w_p . x_anchor for every shared anchor list */

@@ -1422,7 +1422,17 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
   if (rc) return rc;
   const int D = d->D;
   if (d->use_n && d->use_proj && d->mpn_grads[0]) {
-    int splits = sg_div_up(d->R_cap, 512);
+    // rows per CTA.  [r2] measured (B200, same box, 100 steps): chunks of 512 rows leave the launch at 16 CTAs for 32 - 42 us; where it
+    // hides behind a two-layer BPTT chain that is the better shape (PPI-BP 0.3052 ms/step against 0.3065 with 64-row chunks,
+    // HPO-METAB 0.5854 / 0.5893), where it ends the backward pass (one-layer walk encoder) many CTAs win (EM-USER 0.5611 -> 0.5345,
+    // density 0.147 -> 0.142): the caller says which (desc.wgrad_rows)
+    int m_rows = 512;
+    if (d->wgrad_rows >= 16) {
+      m_rows = sg_div_up(sg_div_up(d->R_cap, 16), 16) * 16;                  // at most 16 chunks
+      if (m_rows < d->wgrad_rows) m_rows = d->wgrad_rows;
+    }
+    if (const char* e = getenv("SUBGNN_NWGRAD_ROWS")) { const int v = atoi(e); if (v >= 16) m_rows = v; }
+    int splits = sg_div_up(d->R_cap, m_rows);
     const int m_chunk = sg_div_up(sg_div_up(d->R_cap, splits), 16) * 16;
     splits = sg_div_up(d->R_cap, m_chunk);
     dim3 grid(sg_div_up(2 * D, 64), sg_div_up(D, 64), d->L * 2 * splits);

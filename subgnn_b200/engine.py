@@ -694,6 +694,9 @@ class StepContext:
         d.Z, d.H1, d.H2, d.logits, d.loss_b = ptr(self.Z), ptr(self.H1), ptr(self.H2), ptr(self.logits), ptr(self.loss_b)
         d.loss_sum = self.loss.data_ptr()
         d.mlp_fused = 0
+        # N-channel weight gradients: many small CTAs when the launch ends the backward pass (one-layer walk encoder), one 512-row
+        # chunk per product when it hides behind a longer BPTT chain (model.cu: subgnn_model_wgrad)
+        d.wgrad_rows = 64 if (eng.lstm is None or eng.lstm.nl == 1) else 0
         d.dlogits, d.dH2, d.dH1, d.dZ = ptr(self.dlogits), ptr(self.dH2), ptr(self.dH1), ptr(self.dZ)
         d.seed = eng.seed
         d.n_sub, d.n_cc, d.n_nodes = t.n_sub, t.n_cc, eng.n_nodes
