@@ -1212,6 +1212,69 @@ __global__ void __launch_bounds__(256) n_wgrad_kernel(Desc d, int splits, int m_
   }
 }
 
+// weight / bias gradients of the three MLP layers in ONE launch [r2]: dW_i[n][k] += sum_b dY_i[b][n] X_i[b][k], db_i[n] += sum_b dY_i[b][n]
+// with (dY, X) = (dH1, Z), (dH2, H1), (d logits, H2) — SubGNN.py:303-310 backward.  One CTA per 64 x 64 tile of one dW (a single
+// writer per element: no atomics); thread (tn, tk) owns a 4 x 4 block, the batch is walked in chunks of 32 samples staged in shared
+// memory.  Three generic split-reduction launches took 28 us for these ~4 MFLOP at the reference batch sizes (7 - 11 us of fixed
+// latency each); on a one-layer walk encoder they end the backward pass.
+#define MW_BT 32
+__global__ void __launch_bounds__(256) mlp_wgrad_kernel(Desc d, int tiles0, int tiles1) {
+  sg_pdl_sync();
+  __shared__ float ys[MW_BT][64 + 4];
+  __shared__ float xs[MW_BT][64 + 4];
+  int t = blockIdx.x, li = 0;
+  if (t >= tiles0) { t -= tiles0; li = 1; }
+  if (li == 1 && t >= tiles1) { t -= tiles1; li = 2; }
+  const float* dy = li == 0 ? d.dH1 : li == 1 ? d.dH2 : d.dlogits;
+  const float* x = li == 0 ? d.Z : li == 1 ? d.H1 : d.H2;
+  const int N = li == 0 ? d.h1 : li == 1 ? d.h2 : d.n_classes;
+  const int K = li == 0 ? d.hid : li == 1 ? d.h1 : d.h2;
+  float* gw = d.lin_gw[li];
+  float* gb = d.lin_gb[li];
+  const int tiles_k = (K + 63) / 64;
+  const int n0 = (t / tiles_k) * 64, k0 = (t % tiles_k) * 64;
+  const int tn = threadIdx.x / 16, tk = threadIdx.x % 16;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+  float bsum = 0.f;                                       // threads 0 .. 63 of the k0 == 0 tiles: column sums of dY
+  for (int b0 = 0; b0 < d.B; b0 += MW_BT) {
+    const int bn = min(MW_BT, d.B - b0);
+    __syncthreads();
+    for (int e = threadIdx.x; e < MW_BT * 64; e += 256) {
+      const int b = e / 64, c = e % 64;
+      ys[b][c] = (b < bn && n0 + c < N) ? dy[(size_t)(b0 + b) * N + n0 + c] : 0.f;
+      xs[b][c] = (b < bn && k0 + c < K) ? x[(size_t)(b0 + b) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll 8
+    for (int b = 0; b < MW_BT; ++b) {
+      const float4 yv = *reinterpret_cast<const float4*>(&ys[b][4 * tn]);
+      const float4 xv = *reinterpret_cast<const float4*>(&xs[b][4 * tk]);
+      const float ya[4] = {yv.x, yv.y, yv.z, yv.w}, xa[4] = {xv.x, xv.y, xv.z, xv.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(ya[i], xa[j], acc[i][j]);
+    }
+    if (k0 == 0 && threadIdx.x < 64)
+      for (int b = 0; b < bn; ++b) bsum += ys[b][threadIdx.x];
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int n = n0 + 4 * tn + i;
+    if (n >= N) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int k = k0 + 4 * tk + j;
+      if (k < K) gw[(size_t)n * K + k] += acc[i][j];
+    }
+  }
+  if (k0 == 0 && threadIdx.x < 64 && n0 + threadIdx.x < N && gb) gb[n0 + threadIdx.x] += bsum;
+}
+
 // ------------------------------------------------------------------------------------------------
 static size_t bwd_smem(const Desc& d) { return (size_t)(d.D + 2 * d.D + 4 * d.D + d.L * 4 + 16) * sizeof(float); }
 static int check_desc(const Desc* d) {
@@ -1225,6 +1288,7 @@ static int check_desc(const Desc* d) {
   return SUBGNN_OK;
 }
 
+static int mlp_wgrad_split(const subgnn_model_desc* d, void* stream);
 static int row_grid(const Desc* d);
 // 16 warps per row while the row capacity (B x most components of a subgraph: an upper bound of the rows) stays within the grid cap, else 8 (see ROW_WIDE)
 static int row_width(const Desc* d) {
@@ -1440,7 +1504,9 @@ int subgnn_model_wgrad(const subgnn_model_desc* d, void* stream) {
     rc = subgnn_check_launch("n_wgrad_kernel");
     if (rc) return rc;
   }
-  if (d->lin_gw[0] && !d->mlp_fused) return subgnn_model_mlp_wgrad(d, stream);
+  // at the END of the main stream (behind a two-layer BPTT chain) the three split-reduction launches stay: measured PPI-BP 0.3071
+  // ms/step against 0.3117 with the one-launch kernel below (which wins where these gradients end the step: density 0.1427 -> 0.130)
+  if (d->lin_gw[0] && !d->mlp_fused) return mlp_wgrad_split(d, stream);
   return SUBGNN_OK;
 }
 
@@ -1451,7 +1517,21 @@ int subgnn_model_mlp_wgrad(const subgnn_model_desc* d, void* stream) {
   int rc = check_desc(d);
   if (rc) return rc;
   if (!d->lin_gw[0]) return SUBGNN_OK;
-  // dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples)
+  static const bool one_launch = !(getenv("SUBGNN_MLP_WGRAD_SPLIT") && atoi(getenv("SUBGNN_MLP_WGRAD_SPLIT")) == 1);
+  if (one_launch && d->lin_gw[1] && d->lin_gw[2]) {
+    const int t0 = sg_div_up(d->h1, 64) * sg_div_up(d->hid, 64), t1 = sg_div_up(d->h2, 64) * sg_div_up(d->h1, 64);
+    const int t2 = sg_div_up(d->n_classes, 64) * sg_div_up(d->h2, 64);
+    sg_launch_pdl(mlp_wgrad_kernel, dim3(t0 + t1 + t2), dim3(256), 0, (cudaStream_t)stream, *d, t0, t1);
+    return subgnn_check_launch("mlp_wgrad_kernel");
+  }
+  return mlp_wgrad_split(d, stream);
+}
+
+}  // extern "C"
+
+// dW1 = dH1^T Z, dW2 = dH2^T H1, dW3 = dlogits^T H2 (reduction over the B samples) as three split-reduction launches
+static int mlp_wgrad_split(const subgnn_model_desc* d, void* stream) {
+  int rc;
   rc = subgnn_linear_bwd_weight(d->dH1, d->h1, d->Z, d->hid, nullptr, d->lin_gw[0], d->hid, d->lin_gb[0], d->B, d->h1, d->hid, nullptr, stream);
   if (rc) return rc;
   rc = subgnn_linear_bwd_weight(d->dH2, d->h2, d->H1, d->h1, nullptr, d->lin_gw[1], d->h1, d->lin_gb[1], d->B, d->h2, d->h1, nullptr, stream);
@@ -1459,5 +1539,3 @@ int subgnn_model_mlp_wgrad(const subgnn_model_desc* d, void* stream) {
   return subgnn_linear_bwd_weight(d->dlogits, d->n_classes, d->H2, d->h2, nullptr, d->lin_gw[2], d->h2, d->lin_gb[2], d->B, d->n_classes, d->h2,
                                   nullptr, stream);
 }
-
-}  // extern "C"
