@@ -173,3 +173,28 @@ def test_property_dataset_generator_follows_the_reference_recipe(kind):
     # deterministic in the seed
     e2, s2, l2, v2 = synth.generate_property_dataset(kind, n=n, m=5, n_subgraphs=n_sub, n_subgraph_nodes=k, seed=42)
     assert np.array_equal(edges, e2) and s2 == subs and np.array_equal(values, v2)
+
+
+def test_traffic_table_is_stamped_per_source_file(monkeypatch):
+    """bench.roofline.traffic comes from a committed ncu capture: the table carries the digest of every CUDA source it was captured
+    on, is accepted for an entry point whose defining files are unchanged and refused (traffic = null) once one of them differs."""
+    import json
+    import sys
+    sys.path.insert(0, str(ROOT))
+    import bench
+    table = ROOT / 'profiles' / 'r02_traffic_ppi_bp.json'
+    if not table.exists():
+        pytest.skip('no committed traffic table')
+    tab = json.loads(table.read_text())
+    assert set(tab['csrc_files']) >= {'tcgemm_ws.cu', 'common.cuh', 'model.cu'}
+    now = bench.csrc_file_digests()
+    entry = 'subgnn_tc_gemm_group'
+    fresh = all(tab['csrc_files'].get(f) == now.get(f) for f in bench.ENTRY_SOURCES[entry] + ['common.cuh'])
+    got, src = bench.ncu_traffic('ppi_bp', entry)
+    assert (got is not None) == fresh
+    if fresh:
+        assert got > 0 and 'r02_traffic_ppi_bp.json' in src
+    stale = dict(now, **{'tcgemm_ws.cu': '0' * 16})
+    monkeypatch.setattr(bench, 'csrc_file_digests', lambda: stale)
+    assert bench.ncu_traffic('ppi_bp', entry) == (None, None)                       # the kernel's source changed: refused
+    assert bench.ncu_traffic('ppi_bp', 'subgnn_adam_step')[0] is not None or tab['csrc_files'].get('optim.cu') != now.get('optim.cu')
