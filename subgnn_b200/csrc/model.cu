@@ -1064,7 +1064,7 @@ __global__ void __launch_bounds__(RT) row_bwd_kernel(Desc d, int phases) {
           const float* gp = dpre + side * D;
           for (int kk = st; kk < 2 * D; kk += SIDE_THREADS) {
             float acc = 0.f;
-#pragma unroll 4
+#pragma unroll 16                            // 16 weight loads in flight per thread (ncu source page: at 4, 18 % of the kernel's stall samples sat on this FMA)
             for (int j = 0; j < D; ++j) acc = fmaf(gp[j], __ldg(w + (size_t)j * 2 * D + kk), acc);
             din[side * 2 * D + kk] = acc;
           }
